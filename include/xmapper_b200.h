@@ -1,0 +1,155 @@
+/* xmapper_b200 — C ABI of the B200-native X-Mapper aligner stage.
+ *
+ * Drop-in boundary: replaces the body of mapper.AlignerWorker.process()/align() in mathjeff/Mapper @ ae7f346a
+ * (src/main/java/mapper/AlignerWorker.java:157-261; constructor state :22-33) — a batch of queries in, the
+ * List<QueryAlignments> the AlignmentListeners receive (:652-656) out.  Everything left of the boundary
+ * (FASTA/FASTQ parsing, options, SAM/VCF/mutations writers) stays the reference's Java host; the binding a
+ * maintainer adds (Panama FFM / JNI) is shown in INTEGRATION.md.
+ *
+ * All pointers are HOST memory unless stated.  Every call returns 0 on success and a negative xm_status on
+ * failure; xm_last_error(handle) returns the message (the host throws RuntimeException, matching
+ * AlignerWorker.java:195-197).  There is no CPU fallback: without a CUDA device xm_create fails.
+ *
+ * Sequence layout (QV/SequenceBuilder.java:20-38, QV/Sequence.java:52-74): 4-bit IUPAC set codes
+ * (A=1 C=2 G=4 T=8, N=15, QV/Basepairs.java), base i of a sequence at bits 4*(i&3) of 16-bit word i>>2.
+ */
+#ifndef XMAPPER_B200_H
+#define XMAPPER_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct xm_handle xm_handle;
+typedef struct xm_results xm_results;
+
+enum xm_status {
+  XM_OK = 0,
+  XM_ERR_ARG = -1,          /* bad argument */
+  XM_ERR_CUDA = -2,         /* no device / CUDA failure */
+  XM_ERR_STATE = -3,        /* call order (reference or index missing) */
+  XM_ERR_QUERY = -4         /* at least one query could not be aligned on the device; see xm_results q_status */
+};
+
+/* per-query status in xm_results (q_status) */
+enum xm_query_status {
+  XM_Q_OK = 0,
+  XM_Q_AMBIGUOUS_QUERY = -2,  /* query contains IUPAC-ambiguous bases next to a seed (MultiHashBlock path, HashBlock_ParentRow.java:97-120): not implemented on device */
+  XM_Q_INDEX_TOO_SHORT = -3,  /* a seed needs a table longer than the index was built for (Readable_HashBlock_Database.java:108-113) */
+  XM_Q_WORKSPACE = -5,        /* largest workspace tier exhausted */
+  XM_Q_INTERNAL = -6          /* the reference would have thrown (e.g. PathAligner.java:159 on an empty queue) */
+};
+
+/* AlignmentParameters (src/main/java/mapper/AlignmentParameters.java:6-37) + HashBlock_Database options */
+typedef struct xm_params {
+  double mutation_penalty;            /* MutationPenalty */
+  double insertion_start_penalty;     /* InsertionStart_Penalty */
+  double insertion_extension_penalty; /* InsertionExtension_Penalty */
+  double deletion_start_penalty;      /* DeletionStart_Penalty */
+  double deletion_extension_penalty;  /* DeletionExtension_Penalty */
+  double max_error_rate;              /* MaxErrorRate */
+  double unaligned_penalty;           /* UnalignedPenalty */
+  double ambiguity_penalty;           /* AmbiguityPenalty */
+  double max_penalty_span;            /* Max_PenaltySpan */
+  int32_t max_num_matches;            /* MaxNumMatches */
+  int32_t enable_gapmers;             /* HashBlock_Database enableGapmers (Mapper.java:51) */
+} xm_params;
+
+/* new AlignerWorker(referenceProvider, parameters, duplicationDetector, ...) — AlignerWorker.java:22-33.
+ * device: CUDA ordinal (one handle per GPU; one process per GPU in multi-GPU runs). */
+int xm_create(const xm_params* params, int device, xm_handle** out);
+void xm_destroy(xm_handle* h);
+const char* xm_last_error(const xm_handle* h);
+
+/* SequenceDatabase of the sorted reference (Mapper.sortAndComplementReference, Mapper.java:1151-1172; global
+ * position space QV/SequenceDatabase.java:230-238): forward strands only, in database order; the reverse
+ * complements are implicit (contig i occupies sequence ids 2i and 2i+1). */
+int xm_set_reference(xm_handle* h, int32_t n_contigs, const uint16_t* const* packed4, const int32_t* lengths);
+
+/* One PackedMap (PackedMap.java / QV/ByteKeyStore.java) per numBasepairsUsed, uploaded from the host's
+ * HashBlock_Database: bucket b holds positions[offsets[b] .. offsets[b+1]) ascending global positions;
+ * overfull[b] != 0 means "too many matches" (getNumMatchesLowerBound == Integer.MAX_VALUE).
+ * capacity == 1 with no positions is the empty PackedMap(1, 1, ...) of HashBlock_Database.java:383-389. */
+int xm_set_index_length(xm_handle* h, int32_t n_used, int32_t capacity, int32_t max_count, const int64_t* offsets,
+                        const uint8_t* overfull, const uint32_t* positions);
+/* Declares HashBlock_Database.minInterestingSize (:51-55) and maxFullySetUpSize after all uploads. */
+int xm_finish_index(xm_handle* h, int32_t min_interesting_size, int32_t max_built);
+
+/* Alternative to the two calls above: build every table for numBasepairsUsed <= max_used from the uploaded
+ * reference inside the library (HashBlock_Database.hashSequenceThroughSize/addHashblocks, :490-618).
+ * Unambiguous references only in this round (returns XM_ERR_ARG otherwise). */
+int xm_build_index(xm_handle* h, int32_t max_used, int32_t n_threads);
+/* Reads back a table (for parity tests against the host's PackedMaps). Pass NULL arrays to query sizes. */
+int xm_get_index_length(xm_handle* h, int32_t n_used, int32_t* capacity, int32_t* max_count, int64_t* n_positions,
+                        int64_t* offsets, uint8_t* overfull, uint32_t* positions);
+int xm_index_info(xm_handle* h, int32_t* min_interesting_size, int32_t* max_built);
+
+/* Readable_DuplicationDetector table (Readable_DuplicationDetector.java:28-47): the sorted duplication start
+ * keys of forward contig `contig`; window = DuplicationDetector.windowSize, granularity = getDetectionGranularity()
+ * (DuplicationDetector.java:67-77). */
+int xm_set_duplications(xm_handle* h, int32_t window, double granularity, int32_t contig, int32_t n, const int32_t* starts);
+/* Or build it inside the library from the index (DuplicationDetector.process, :129-214). */
+int xm_build_duplications(xm_handle* h, int32_t min_len, int32_t max_len, int32_t min_copies, int32_t window);
+int xm_get_duplications(xm_handle* h, int32_t contig, int32_t* n, int32_t* starts);
+
+/* AlignerWorker.process(): aligns n_queries queries. Query q owns n_seqs_per_query[q] (1 or 2) consecutive
+ * sequences; sequence s is seq_len[s] bases at packed4 + seq_word_off[s] (16-bit words). expected_inner /
+ * spacing_per_penalty are Query.expectedInnerDistance / spacingDeviationPerUnitPenalty (QV/Query.java:17-30),
+ * ignored for single-sequence queries. Blocking; one call at a time per handle. */
+int xm_align_batch(xm_handle* h, int32_t n_queries, const uint16_t* packed4, const int64_t* seq_word_off,
+                   const int32_t* seq_len, const uint8_t* n_seqs_per_query, const double* expected_inner,
+                   const double* spacing_per_penalty, xm_results** out);
+/* Same, with every array already resident on the device of this handle (device pointers). Used by the
+ * kernel-only timing leg of bench.py. */
+int xm_align_batch_device(xm_handle* h, int32_t n_queries, const uint16_t* d_packed4, int64_t n_words,
+                          const int64_t* d_seq_word_off, const int32_t* d_seq_len, const uint8_t* d_n_seqs_per_query,
+                          const double* d_expected_inner, const double* d_spacing_per_penalty, int32_t max_seq_len,
+                          xm_results** out);
+
+/* Result = List<QueryAlignments> (QV/QueryAlignments.java:34-37) flattened CSR-style:
+ *   query q           -> components  q_comp_off[q] .. q_comp_off[q+1]      (1, or 2 for unpaired mates)
+ *   component c       -> choices     comp_choice_off[c] .. [c+1]           (QueryAlignment, QV/QueryAlignment.java:16-23)
+ *   choice k          -> choice_f64[4k..] = spacingPenalty, overlapMultiplier, duplicationBonus, totalPenalty;
+ *                        choice_inner[k] = totalDistanceBetweenComponents;
+ *                        sequence alignments choice_sa_off[k] .. [k+1]
+ *   seq alignment a   -> sa_contig[a] (forward contig index), sa_reversed[a] (referenceReversed),
+ *                        sa_f64[2a..] = penalty, alignedPenalty (QV/SequenceAlignment.java:18-24);
+ *                        blocks sa_block_off[a] .. [a+1]
+ *   block b           -> blocks[4b..] = aStart, bStart, aLen, bLen (QV/AlignedBlock.java:6-19)
+ */
+enum xm_array {
+  XM_Q_COMP_OFF = 0, XM_COMP_CHOICE_OFF = 1, XM_CHOICE_SA_OFF = 2, XM_SA_BLOCK_OFF = 3, /* int64 */
+  XM_CHOICE_F64 = 4, XM_SA_F64 = 5,                                                     /* double */
+  XM_CHOICE_INNER = 6, XM_SA_CONTIG = 7, XM_BLOCKS = 8, XM_Q_STATUS = 9,                /* int32 */
+  XM_SA_REVERSED = 10,                                                                  /* uint8 */
+  XM_STATS = 11                                                                         /* int64: see xm_stat */
+};
+enum xm_stat {
+  XM_STAT_KERNEL_NS = 0,        /* device time of all kernels of this batch (CUDA events) */
+  XM_STAT_LAUNCHES = 1,         /* kernel launches */
+  XM_STAT_TIER0_QUERIES = 2, XM_STAT_TIER1_QUERIES = 3, XM_STAT_TIER2_QUERIES = 4,
+  XM_STAT_PROBES = 5,           /* bucket-count probes (HashBlockPath.java:143-223) */
+  XM_STAT_SEEDS = 6,            /* emitted seeds */
+  XM_STAT_HITS = 7,             /* verified + rejected hits (Counting_HashBlockPath.java:93-153) */
+  XM_STAT_STRAIGHT = 8,         /* StraightAligner calls */
+  XM_STAT_PATH_CALLS = 9, XM_STAT_PATH_STEPS = 10, XM_STAT_PATH_CELLS = 11,
+  XM_STAT_H2D_BYTES = 12, XM_STAT_D2H_BYTES = 13,
+  XM_STAT_ALIGN_KERNEL_NS = 14, /* device time of the dominant kernel (xm_align_kernel, tier 0) */
+  XM_STAT_COUNT = 16
+};
+int64_t xm_results_array(const xm_results* r, int which, const void** ptr);
+void xm_release_results(xm_results* r);
+
+/* Per-position count planes for --out-vcf/--out-mutations (QV/MatchDatabase.java:16-59, QV/Alignments.java:89-150,
+ * QV/DirectionalAlignments.java:20-55): reference-base depth in int32 units of 1/100 per
+ * [region: 0 middle, 1 end][direction: 0 forward, 1 reverse][position].  xm_counts_enable allocates the planes on
+ * the device; every later xm_align_batch accumulates into them; xm_counts_device_ptr exposes the device buffer so
+ * the multi-GPU driver can all-reduce it in place with NCCL (int32 sum, exact and order-free). */
+int xm_counts_enable(xm_handle* h, double query_end_fraction);
+int xm_counts_device_ptr(xm_handle* h, void** d_ptr, int64_t* n_int32);
+int xm_counts_fetch(xm_handle* h, int32_t contig, int32_t* out /* 4 * contig length */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

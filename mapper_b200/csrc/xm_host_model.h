@@ -1,0 +1,305 @@
+// xmapper_b200 — host-side model behind the C ABI: reference, per-length bucket tables in the device layout,
+// duplication table; plus the library's own index builder and duplication detector (reference-time
+// preprocessing, multi-threaded C++; the device-side builder is a later row of SURVEY.md §8f).
+// No CUDA in this header: xm_capi.cu mirrors these arrays to the GPU.
+//
+// Index builder follows M/HashBlock_Database.java:490-665 (which blocks exist, gapmer extension, per-length
+// capacity estimate, per-bucket cap, polarity), M/PackedMap.java:99-153 and QV/ByteKeyStore.java (sorted bucket,
+// overfull bucket dropped).  Duplication detector follows M/DuplicationDetector.java:129-436.
+#pragma once
+#include "xm_seed.h"
+#include <vector>
+#include <string>
+#include <map>
+#include <set>
+#include <thread>
+#include <atomic>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace xm {
+
+struct HostTable {
+  int capacity = 1, max_count = 1;
+  std::vector<uint64_t> buckets;   // empty => PackedMap(1,1)
+  std::vector<uint32_t> positions;
+};
+
+struct HostModel {
+  Params prm{};
+  int gapmers = 1;
+  // reference
+  int n_contigs = 0;
+  std::vector<uint16_t> words;
+  std::vector<int64_t> word_off;
+  std::vector<int32_t> len;
+  std::vector<int64_t> gstart;
+  int64_t total_forward = 0, total_fr = 0;
+  bool ref_ambiguous = false;
+  // index
+  std::vector<HostTable> tables;
+  int min_interesting = 1, max_built = 0;
+  bool index_finished = false;
+  // duplications
+  int dup_window = 1; double dup_granularity = 1;
+  std::vector<std::vector<int32_t>> dup_starts;
+  bool dup_set = false;
+  uint64_t generation = 0;  // bumped on every change so the device mirror knows to refresh
+
+  SeqView contig_view(int c, int rc) const { SeqView v; v.w = words.data() + word_off[c]; v.len = len[c]; v.rc = rc; return v; }
+
+  void set_reference(int n, const uint16_t* const* packed4, const int32_t* lengths) {
+    n_contigs = n; words.clear(); word_off.assign(n, 0); len.assign(lengths, lengths + n); gstart.assign(2 * (size_t)n + 1, 0);
+    total_forward = 0; ref_ambiguous = false;
+    for (int c = 0; c < n; c++) {
+      size_t w0 = (words.size() + 7) & ~(size_t)7;  // 16-byte aligned contig starts
+      words.resize(w0, 0);
+      word_off[c] = (int64_t)w0;
+      size_t nw = ((size_t)lengths[c] + 3) / 4;
+      words.insert(words.end(), packed4[c], packed4[c] + nw);
+      total_forward += lengths[c];
+    }
+    words.resize((words.size() + 15) & ~(size_t)7, 0);
+    int64_t g = 0;
+    for (int c = 0; c < n; c++) { gstart[2 * c] = g; g += lengths[c]; gstart[2 * c + 1] = g; g += lengths[c]; }
+    gstart[2 * (size_t)n] = g; total_fr = g;
+    for (int c = 0; c < n && !ref_ambiguous; c++) { SeqView v = contig_view(c, 0); for (int i = 0; i < v.len; i++) if (bp_is_ambiguous(v.at(i))) { ref_ambiguous = true; break; } }
+    tables.clear(); max_built = 0; index_finished = false; dup_starts.assign(n, {}); dup_set = false;
+    generation++;
+  }
+
+  static uint64_t bucket_word(int64_t start, bool overfull, int count) { return ((uint64_t)start << 24) | ((uint64_t)(overfull ? 1 : 0) << 16) | (uint64_t)(count & 0xFFFF); }
+
+  void set_index_length(int n_used, int capacity, int max_count, const int64_t* offsets, const uint8_t* overfull, const uint32_t* positions) {
+    if ((int)tables.size() <= n_used) tables.resize((size_t)n_used + 1);
+    HostTable& T = tables[(size_t)n_used];
+    T.capacity = capacity < 1 ? 1 : capacity; T.max_count = max_count;
+    T.buckets.clear(); T.positions.clear();
+    int64_t total = offsets ? offsets[capacity] : 0;
+    if (offsets) {
+      T.buckets.resize((size_t)T.capacity);
+      for (int b = 0; b < capacity; b++) T.buckets[(size_t)b] = bucket_word(offsets[b], overfull && overfull[b], (int)(offsets[b + 1] - offsets[b]));
+      T.positions.assign(positions, positions + total);
+    }
+    generation++;
+  }
+  void finish_index(int min_int, int built) {
+    min_interesting = min_int; max_built = built;
+    if ((int)tables.size() <= built) tables.resize((size_t)built + 1);
+    index_finished = true; generation++;
+  }
+
+  // ---- the library's own index builder ----
+  static int log2_round_up(long long value) { int nb = 1; long long e = 2; while (true) { if (e >= value) return nb; nb++; e *= 2; } }
+  int choose_min_dup_len() const { return log2_round_up(total_forward); }
+  int estimate_capacity(int n) const {  // HashBlock_Database.estimateRequiredCapacity :620-665
+    int anchor = gapmers ? n * 2 / 3 : n;
+    double size_p = std::min(1.0, 2.0 / anchor), off_p = std::min(1.0, 2.0 / anchor);
+    double poss = size_p * off_p;
+    long long max_seqs = (n <= 16) ? (1LL << (n * 2)) : (1LL << 32);
+    long long max_stored = max_seqs / 2;
+    double mh = (double)max_stored * poss;
+    long long max_hashcodes = mh >= 9.2233720368547758e18 ? INT64_MAX : (long long)mh;
+    long long num_blocks = (long long)((double)total_forward * poss);
+    double existence = 1 - std::pow((double)((double)max_hashcodes - 1.0) / (double)max_hashcodes, (double)num_blocks);
+    int unique = j2i((double)max_hashcodes * existence);
+    if (unique % 2 == 0) unique++;
+    return unique;
+  }
+  static int max_count_for(int n, int max_short) { int m = n * n; if (m < max_short) m = max_short; if (m > 32766) m = 32766; if (m < 1) m = 1; return m; }
+
+  struct Entry { uint32_t bucket, pos; };
+
+  bool build_index(int max_used, int n_threads, std::string& err) {
+    if (ref_ambiguous) { err = "xm_build_index: reference contains IUPAC-ambiguous bases (MultiHashBlock expansion is host-side in this round; upload the tables with xm_set_index_length)"; return false; }
+    min_interesting = j2i(std::max((std::log((double)(total_forward + 1)) / std::log(4.0)) - 2, 1.0));  // :51-55
+    int hi = std::max(max_used, 2 * choose_min_dup_len());
+    std::vector<int> cap((size_t)hi + 1, 1);
+    for (int n = 1; n <= hi; n++) { int c = estimate_capacity(n); cap[(size_t)n] = c < 1 ? 1 : c; }
+    struct Slice { int contig, s, e; };
+    std::vector<Slice> slices;
+    const int slice_len = 65536;
+    for (int c = 0; c < n_contigs; c++) for (int s = 0; s < len[c]; s += slice_len) slices.push_back({c, s, std::min(len[c], s + slice_len)});
+    int nt = std::max(1, n_threads);
+    std::vector<std::vector<std::vector<Entry>>> parts((size_t)nt);
+    for (auto& p : parts) p.resize((size_t)hi + 1);
+    std::atomic<size_t> next(0);
+    auto work = [&](int t) {
+      std::vector<HB> cur, nxt;
+      while (true) {
+        size_t si = next.fetch_add(1);
+        if (si >= slices.size()) break;
+        const Slice& sl = slices[si];
+        SeqView seq = contig_view(sl.contig, 0);
+        int ext_end = std::min(seq.len, sl.e + hi + 2);
+        cur.clear();
+        for (int i = sl.s; i < ext_end; i++) cur.push_back(base_block(seq.at(i), i));
+        int level = 0;
+        while (!cur.empty()) {
+          bool any_short = false;
+          for (const HB& b : cur) {
+            if (b.start >= sl.e) break;
+            if (b.len <= hi) any_short = true;
+            HB g;
+            if (gapmers) { if (!with_gap_and_extension(b, seq, g)) continue; } else g = b;
+            int n = g.used;
+            if (n < min_interesting || n > hi) continue;
+            int c = cap[(size_t)n];
+            bool rml = g.rml(), rmr = g.rmr();
+            bool primary = (rml != rmr) ? rml : (g.fwd >= g.rev);
+            bool secondary = (rml != rmr) ? rmr : (g.fwd <= g.rev);  // HashBlock.isSecondaryPolarity :339-343
+            if (primary) { int r = g.fwd % c; if (r < 0) r += c; parts[(size_t)t][(size_t)n].push_back({(uint32_t)r, (uint32_t)(gstart[2 * sl.contig] + g.start)}); }
+            if (secondary) { int r = g.rev % c; if (r < 0) r += c; parts[(size_t)t][(size_t)n].push_back({(uint32_t)r, (uint32_t)(gstart[2 * sl.contig + 1] + (seq.len - g.end()))}); }
+          }
+          if (!any_short) break;
+          level++;
+          nxt.clear();
+          for (size_t i = 0; i + 1 < cur.size(); i++) {
+            const HB& L = cur[i]; const HB& R = cur[i + 1];
+            if (L.end() >= R.start && (L.rmr() || R.rml())) nxt.push_back(merge_blocks(L, R, level));
+          }
+          cur.swap(nxt);
+        }
+      }
+    };
+    if (nt == 1) work(0);
+    else { std::vector<std::thread> th; for (int t = 0; t < nt; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
+    tables.assign((size_t)hi + 1, HostTable());
+    std::atomic<int> nn(1);
+    auto fin = [&]() {
+      while (true) {
+        int n = nn.fetch_add(1);
+        if (n > hi) break;
+        size_t total = 0;
+        for (int t = 0; t < nt; t++) total += parts[(size_t)t][(size_t)n].size();
+        HostTable& T = tables[(size_t)n];
+        if (total == 0) { T.capacity = 1; T.max_count = 1; continue; }
+        T.capacity = cap[(size_t)n]; T.max_count = max_count_for(n, 5);
+        std::vector<Entry> all; all.reserve(total);
+        for (int t = 0; t < nt; t++) { auto& v = parts[(size_t)t][(size_t)n]; all.insert(all.end(), v.begin(), v.end()); std::vector<Entry>().swap(v); }
+        std::sort(all.begin(), all.end(), [](const Entry& a, const Entry& b) { return a.bucket != b.bucket ? a.bucket < b.bucket : a.pos < b.pos; });
+        T.buckets.assign((size_t)T.capacity, 0);
+        size_t i = 0; int64_t off = 0;
+        for (int b = 0; b < T.capacity; b++) {
+          size_t j = i;
+          while (j < all.size() && all[j].bucket == (uint32_t)b) j++;
+          int64_t cnt = (int64_t)(j - i);
+          if (cnt > T.max_count) T.buckets[(size_t)b] = bucket_word(off, true, 0);
+          else { T.buckets[(size_t)b] = bucket_word(off, false, (int)cnt); for (size_t k = i; k < j; k++) T.positions.push_back(all[k].pos); off += cnt; }
+          i = j;
+        }
+      }
+    };
+    if (nt == 1) fin();
+    else { std::vector<std::thread> th; for (int t = 0; t < nt; t++) th.emplace_back(fin); for (auto& x : th) x.join(); }
+    max_built = hi; index_finished = true; generation++;
+    return true;
+  }
+
+  // reads a table back in the xm_set_index_length layout
+  void get_index_length(int n, int& capacity, int& max_count, int64_t& n_pos, int64_t* offsets, uint8_t* overfull, uint32_t* positions) const {
+    const HostTable& T = tables[(size_t)n];
+    capacity = T.capacity; max_count = T.max_count; n_pos = (int64_t)T.positions.size();
+    if (offsets) {
+      if (T.buckets.empty()) { for (int b = 0; b <= T.capacity; b++) offsets[b] = 0; if (overfull) for (int b = 0; b < T.capacity; b++) overfull[b] = 0; }
+      else {
+        for (int b = 0; b < T.capacity; b++) { offsets[b] = (int64_t)(T.buckets[(size_t)b] >> 24); if (overfull) overfull[b] = (uint8_t)((T.buckets[(size_t)b] >> 16) & 1); }
+        offsets[T.capacity] = n_pos;
+      }
+    }
+    if (positions && n_pos) memcpy(positions, T.positions.data(), (size_t)n_pos * 4);
+  }
+
+  // ---- duplication detector (DuplicationDetector.process :129-214, saveDuplications :332-400) ----
+  struct Dup { int length, count; };
+  static int compare_dups(int window, int s1, const Dup& d1, int s2, const Dup& d2) {  // :406-436
+    if (window > 1) { if (s1 / window != s2 / window) return 0; }
+    int e1 = s1 + d1.length, e2 = s2 + d2.length;
+    if (s1 <= s2 && e1 >= e2) return 1;
+    if (s1 >= s2 && e1 <= e2) return -1;
+    if (window > 1) { int cd = d1.count - d2.count; if (cd != 0) return cd; if (s1 != s2) return s1 - s2; }
+    return 0;
+  }
+  void build_duplications(int min_len, int max_len, int min_copies, int window) {
+    if (min_len < 0) min_len = choose_min_dup_len();
+    if (max_len < 0) max_len = 2 * choose_min_dup_len();
+    dup_window = window; dup_granularity = gapmers ? (double)(min_len * 5 / 8) : (double)min_len;  // :67-77
+    std::vector<std::map<int, Dup>> all((size_t)2 * n_contigs);  // per sequence id
+    auto save = [&](std::map<int, std::map<int, Dup>>& blocks) {
+      for (auto& e : blocks) {
+        auto& m = all[(size_t)e.first];
+        for (auto& pos : e.second) {
+          int ds = pos.first; const Dup& nd = pos.second; bool insert = true;
+          while (true) {
+            auto it = m.upper_bound(ds);
+            if (it != m.begin()) { --it; int c = compare_dups(window, ds, nd, it->first, it->second); if (c > 0) { insert = false; break; } if (c < 0) { m.erase(it); continue; } }
+            break;
+          }
+          while (true) {
+            auto it = m.lower_bound(ds);
+            if (it != m.end()) { int c = compare_dups(window, ds, nd, it->first, it->second); if (c > 0) { insert = false; break; } if (c < 0) { m.erase(it); continue; } }
+            break;
+          }
+          if (insert) m[ds] = nd;
+        }
+      }
+      blocks.clear();
+    };
+    for (int bl = min_len; bl <= max_len && bl <= max_built; bl++) {
+      const HostTable& T = tables[(size_t)bl];
+      std::map<int, std::map<int, Dup>> blocks;
+      for (int hc = 0; hc < T.capacity; hc++) {
+        if (!T.buckets.empty()) {
+          uint64_t word = T.buckets[(size_t)hc];
+          int cnt = (int)(word & 0xFFFF);
+          if (!((word >> 16) & 1) && cnt >= min_copies) {
+            // lookupByForwardHash :41-52: every stored position plus its reverse complement (using numBasepairsUsed as the length)
+            std::map<std::string, std::set<std::pair<int, int>>> by_text;
+            int prefix = (bl + 3) / 4;
+            for (int k = 0; k < 2 * cnt; k++) {
+              int64_t g = T.positions[(size_t)(word >> 24) + (size_t)(k % cnt)];
+              int sid = (int)(std::upper_bound(gstart.begin(), gstart.end(), g) - gstart.begin()) - 1;
+              int st = (int)(g - gstart[(size_t)sid]);
+              if (k >= cnt) { sid ^= 1; st = len[(size_t)(sid >> 1)] - st - bl; }
+              SeqView v = contig_view(sid >> 1, sid & 1);
+              std::string text; bool amb = false;
+              for (int i = 0; i < prefix; i++) { uint8_t c = v.at(st + i); if (bp_is_ambiguous(c)) amb = true; text.push_back((char)c); }
+              for (int i = 0; i < prefix; i++) { uint8_t c = v.at(st + bl - prefix + i); if (bp_is_ambiguous(c)) amb = true; text.push_back((char)c); }
+              if (!amb) by_text[text].insert({sid, st});
+            }
+            for (auto& g : by_text) {
+              Dup d{bl, (int)g.second.size()};
+              if (d.count >= min_copies) for (auto& u : g.second) blocks[u.first][u.second] = d;
+            }
+          }
+        }
+        if (hc % 10000 == 9999 || hc == T.capacity - 1) save(blocks);
+      }
+    }
+    dup_starts.assign((size_t)n_contigs, {});
+    for (int c = 0; c < n_contigs; c++) for (auto& e : all[(size_t)2 * c]) dup_starts[(size_t)c].push_back(e.first);
+    dup_set = true; generation++;
+  }
+  void set_duplications(int window, double granularity, int contig, int n, const int32_t* starts) {
+    dup_window = window; dup_granularity = granularity;
+    if ((int)dup_starts.size() < n_contigs) dup_starts.resize((size_t)n_contigs);
+    dup_starts[(size_t)contig].assign(starts, starts + n);
+    dup_set = true; generation++;
+  }
+};
+
+// Workspace tiers: bytes of per-query arena. Queries that exhaust a tier are re-run from scratch in the next one
+// (the algorithm is deterministic), so small arenas keep the common case at full occupancy.
+static const int XM_NUM_TIERS = 3;
+inline long long tier_arena_bytes(int tier, int max_seq_len, int n_seqs_max) {
+  long long rows = (long long)(max_seq_len + 2) * (long long)sizeof(RowWin) * n_seqs_max;
+  long long grid = (long long)(max_seq_len + 2) * (long long)(max_seq_len * 2 + 64) * 26;  // full-read PathAligner grid
+  switch (tier) {
+    case 0: return std::max<long long>(24 * 1024, std::min<long long>(rows / 4 + 16 * 1024, 96 * 1024));
+    case 1: return std::max<long long>(256 * 1024, rows * 2 + grid / 4);
+    default: return std::max<long long>(4 * 1024 * 1024, rows * 4 + grid * 4);
+  }
+}
+
+}  // namespace xm

@@ -1,0 +1,676 @@
+// xmapper_b200 device core — seeding: content-defined hash blocks, gapmers, the seed walk, index lookups,
+// flank verification, candidate binning and mate pairing.  One query per thread; all state lives in the
+// per-thread workspace (WS).  Reproduces, result for result:
+//   M/HashBlock.java, M/HashBlock_BaseRow.java, M/HashBlock_ParentRow.java (rows are kept as small sliding
+//   windows: a block is a pure function of the bases at and after its start, so a row may restart its scan at
+//   any requested position — same blocks as the reference's append-only lists, bounded memory),
+//   M/HashBlockPath.java, M/Readable_HashBlock_Database.java, M/PackedMap.java (read side),
+//   M/Counting_HashBlockPath.java, M/HashBlockMatch_Counter.java, M/HashBlockPaths_Counter.java.
+#pragma once
+#include "xm_types.h"
+
+namespace xm {
+
+struct HB {  // M/HashBlock.java:385-397
+  int start, len, used;
+  int32_t fwd, rev;
+  int8_t gap_dir;
+  uint8_t flags;  // 1 requestMergeLeft, 2 requestMergeRight, 4 nextRequestMergeLeft, 8 nextRequestMergeRight
+  int16_t extra;
+  long long ident;  // object identity stand-in (HashBlockMatch_Counter.update compares references)
+  XM_INLINE int end() const { return start + len; }
+  XM_INLINE bool rml() const { return flags & 1; }
+  XM_INLINE bool rmr() const { return flags & 2; }
+  XM_INLINE bool primary() const { return (rml() != rmr()) ? rml() : (fwd >= rev); }  // :332-337
+  XM_INLINE int32_t lookup_key() const { return primary() ? fwd : rev; }
+};
+
+XM_INLINE int max_gapmer_used(int len) { return len + len * 9 / 8 + 1; }  // HashBlock.java:12-14
+
+XM_INLINE int32_t merge_hash(int l_len, int32_t l_h, int r_len, int32_t r_h) {  // :261-269
+  unsigned long long rl = (unsigned long long)((long long)l_h + 1) * (unsigned long long)(54323LL + 323LL * (long long)r_len);
+  unsigned long long rr = (unsigned long long)(long long)wadd(r_h, 1) * (unsigned long long)(long long)l_len;
+  unsigned long long top = rl + rr;
+  return wadd((int32_t)(uint32_t)top, (int32_t)(uint32_t)(top >> 32));
+}
+
+XM_INLINE HB base_block(uint8_t code, int index) {  // HashBlock(char,int) + hashChar :60-65,171-188
+  HB b;
+  b.start = index; b.len = 1; b.used = 1; b.gap_dir = 0; b.extra = 0;
+  b.fwd = (code == 1) ? 0 : (code == 2) ? 1 : (code == 4) ? 2 : 3;
+  bool rml = (b.fwd / 2 == 0), nrml = (b.fwd % 2 == 0);
+  b.flags = (uint8_t)((rml ? 1 : 2) | (nrml ? 4 : 8));
+  b.rev = 3 - b.fwd;
+  b.ident = index;
+  return b;
+}
+
+XM_HD inline HB merge_blocks(const HB& L, const HB& R, int level) {  // HashBlock(seq,start,len,l,r) :20-44 + mergeHashes :192-259
+  HB b;
+  b.start = L.start; b.len = R.end() - L.start; b.used = b.len;
+  b.fwd = merge_hash(L.len, L.fwd, R.len, R.fwd);
+  b.rev = merge_hash(R.len, R.rev, L.len, L.rev);
+  bool rml = true, rmr = true, nrml = true, nrmr = true;
+  int anchor = 0;  // 0 none, 1 left, 2 right
+  if (L.fwd != R.rev) anchor = (L.fwd > R.rev) ? 2 : 1;
+  if (anchor != 0 && b.fwd != b.rev) {
+    const HB& A = (anchor == 2) ? R : L;
+    const HB& O = (anchor == 2) ? L : R;
+    bool is_reverse = b.fwd < b.rev;
+    bool invert = is_reverse == (anchor == 2);
+    bool aL = (A.flags & 4) != 0, aR = (A.flags & 8) != 0;
+    if (aL && aR) { if (anchor == 2) aR = false; else aL = false; }
+    bool oL = (O.flags & 4) != 0, oR = (O.flags & 8) != 0;
+    if (oL && oR) { if (anchor == 1) oL = false; else oR = false; }  // "other == rightParent" <=> anchor is left
+    rml = aL != invert; rmr = aR != invert; nrml = oL != invert; nrmr = oR != invert;
+  }
+  if (L.len != R.len) { rml = (L.len > R.len); rmr = !rml; nrml = !rml; nrmr = !nrml; }
+  if (b.fwd != b.rev) {
+    if (rml && rmr) { rml = (b.fwd > b.rev); rmr = !rml; }
+    if (nrml && nrmr) { nrml = rml; nrmr = !nrml; }
+  }
+  b.flags = (uint8_t)((rml ? 1 : 0) | (rmr ? 2 : 0) | (nrml ? 4 : 0) | (nrmr ? 8 : 0));
+  b.gap_dir = 0;
+  if (rml != rmr) b.gap_dir = rml ? 1 : -1;
+  else if (L.fwd != R.rev) b.gap_dir = (L.fwd > R.rev) ? 1 : -1;
+  b.extra = (int16_t)((L.len + R.len - b.len) / 4);
+  b.ident = ((long long)level << 40) | (long long)b.start;
+  return b;
+}
+
+XM_INLINE int ext_char_to_int(uint8_t c) { return c == 1 ? 1 : c == 2 ? 2 : c == 4 ? 3 : c == 8 ? 4 : 0; }
+
+// HashBlock.withGapAndExtension :67-150. false = null
+XM_HD inline bool with_gap_and_extension(const HB& b, const SeqView& seq, HB& out) {
+  if (b.gap_dir == 0) { out = b; return true; }
+  int target = b.len + (jabs(b.fwd > b.rev ? b.fwd : b.rev) % 3) + b.extra;
+  int gap = b.len / 2;
+  int ext = target - gap;
+  int32_t h = 0;
+  HB r;
+  if (b.gap_dir < 0) {
+    int ext_end = b.start - gap, ext_start = ext_end - ext;
+    if (ext_start < 0) return false;
+    for (int i = ext_end - 1; i >= ext_start; i--) h = wadd(wmul(h, 7654337), ext_char_to_int(seq.at(i)));
+    r.start = ext_start; r.len = ext + gap + b.len;
+  } else {
+    int ext_start = b.end() + gap, ext_end = ext_start + ext;
+    if (ext_end > seq.len) return false;
+    for (int i = ext_start; i < ext_end; i++) h = wadd(wmul(h, 7654337), ext_char_to_int(bp_complement(seq.at(i))));
+    r.start = b.start; r.len = b.len + gap + ext;
+  }
+  r.fwd = wadd(b.fwd, h); r.rev = wadd(b.rev, h);
+  r.used = b.len + ext;
+  r.gap_dir = 0; r.flags = 0; r.extra = 0; r.ident = 0;
+  out = r;
+  return true;
+}
+
+// ---------------- workspace ----------------
+static const int ROW_W = 8;
+struct RowWin { int mpc, low, head, cnt; HB ring[ROW_W]; };
+
+struct Counter {  // M/HashBlockMatch_Counter.java
+  int set, contig, offset;  // set 0 = reversed matches ("forwardMatchCounters"), 1 = the others
+  int num_matches, num_distinct, last_mismatched_pos;
+  long long last_matched_ident;
+  int has_last, hist_processed, good, priority;
+  int next, prev;
+};
+struct Hist { int start, end; long long ident; };
+struct SM { int mate, rev, contig, offset, from_hash; };  // M/SequenceMatch.java: a = rev ? RC(read[mate]) : read[mate]
+struct CL { int id, kind, G, k, size; };                  // lazily evaluated List<HashBlockMatch_Counter>
+struct QM { int c[2]; int priority; int hint; };          // M/QueryMatch.java, components as counter indices
+
+struct MatePath {
+  SeqView q;  // sequence the path walks (mate 2: reverse complement of the read, AlignerWorker.java:317-318)
+  int mate, path_is_rc;
+  RowWin* rows; int max_levels;
+  // HashBlockPath
+  int batch_index, cur_valid; HB cur; int have_gapmer; HB gapmer;
+  int have_prev, have_prevprev; int32_t prev_fwd, prevprev_fwd; long long gapmer_serial;
+  // Counting_HashBlockPath
+  Counter* counters; int n_counters, cap_counters;
+  int* good; int n_good;
+  Hist* history; int n_hist, cap_hist;
+  HB* pending; int pend_head, pend_cnt, cap_pend;
+  int found_good, n_blocks_anywhere, max_nonoverlap_visited, n_nonoverlap_visited, min_num_distinct, done, max_indel_consider;
+  int ph_valid; CL ph;   // previousHighPriorityMatchCounters
+  int pa_valid; CL pa;   // previousAllPositions
+};
+
+struct DAlnStore;  // xm_align.h
+
+struct WS {
+  const RefD* ref; const IndexD* ix; const DupD* dup;
+  Params prm; QueryIn query;
+  int status;
+  int next_list_id;
+  MatePath mp[2];
+  // HashBlockPaths_Counter
+  int pc_max_offset_between, pc_have_prev, pc_prev_ids[2], pc_found_nonempty;
+  QM* assembled; int n_assembled, cap_assembled;
+  // scratch (stack discipline)
+  char* scratch; long long scratch_size, scratch_top;
+  // alignment store (xm_align.h)
+  char* store; long long store_size, store_top;
+  unsigned long long st_probes, st_seeds, st_hits, st_straight, st_path_calls, st_path_steps, st_path_cells;
+
+  XM_INLINE void fail(int s) { if (status == 0) { status = s; XM_T("FAIL status=%d\n", s); } }
+  XM_INLINE void* salloc(long long bytes) {
+    bytes = (bytes + 7) & ~7LL;
+    if (scratch_top + bytes > scratch_size) { fail(Q_NEED_MORE); return nullptr; }
+    void* p = scratch + scratch_top; scratch_top += bytes; return p;
+  }
+  XM_INLINE SeqView query_view(int mate, int rev) const { SeqView v = query.seq[mate]; v.rc = rev; return v; }
+};
+
+XM_INLINE int sm_start_b(const WS& w, const SM& m) { return imax(0, m.offset); }
+XM_INLINE int sm_end_b(const WS& w, const SM& m) { return imin(m.offset + w.query.seq[m.mate].len, w.ref->len[m.contig]); }
+XM_INLINE SM counter_match(const MatePath& m, const Counter& c) {
+  SM s; s.mate = m.mate; s.rev = (c.set == 0) ? 1 : 0; s.contig = c.contig; s.offset = c.offset; s.from_hash = 1; return s;
+}
+
+// ---------------- rows ----------------
+XM_HD bool row_get_after(WS& w, MatePath& m, int level, int p, HB& out);
+
+XM_HD inline void row_push(RowWin& r, const HB& b) {
+  if (r.cnt == ROW_W) {  // evict the oldest: the window is now complete only for starts > its start
+    int es = r.ring[r.head].start;
+    if (es > r.low) r.low = es;
+    r.head = (r.head + 1) % ROW_W; r.cnt--;
+  }
+  r.ring[(r.head + r.cnt) % ROW_W] = b; r.cnt++;
+}
+
+// HashBlock_ParentRow.maybeMakeBlock :69-127 (single blocks only)
+XM_HD inline void row_maybe_make(WS& w, MatePath& m, int level) {
+  RowWin& r = m.rows[level];
+  HB left, right;
+  if (!row_get_after(w, m, level - 1, r.mpc, left)) { r.mpc = m.q.len; return; }
+  r.mpc = left.start;
+  if (row_get_after(w, m, level - 1, left.start, right)) {
+    if (left.end() >= right.start && (left.rmr() || right.rml())) row_push(r, merge_blocks(left, right, level));  // shouldMergeBlocks :200-208
+  }
+}
+
+XM_HD inline bool row_get_after(WS& w, MatePath& m, int level, int p, HB& out) {
+  if (w.status != 0) return false;
+  if (level == 0) {  // HashBlock_BaseRow.get :27-59
+    int idx = p + 1;
+    if (idx >= m.q.len) return false;
+    uint8_t code = m.q.at(idx);
+    if (bp_is_ambiguous(code)) { w.fail(Q_AMBIGUOUS_QUERY); return false; }
+    out = base_block(code, idx);
+    return true;
+  }
+  if (level >= m.max_levels) { w.fail(Q_NEED_MORE); return false; }
+  RowWin& r = m.rows[level];
+  if (p < r.low) { r.mpc = p; r.low = p; r.cnt = 0; r.head = 0; }
+  for (int i = 0; i < r.cnt; i++) {
+    const HB& b = r.ring[(r.head + i) % ROW_W];
+    if (b.start > p) { out = b; return true; }
+  }
+  while (true) {  // HashBlock_ParentRow.getAfter :44-59
+    if (w.status != 0) return false;
+    if (r.mpc >= m.q.len) return false;
+    if (r.cnt > 0) {
+      const HB& last = r.ring[(r.head + r.cnt - 1) % ROW_W];
+      if (last.start > p) { out = last; return true; }
+    }
+    row_maybe_make(w, m, level);
+  }
+}
+XM_HD inline bool row_get(WS& w, MatePath& m, int level, int index, HB& out) {  // :21-26
+  if (!row_get_after(w, m, level, index - 1, out)) return false;
+  return out.start == index;
+}
+
+// ---------------- index reads (Readable_HashBlock_Database / PackedMap) ----------------
+XM_HD inline bool ix_table(WS& w, int used, const TableD*& t) {
+  if (used > w.ix->max_built) { w.fail(Q_INDEX_TOO_SHORT); return false; }
+  t = &w.ix->tables[used];
+  return true;
+}
+XM_INLINE uint64_t ix_bucket(const TableD& t, int32_t key) {
+  int r = key % t.capacity;
+  if (r < 0) r += t.capacity;
+  return t.buckets[r];
+}
+XM_HD inline int ix_num_matches_lower_bound(WS& w, const HB& b) {  // Readable_HashBlock_Database.java:72-80
+  if (b.used < w.ix->min_interesting) return JMAX;
+  const TableD* t;
+  if (!ix_table(w, b.used, t)) return JMAX;
+  w.st_probes++;
+  if (t->buckets == nullptr) return 0;
+  uint64_t word = ix_bucket(*t, b.lookup_key());
+  if ((word >> 16) & 1) return JMAX;
+  return (int)(word & 0xFFFF);
+}
+XM_HD inline int ix_max_num_matches_allowed(WS& w, const HB& b) {  // :82-90
+  if (b.used < w.ix->min_interesting) return -1;
+  const TableD* t;
+  if (!ix_table(w, b.used, t)) return 0;
+  return t->max_count;
+}
+
+// ---------------- HashBlockPath ----------------
+XM_HD inline void path_init(WS& w, MatePath& m) {
+  m.batch_index = -1; m.cur_valid = 1;
+  HB d; d.start = 0; d.len = 0; d.used = 0; d.fwd = 0; d.rev = 0; d.gap_dir = 0; d.flags = 0; d.extra = 0; d.ident = -1;  // new HashBlock(0, 0)
+  m.cur = d; m.have_gapmer = 0; m.have_prev = 0; m.have_prevprev = 0; m.prev_fwd = 0; m.prevprev_fwd = 0; m.gapmer_serial = 0;
+}
+XM_HD inline bool path_with_gap(WS& w, MatePath& m, HB& out) {  // :197-203
+  if (!w.ix->gapmers) { out = m.cur; return true; }
+  if (!m.have_gapmer) {
+    HB g;
+    if (!with_gap_and_extension(m.cur, m.q, g)) return false;
+    if (m.cur.gap_dir != 0) g.ident = (1LL << 60) + (m.gapmer_serial++);
+    m.gapmer = g; m.have_gapmer = 1;
+  }
+  out = m.gapmer;
+  return true;
+}
+XM_HD inline void path_move_right(WS& w, MatePath& m) {  // :125-128
+  HB n;
+  m.cur_valid = row_get_after(w, m, m.batch_index, m.cur.start, n) ? 1 : 0;
+  if (m.cur_valid) m.cur = n;
+  m.have_gapmer = 0;
+}
+XM_HD inline void path_move_down(WS& w, MatePath& m) {  // :99-108
+  m.batch_index--;
+  path_move_right(w, m);
+}
+XM_HD inline void path_move_up_or_right(WS& w, MatePath& m) {  // :111-122
+  HB up;
+  if (row_get(w, m, m.batch_index + 1, m.cur.start, up) && up.start <= m.cur.start) { m.batch_index++; m.cur = up; m.have_gapmer = 0; }
+  else path_move_right(w, m);
+}
+XM_HD inline int path_max_allowed(WS& w, MatePath& m, const HB& b) {  // :205-219
+  if (b.len >= m.q.len / 6) return ix_max_num_matches_allowed(w, b);
+  if (b.rmr()) return 5;
+  return b.used + 1;
+}
+XM_HD inline bool path_advance(WS& w, MatePath& m) {  // advanceToNextPosition :143-195 (multi-blocks cannot occur: ambiguous queries are rejected)
+  const HB single = m.cur;
+  if (max_gapmer_used(single.len) < w.ix->min_interesting && w.ix->gapmers) path_move_up_or_right(w, m);
+  else {
+    HB ext;
+    if (path_with_gap(w, m, ext)) {
+      int num = ix_num_matches_lower_bound(w, ext);
+      if (num < 6) { if (m.batch_index > 0) path_move_down(w, m); else path_move_right(w, m); }
+      else if (num > path_max_allowed(w, m, ext)) path_move_up_or_right(w, m);
+      else path_move_right(w, m);
+    } else {
+      int typical = single.len * 3 / 2;
+      if (typical <= w.ix->min_interesting && w.ix->gapmers) path_move_up_or_right(w, m);
+      else { if (m.batch_index > 0) path_move_down(w, m); else path_move_right(w, m); }
+    }
+  }
+  return m.cur_valid && w.status == 0;
+}
+XM_HD inline bool path_next_interesting_block(WS& w, MatePath& m, HB& out) {  // getNextInterestingBlock :27-50 + :68-96
+  if (!m.cur_valid) return false;
+  while (true) {
+    if (!path_advance(w, m)) return false;
+    HB ext;
+    if (!path_with_gap(w, m, ext)) continue;
+    if (!(ix_num_matches_lower_bound(w, ext) <= path_max_allowed(w, m, ext))) continue;
+    if (w.status != 0) return false;
+    // recentlySeen :52-65
+    bool seen = (m.have_prev && ext.fwd == m.prev_fwd) || (m.have_prevprev && ext.fwd == m.prevprev_fwd);
+    m.have_prevprev = m.have_prev; m.prevprev_fwd = m.prev_fwd; m.have_prev = 1; m.prev_fwd = ext.fwd;
+    if (seen) continue;
+    out = ext;
+    return true;
+  }
+}
+
+// ---------------- Counting_HashBlockPath ----------------
+XM_HD inline void counter_update(MatePath& m, Counter& c, const WS& w) {  // HashBlockMatch_Counter.update :50-55,83-97
+  int blen = w.ref->len[c.contig];
+  while (c.hist_processed < m.n_hist) {
+    const Hist& h = m.history[c.hist_processed];
+    if (!(c.has_last && h.ident == c.last_matched_ident)) {
+      if (h.start >= c.last_mismatched_pos) {
+        if (c.offset + h.end <= blen) { c.num_distinct++; c.last_mismatched_pos = h.end; }
+      }
+    }
+    c.hist_processed++;
+  }
+}
+XM_HD inline void counter_declare_good(MatePath& m, Counter& c, int idx, const WS& w) {  // declareGood :282-287
+  if (!c.good) { m.good[m.n_good++] = idx; c.good = 1; counter_update(m, c, w); c.priority = c.num_distinct; }
+}
+XM_HD inline void counting_add_match(WS& w, MatePath& m, const SM& full, const HB& qb, int ci, int qb_num_matches) {  // addMatch :254-279
+  Counter& c = m.counters[ci];
+  c.num_matches++; c.has_last = 1; c.last_matched_ident = qb.ident;
+  counter_update(m, c, w);
+  if (c.num_matches <= 1) {
+    if (c.num_matches == 1) { m.found_good = 1; counter_declare_good(m, c, ci, w); }
+    else if (qb_num_matches <= qb.len) {
+      int from_start = full.offset;
+      int from_end = w.ref->len[full.contig] - (full.offset + w.query.seq[full.mate].len);
+      if (imin(from_start, from_end) < 0) counter_declare_good(m, c, ci, w);
+    }
+  }
+}
+XM_HD inline void counting_update_matches(WS& w, MatePath& m, const SM& sm, const HB& qb, int qb_num_matches) {  // updateMatches :193-252
+  int set = sm.rev ? 0 : 1;  // reversed matches live in "forwardMatchCounters" (:197-200)
+  int cur = -1, lower = -1, higher = -1;
+  for (int i = 0; i < m.n_counters; i++) {
+    const Counter& c = m.counters[i];
+    if (c.set != set || c.contig != sm.contig) continue;
+    if (c.offset == sm.offset) { cur = i; break; }
+    if (c.offset < sm.offset) { if (lower < 0 || c.offset > m.counters[lower].offset) lower = i; }
+    else { if (higher < 0 || c.offset < m.counters[higher].offset) higher = i; }
+  }
+  if (cur < 0) {
+    if (m.n_counters >= m.cap_counters) { w.fail(Q_NEED_MORE); return; }
+    cur = m.n_counters++;
+    Counter& c = m.counters[cur];
+    c.set = set; c.contig = sm.contig; c.offset = sm.offset;
+    c.num_matches = 0; c.num_distinct = m.n_nonoverlap_visited; c.last_mismatched_pos = qb.start;
+    c.has_last = 0; c.last_matched_ident = 0; c.hist_processed = m.n_hist - 1; c.good = 0; c.priority = 0; c.next = -1; c.prev = -1;
+    if (lower >= 0 && iabs(m.counters[lower].offset - sm.offset) <= m.max_indel_consider) { c.prev = lower; m.counters[lower].next = cur; }
+    if (higher >= 0 && iabs(m.counters[higher].offset - sm.offset) <= m.max_indel_consider) { c.next = higher; m.counters[higher].prev = cur; }
+  }
+  int pc = m.counters[cur].prev, nc = m.counters[cur].next;
+  if (pc >= 0) counting_add_match(w, m, sm, qb, pc, qb_num_matches);
+  if (nc >= 0) counting_add_match(w, m, sm, qb, nc, qb_num_matches);
+  bool update_this = true;
+  if ((pc >= 0 && m.counters[pc].good) || (nc >= 0 && m.counters[nc].good)) { if (!m.counters[cur].good) update_this = false; }
+  if (update_this) counting_add_match(w, m, sm, qb, cur, qb_num_matches);
+}
+// key order of tryEnsureGoodMatchCounter / getAllPositions: set 0 first, then contig, then offset (TreeMap)
+XM_INLINE bool counter_key_less(const Counter& a, const Counter& b) {
+  if (a.set != b.set) return a.set < b.set;
+  if (a.contig != b.contig) return a.contig < b.contig;
+  return a.offset < b.offset;
+}
+XM_HD inline int counters_next_sorted(const MatePath& m, int n, int after) {  // smallest key greater than counters[after] among [0, n)
+  int best = -1;
+  for (int i = 0; i < n; i++) {
+    if (after >= 0 && !counter_key_less(m.counters[after], m.counters[i])) continue;
+    if (best < 0 || counter_key_less(m.counters[i], m.counters[best])) best = i;
+  }
+  return best;
+}
+XM_HD inline void counting_try_ensure_good(WS& w, MatePath& m) {  // :292-308
+  if (!m.found_good && m.n_counters <= m.q.len) {
+    int after = -1;
+    while (true) {
+      int i = counters_next_sorted(m, m.n_counters, after);
+      if (i < 0) break;
+      counter_declare_good(m, m.counters[i], i, w);
+      after = i;
+    }
+    m.found_good = 1;
+  }
+}
+XM_HD inline bool counting_next_block(WS& w, MatePath& m, HB& out) {  // getNextInterestingBlock :344-368
+  m.pa_valid = 0;
+  while (true) {
+    HB b;
+    if (!path_next_interesting_block(w, m, b)) {
+      if (w.status != 0) return false;
+      if (m.pend_cnt < 1) return false;
+      out = m.pending[m.pend_head]; m.pend_head = (m.pend_head + 1) % m.cap_pend; m.pend_cnt--;
+      return true;
+    }
+    if (b.start < m.max_nonoverlap_visited) {
+      if (m.pend_cnt >= m.cap_pend) { w.fail(Q_NEED_MORE); return false; }
+      m.pending[(m.pend_head + m.pend_cnt) % m.cap_pend] = b; m.pend_cnt++;
+      continue;
+    }
+    out = b;
+    return true;
+  }
+}
+XM_HD inline bool counting_step(WS& w, MatePath& m) {  // step :40-179
+  if (m.done || w.status != 0) return false;
+  HB qb;
+  const TableD* t = nullptr;
+  uint64_t word = 0;
+  int count = 0;
+  while (true) {  // getNextInterestingMatch :371-388 + matchBlock (Readable_HashBlock_Database.java:22-38)
+    if (!counting_next_block(w, m, qb)) {
+      if (w.status != 0) return false;
+      m.done = 1;
+      if (m.n_blocks_anywhere < 1) counting_try_ensure_good(w, m);
+      return false;
+    }
+    if (qb.used < w.ix->min_interesting) continue;  // null
+    if (!ix_table(w, qb.used, t)) return false;
+    if (t->buckets == nullptr) { count = 0; break; }
+    word = ix_bucket(*t, qb.lookup_key());
+    if ((word >> 16) & 1) continue;  // too many matches => null
+    count = (int)(word & 0xFFFF);
+    if (count > t->max_count) continue;
+    break;
+  }
+  if (m.n_hist >= m.cap_hist) { w.fail(Q_NEED_MORE); return false; }
+  XM_T("seed start=%d len=%d used=%d fwd=%d rev=%d count=%d invert=%d\n", qb.start, qb.len, qb.used, qb.fwd, qb.rev, count, (int)!qb.primary());
+  Hist hh; hh.start = qb.start; hh.end = qb.end(); hh.ident = qb.ident;
+  m.history[m.n_hist++] = hh;
+  w.st_seeds++; w.st_hits += (unsigned long long)count;
+  bool invert = !qb.primary();
+  const uint32_t* pos = (count > 0) ? t->positions + (word >> 24) : nullptr;
+  int qlen = m.q.len;
+  for (int k = 0; k < count; k++) {
+    int seq_id, rstart;
+    w.ref->decode((int64_t)pos[k], seq_id, rstart);
+    if (invert) { seq_id ^= 1; rstart = w.ref->len[seq_id >> 1] - rstart - qb.len; }
+    int contig = seq_id >> 1, on_rc = seq_id & 1;
+    SeqView cms = w.ref->contig(contig, on_rc);
+    int mism = 0, mat = 0;
+    for (int d = 1; d < 20; d++) {  // :98-153
+      int qi = qb.start - d;
+      if (qi >= 0 && qi < qlen) {
+        int ri = rstart - d;
+        if (ri >= 0 && ri < cms.len) { if (!bp_can_match(m.q.at(qi), cms.at(ri))) mism++; else mat++; }
+      }
+      qi = qb.start + qb.len - 1 + d;
+      if (qi >= 0 && qi < qlen) {
+        int ri = rstart + qb.len - 1 + d;
+        if (ri >= 0 && ri < cms.len) { if (!bp_can_match(m.q.at(qi), cms.at(ri))) mism++; else mat++; }
+      }
+      if (mat < mism) break;
+      if (mat >= mism + qb.used) break;
+    }
+    XM_T("  hit seq=%d rstart=%d mism=%d mat=%d\n", seq_id, rstart, mism, mat);
+    if (mism > mat) continue;
+    SM full; full.mate = m.mate; full.contig = contig; full.from_hash = 1;
+    if (on_rc) {  // :155-166
+      int rq = qlen - qb.end();
+      int rr = cms.len - (rstart + qb.len);
+      full.rev = m.path_is_rc ? 0 : 1;  // a = reverseComplementQuery
+      full.offset = rr - rq;
+    } else { full.rev = m.path_is_rc ? 1 : 0; full.offset = rstart - qb.start; }
+    counting_update_matches(w, m, full, qb, count);
+    if (w.status != 0) return false;
+  }
+  if (qb.start >= m.max_nonoverlap_visited) { m.max_nonoverlap_visited = qb.end(); m.n_nonoverlap_visited++; }
+  m.n_blocks_anywhere++;
+  m.min_num_distinct = -1;
+  return true;
+}
+
+// ---- lazily evaluated counter lists ----
+// kind 0: good[0..G) with priority <= k     (findGoodPositionsHavingPriorityUpTo :406-433)
+// kind 2: good[0..G) with numDistinct <= k  (getBestMatches :471-493)
+// kind 1: all counters [0..G) in key order  (getAllPositions :435-452)
+XM_HD inline int list_next(WS& w, MatePath& m, const CL& l, int& cursor) {  // cursor starts at -1; returns counter index or -1
+  if (l.kind == 1) { int i = counters_next_sorted(m, l.G, cursor); cursor = i; return i; }
+  for (int i = cursor + 1; i < l.G; i++) {
+    Counter& c = m.counters[m.good[i]];
+    bool take;
+    if (l.kind == 0) take = c.priority <= l.k;
+    else { counter_update(m, c, w); take = c.num_distinct <= l.k; }
+    if (take) { cursor = i; return m.good[i]; }
+  }
+  cursor = l.G;
+  return -1;
+}
+XM_HD inline int list_size(WS& w, MatePath& m, const CL& l) {
+  if (l.kind == 1) return l.G;
+  int n = 0, cur = -1;
+  while (list_next(w, m, l, cur) >= 0) n++;
+  return n;
+}
+XM_HD inline CL counting_find_good_up_to(WS& w, MatePath& m, int priority) {  // :406-433
+  while (true) {
+    if (m.n_nonoverlap_visited >= wadd(priority, 1)) break;
+    if (!counting_step(w, m)) break;
+  }
+  if (m.ph_valid && m.ph.size == m.n_good) return m.ph;
+  CL l; l.id = w.next_list_id++; l.kind = 0; l.G = m.n_good; l.k = priority; l.size = 0;
+  l.size = list_size(w, m, l);
+  m.ph = l; m.ph_valid = 1;
+  return l;
+}
+XM_HD inline CL counting_all_positions(WS& w, MatePath& m) {
+  if (!m.pa_valid) { CL l; l.id = w.next_list_id++; l.kind = 1; l.G = m.n_counters; l.k = 0; l.size = m.n_counters; m.pa = l; m.pa_valid = 1; }
+  return m.pa;
+}
+XM_HD inline CL counting_best_matches(WS& w, MatePath& m) {  // getBestMatches :471-493 + getNumGoodDistinctMismatches :458-470
+  CL l; l.id = w.next_list_id++; l.kind = 2; l.G = 0; l.k = 0; l.size = 0;
+  if (m.n_blocks_anywhere < 1) return l;
+  if (m.min_num_distinct < 0) {
+    int mn = m.n_nonoverlap_visited - 1;
+    for (int i = 0; i < m.n_good; i++) { Counter& c = m.counters[m.good[i]]; counter_update(m, c, w); if (mn >= c.num_distinct) mn = c.num_distinct; }
+    m.min_num_distinct = mn;
+  }
+  l.G = m.n_good; l.k = m.min_num_distinct;
+  l.size = list_size(w, m, l);
+  return l;
+}
+
+// ---------------- HashBlockPaths_Counter ----------------
+XM_HD inline int pc_count_priority(WS& w, const QM& q) {  // countPriority :314-334
+  const Counter& c1 = w.mp[0].counters[q.c[0]]; const Counter& c2 = w.mp[1].counters[q.c[1]];
+  SM m1 = counter_match(w.mp[0], c1), m2 = counter_match(w.mp[1], c2);
+  if (sm_start_b(w, m1) < sm_end_b(w, m2) && sm_end_b(w, m1) > sm_start_b(w, m2)) return imax(imax(0, c1.priority), c2.priority);
+  return c1.priority + c2.priority;
+}
+// matchWithoutCache :136-246 + assembleQueryMatches :248-265
+XM_HD inline void pc_match_without_cache(WS& w, const CL* lists, int n_lists) {
+  w.n_assembled = 0;
+  if (n_lists == 1) {
+    int cur = -1, ci;
+    while ((ci = list_next(w, w.mp[0], lists[0], cur)) >= 0) {
+      if (w.n_assembled >= w.cap_assembled) { w.fail(Q_NEED_MORE); return; }
+      QM q; q.c[0] = ci; q.c[1] = -1; q.priority = w.mp[0].counters[ci].priority; q.hint = 0;
+      w.assembled[w.n_assembled++] = q;
+    }
+    return;
+  }
+  bool last_largest = lists[0].size <= lists[1].size;
+  int first_ci = last_largest ? 0 : 1, second_ci = 1 - first_ci;
+  MatePath& A = w.mp[first_ci]; MatePath& B = w.mp[second_ci];
+  long long mark = w.scratch_top;
+  int na = lists[first_ci].size;
+  int* a_idx = (int*)w.salloc((long long)sizeof(int) * (na > 0 ? na : 1));
+  int* near = (int*)w.salloc((long long)sizeof(int) * (na > 0 ? na : 1));
+  if (w.status != 0) return;
+  { int cur = -1, ci, k = 0; while ((ci = list_next(w, A, lists[first_ci], cur)) >= 0 && k < na) a_idx[k++] = ci; na = k; }
+  int cur = -1, cb;
+  while ((cb = list_next(w, B, lists[second_ci], cur)) >= 0) {
+    const Counter& c = B.counters[cb];
+    bool b_rev = (c.set == 0);
+    bool b_qrev = (b_rev == (second_ci % 2 == 0));
+    int max_reverse = B.q.len / 2;
+    int s0, s1;
+    bool other_earlier = (b_qrev == last_largest);
+    if (other_earlier) { s0 = c.offset - max_reverse; s1 = c.offset + w.pc_max_offset_between; }
+    else { s0 = c.offset - w.pc_max_offset_between; s1 = c.offset + max_reverse; }
+    int nn = 0;
+    for (int k = 0; k < na; k++) {
+      const Counter& a = A.counters[a_idx[k]];
+      bool a_qrev = ((a.set == 0) == (first_ci % 2 == 0));
+      if (a_qrev != b_qrev || a.contig != c.contig) continue;
+      if (a.offset < s0 || a.offset > s1) continue;
+      int j = nn++;  // insertion sort by offset ascending
+      while (j > 0 && A.counters[near[j - 1]].offset > a.offset) { near[j] = near[j - 1]; j--; }
+      near[j] = a_idx[k];
+    }
+    bool desc = b_qrev && nn > 1;
+    for (int t = 0; t < nn; t++) {
+      int ai = near[desc ? nn - 1 - t : t];
+      if (w.n_assembled >= w.cap_assembled) { w.fail(Q_NEED_MORE); w.scratch_top = mark; return; }
+      QM q;
+      if (last_largest) { q.c[0] = ai; q.c[1] = cb; } else { q.c[0] = cb; q.c[1] = ai; }
+      Counter& g0 = w.mp[0].counters[q.c[0]]; Counter& g1 = w.mp[1].counters[q.c[1]];
+      counter_update(w.mp[0], g0, w); counter_update(w.mp[1], g1, w);
+      q.hint = g0.num_distinct < g1.num_distinct ? 1 : 0;
+      q.priority = pc_count_priority(w, q);
+      w.assembled[w.n_assembled++] = q;
+    }
+  }
+  w.scratch_top = mark;
+}
+XM_HD inline void pc_match(WS& w, const CL* lists, int n_lists) {  // match :116-133 (list identity cache)
+  bool same = w.pc_have_prev != 0;
+  if (same) for (int i = 0; i < n_lists; i++) if (w.pc_prev_ids[i] != lists[i].id) { same = false; break; }
+  if (!same) {
+    pc_match_without_cache(w, lists, n_lists);
+    for (int i = 0; i < n_lists; i++) w.pc_prev_ids[i] = lists[i].id;
+    w.pc_have_prev = 1;
+  }
+}
+XM_HD inline void pc_find_good_up_to(WS& w, int k) {  // findGoodPositionsWithPriorityUpTo :52-82
+  CL lists[2];
+  int n = w.query.n_seqs;
+  for (int i = 0; i < n; i++) {
+    lists[i] = counting_find_good_up_to(w, w.mp[i], k);
+    if (lists[i].size >= 1) w.pc_found_nonempty = 1;
+  }
+  if (w.status != 0) return;
+  pc_match(w, lists, n);
+}
+// optimisticGetBestMatches :84-98; returns the priority to filter on (filterMatchesHavingMinPriority selects the MAX, §9-5)
+XM_HD inline int pc_optimistic_best(WS& w) {
+  CL lists[2];
+  int n = w.query.n_seqs;
+  for (int i = 0; i < n; i++) {
+    while (true) {
+      CL best = counting_best_matches(w, w.mp[i]);
+      if (best.size == 1 || !counting_step(w, w.mp[i])) { lists[i] = best; break; }
+    }
+    if (w.status != 0) return -1;
+  }
+  pc_match(w, lists, n);
+  int mn = -1;
+  for (int i = 0; i < w.n_assembled; i++) if (mn < 0 || mn < w.assembled[i].priority) mn = w.assembled[i].priority;
+  return mn;
+}
+XM_HD inline bool pc_find_partially_good(WS& w) {  // findPartiallyGoodPositions :26-50; false = empty list
+  if (w.query.n_seqs != 2) return false;
+  if (!w.pc_found_nonempty) return false;
+  CL lists[2];
+  bool good = false, bad = false;
+  for (int i = 0; i < 2; i++) {
+    CL here = counting_find_good_up_to(w, w.mp[i], JMAX);
+    if (here.size == 0) { bad = true; here = counting_all_positions(w, w.mp[i]); } else good = true;
+    lists[i] = here;
+  }
+  if (w.status != 0) return false;
+  if (good && bad) { pc_match(w, lists, 2); return true; }
+  return false;
+}
+XM_HD inline int pc_num_blocks(const WS& w) { int t = 0; for (int i = 0; i < w.query.n_seqs; i++) t += w.mp[i].n_blocks_anywhere; return t; }
+
+// QueryMatch helpers (M/QueryMatch.java)
+XM_HD inline SM qm_comp(const WS& w, const QM& q, int i) {
+  const MatePath& m = w.mp[i];
+  const Counter& c = m.counters[q.c[i]];
+  SM s; s.mate = i; s.rev = (c.set == 0) ? 1 : 0; s.contig = c.contig; s.offset = c.offset; s.from_hash = 1;
+  return s;
+}
+XM_INLINE bool qm_same_position(const QM& a, int na, const QM& b, int nb) {  // samePosition :83-95 (counters are unique per position)
+  if (na != nb) return false;
+  for (int i = 0; i < na; i++) if (a.c[i] != b.c[i]) return false;
+  return true;
+}
+
+}  // namespace xm

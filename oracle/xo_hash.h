@@ -229,12 +229,10 @@ struct ParentRow : Row {  // M/HashBlock_ParentRow.java (assumeOnlyUsedOnce = fa
   }
   const MB* getAfter(int position) override {  // :28-60
     if (position < maxPositionChecked) {
-      const MB* p = nullptr;
-      for (int i = (int)blockList.size() - 1; i >= 0; i--) {
-        const MB& b = blockList[i];
-        if (b.startIndex() > position) p = &b; else break;
-      }
-      if (p != nullptr) return p;
+      // Java scans backwards from the end; block starts are ascending, so a binary search finds the same block
+      size_t lo = 0, hi = blockList.size();
+      while (lo < hi) { size_t mid = (lo + hi) / 2; if (blockList[mid].startIndex() > position) hi = mid; else lo = mid + 1; }
+      if (lo < blockList.size()) return &blockList[lo];
     }
     while (true) {
       if (maxPositionChecked >= seq->length()) break;

@@ -238,16 +238,20 @@ struct Index {  // M/HashBlock_Database.java (+ Readable view)
     };
     for (int level = 0;; level++) {
       Row* row = pyr.get(level);
-      int pos = s - 1;
       bool any = false, anyShort = false;
-      while (true) {
-        const MB* b = row->getAfter(pos);
-        if (b == nullptr || b->startIndex() >= e) break;
+      auto visit = [&](const MB* b) {
         any = true;
         if (b->minLength() <= hi) anyShort = true;
         if (b->single) addOne(b->hb, false);
         else for (auto& p : b->poss) if (p.has) addOne(p.hb, true);
-        pos = b->startIndex();
+      };
+      if (level == 0) {
+        for (int i = s; i < e; i++) visit(row->get(i));
+      } else {
+        // force the row through e, then walk its block list in order (getAfter() scans backwards from the end)
+        ParentRow* pr = static_cast<ParentRow*>(row);
+        pr->getAfter(e - 1);
+        for (const MB& b : pr->blockList) { int st = b.startIndex(); if (st >= e) break; if (st >= s) visit(&b); }
       }
       if (!any || !anyShort) break;
     }

@@ -10,6 +10,12 @@
 #include "xo_index.h"
 #include <deque>
 
+#ifdef XO_TRACE
+#include <cstdio>
+#define XO_T(...) fprintf(stderr, __VA_ARGS__)
+#else
+#define XO_T(...)
+#endif
 namespace xo {
 
 struct SeqMatch {  // M/SequenceMatch.java
@@ -221,6 +227,7 @@ struct CountingPath {  // M/Counting_HashBlockPath.java
       return false;
     }
     history.push_back(queryBlock);
+    XO_T("seed start=%d len=%d used=%d fwd=%d rev=%d count=%d invert=%d\n", queryBlock.start, queryBlock.len, queryBlock.used, queryBlock.fwd, queryBlock.rev, (int)matches.size(), (int)!queryBlock.primary());
     if (stats) { stats->seeds++; stats->hits += (long long)matches.size(); }
     int queryBlockNumMatches = (int)matches.size();
     for (auto& ref : matches) {
@@ -246,6 +253,7 @@ struct CountingPath {  // M/Counting_HashBlockPath.java
         if (numMatched < numMismatched) break;
         if (numMatched >= numMismatched + queryBlock.used) break;
       }
+      XO_T("  hit seq=%d rstart=%d mism=%d mat=%d\n", (int)ref.seq->id, ref.start, numMismatched, numMatched);
       if (numMismatched > numMatched) continue;
       SeqMatch full;
       if (cms->complementedFrom != nullptr) {

@@ -1,0 +1,78 @@
+"""Device-core logic (compiled for the host by the emulation harness) vs the oracle, bit for bit.
+These run without a GPU; the same comparisons run against the real CUDA library in test_gpu_parity.py."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import parity
+import xm_emu
+import xm_oracle as xo
+from mapper_b200 import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+V = json.load(open(os.path.join(HERE, "golden", "junit_vectors.json")))
+
+
+def run_both(oracle_db, params, batch, window, max_used, upload_index=True, upload_dups=True, dup=None):
+    emu = xm_emu.Emu(params)
+    parity.feed_from_oracle(emu, oracle_db, max_used, window, upload_index, upload_dups)
+    if not upload_index:
+        emu.build_index(max_used, threads=2)
+    if not upload_dups:
+        d = dup or {}
+        emu.build_duplications(d.get("min_len", -1), d.get("max_len", -1), d.get("min_copies", 2), window)
+    a = oracle_db.align_batch(params, batch, threads=1)
+    b = emu.align_batch(batch, threads=1)
+    emu.close()
+    return a, b
+
+
+@pytest.mark.parametrize("case", V["api_cases"], ids=[c["name"] for c in V["api_cases"]])
+def test_junit_api_cases(case):
+    if any(ch not in "ACGT" for s in case["seqs"] for ch in s):
+        pytest.skip("ambiguous query")
+    db = xo.Oracle([("reference-0", case["reference"])], dup=dict(min_copies=2, window=1))
+    batch = parity.batch_from_texts([case["seqs"]], [case["expected_inner"]], [case["per_penalty"]])
+    max_used = max(len(s) for s in case["seqs"]) + 2
+    a, b = run_both(db, case["params"], batch, 1, max_used)
+    parity.assert_same_results(a, b, case["name"])
+    # and the reference's own expectation
+    nchoice = b["comp_choice_off"][1] - b["comp_choice_off"][0] if len(b["comp_choice_off"]) == 2 else 0
+    assert nchoice == case["expect"]["count"]
+
+
+@pytest.mark.parametrize("paired", [False, True], ids=["single", "paired"])
+def test_random_reads_small_reference(paired):
+    ref = synth.random_reference(300000, seed=11, n_contigs=3, repeat_fraction=0.08, repeat_len=(200, 1500))
+    db = xo.Oracle([(n, synth.codes_to_text(s)) for n, s in ref], sort_by_length=True, dup=dict(min_copies=2, window=1000))
+    contigs = [db.contig(i) for i in range(db.num_contigs())]
+    batch = synth.simulate_reads(contigs, 3000, 150, seed=12 + paired, sub_rate=0.02, indel_rate=0.003, paired=paired)
+    a, b = run_both(db, synth.DEFAULT_PARAMS, batch, 1000, 150)
+    assert (a["q_status"] == 0).all()
+    parity.assert_same_results(a, b, "random %s" % ("paired" if paired else "single"))
+
+
+def test_library_index_builder_matches_host_tables():
+    ref = synth.random_reference(200000, seed=21, n_contigs=2, repeat_fraction=0.1, repeat_len=(100, 800))
+    db = xo.Oracle([(n, synth.codes_to_text(s)) for n, s in ref], sort_by_length=True, dup=dict(min_copies=2, window=1000))
+    built = db.build_through(120)
+    emu = xm_emu.Emu(synth.DEFAULT_PARAMS)
+    parity.feed_reference(emu, db)
+    emu.build_index(120, threads=3)
+    mi, mb = emu.index_info()
+    assert mi == db.min_interesting()
+    for n in range(1, min(built, mb) + 1):
+        t0, t1 = db.table(n), emu.get_index_length(n)
+        assert t0["capacity"] == t1["capacity"] and t0["max_count"] == t1["max_count"], n
+        assert np.array_equal(t0["overfull"], t1["overfull"]), n
+        assert np.array_equal(t0["positions"], t1["positions"]), n
+        keep = t0["overfull"] == 0
+        assert np.array_equal(np.diff(t0["offsets"])[keep], np.diff(t1["offsets"])[keep]), n
+    # duplication keys
+    db.detect_duplications()
+    emu.build_duplications(-1, -1, 2, 1000)
+    for c in range(db.num_contigs()):
+        assert np.array_equal(db.dup_starts(c), emu.get_duplications(c)), c
+    emu.close()
