@@ -1,0 +1,528 @@
+// xmapper_b200 — CUDA kernels + the C ABI (include/xmapper_b200.h).
+// One query per thread; queries are handed out dynamically (atomic ticket) to a persistent grid sized from the
+// SM count.  Every thread owns a private workspace arena in HBM; queries that exhaust the arena of one tier are
+// collected and re-run from scratch in the next tier (bigger arenas, fewer threads).  There is no CPU path: the
+// host only stages inputs, launches, and reshapes the result arena.
+#include "../../include/xmapper_b200.h"
+#include "xm_align.h"
+#include "xm_host_model.h"
+#include "xm_results.h"
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include <cstdio>
+#include <cstdlib>
+
+using namespace xm;
+
+// ---------------------------------------------------------------- kernels
+struct BatchD {
+  int n_queries;
+  const uint16_t* packed; const int64_t* seq_word_off; const int32_t* seq_len; const int64_t* first_seq;  // first_seq: n_queries+1
+  const double* expected_inner; const double* per_penalty;
+};
+struct LaunchD {
+  RefD ref; IndexD ix; DupD dup; Params prm;
+  BatchD batch;
+  OutArena out;
+  const int32_t* ids; int n_ids;          // queries of this tier (nullptr = identity)
+  int* ticket;                            // dynamic work counter
+  int32_t* need_more; int* n_need_more;   // queries to re-run in the next tier
+  int32_t* out_full; int* n_out_full;     // queries to re-run after growing the result arena
+  char* arenas; long long arena_bytes;
+  int last_tier;
+};
+
+__global__ void __launch_bounds__(128) xm_align_kernel(LaunchD L) {
+  long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  char* arena = L.arenas + tid * L.arena_bytes;
+  unsigned long long st[7] = {0, 0, 0, 0, 0, 0, 0};
+  while (true) {
+    int t = atomicAdd(L.ticket, 1);
+    if (t >= L.n_ids) break;
+    int qi = L.ids ? L.ids[t] : t;
+    QueryIn q;
+    long long s0 = L.batch.first_seq[qi];
+    q.n_seqs = (int)(L.batch.first_seq[qi + 1] - s0);
+    for (int s = 0; s < q.n_seqs; s++) { q.seq[s].w = L.batch.packed + L.batch.seq_word_off[s0 + s]; q.seq[s].len = L.batch.seq_len[s0 + s]; q.seq[s].rc = 0; }
+    if (q.n_seqs < 2) { q.seq[1] = q.seq[0]; q.seq[1].len = 0; }
+    q.expected_inner = q.n_seqs > 1 ? L.batch.expected_inner[qi] : 0.0;
+    q.per_penalty = q.n_seqs > 1 ? L.batch.per_penalty[qi] : 1.0;
+    WS w;
+    OutQuery rec; rec.status = 0; rec.n_comp = 1; rec.n_choice[0] = 0; rec.n_choice[1] = 0; rec.choice_first[0] = 0; rec.choice_first[1] = 0;
+    if (!ws_init(w, arena, L.arena_bytes, &L.ref, &L.ix, &L.dup, L.prm, q)) w.status = Q_NEED_MORE;
+    else align_query(w, L.out, rec);
+    int status = w.status;
+    if (status == Q_NEED_MORE) {
+      if (L.last_tier) status = Q_WORKSPACE;
+      else { int k = atomicAdd(L.n_need_more, 1); L.need_more[k] = qi; }
+    } else if (status == Q_OUT_FULL) { int k = atomicAdd(L.n_out_full, 1); L.out_full[k] = qi; }
+    rec.status = status;
+    L.out.q[qi] = rec;
+    if (status != Q_NEED_MORE && status != Q_OUT_FULL) {
+      st[0] += w.st_probes; st[1] += w.st_seeds; st[2] += w.st_hits; st[3] += w.st_straight; st[4] += w.st_path_calls; st[5] += w.st_path_steps; st[6] += w.st_path_cells;
+    }
+  }
+  for (int i = 0; i < 7; i++) if (st[i]) atomicAdd(&L.out.stats[i], st[i]);
+}
+
+// first_seq[q] = exclusive prefix sum of n_seqs_per_query (single block scan is enough off the hot path; uses a
+// simple two-pass chunked scan)
+__global__ void xm_chunk_sums_kernel(const uint8_t* n_seqs, int n, int chunk, long long* sums) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  long long lo = (long long)c * chunk;
+  if (lo >= n) return;
+  long long hi = lo + chunk < n ? lo + chunk : n;
+  long long s = 0;
+  for (long long i = lo; i < hi; i++) s += n_seqs[i];
+  sums[c] = s;
+}
+__global__ void xm_chunk_scan_kernel(const uint8_t* n_seqs, int n, int chunk, const long long* chunk_off, int64_t* first_seq) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  long long lo = (long long)c * chunk;
+  if (lo >= n) return;
+  long long hi = lo + chunk < n ? lo + chunk : n;
+  long long s = chunk_off[c];
+  for (long long i = lo; i < hi; i++) { first_seq[i] = s; s += n_seqs[i]; }
+  if (hi == n) first_seq[n] = s;
+}
+
+// ---- per-position reference-base depth planes (QV/Alignments.java:89-150, DirectionalAlignments.java:20-28) ----
+// One thread per (choice, sequence alignment); walks its blocks and adds (int)(weight*100) for every aligned
+// reference position whose query base can match it, where weight = 1/numChoices/numMatesCoveringPosition.
+struct CountsD {
+  int32_t* planes;            // [contig_off[c]*4 + ((region*2+dir)*len + pos)]
+  const int64_t* contig_off;  // prefix of contig lengths
+  double end_fraction;
+};
+__global__ void xm_counts_kernel(RefD ref, BatchD batch, OutArena out, CountsD C, int n_queries) {
+  int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= n_queries) return;
+  const OutQuery& oq = out.q[qi];
+  if (oq.status != 0) return;
+  long long s0 = batch.first_seq[qi];
+  for (int comp = 0; comp < oq.n_comp; comp++) {
+    int nch = oq.n_choice[comp];
+    if (nch < 1) continue;
+    double weight = 1.0 / (double)nch;  // MatchDatabase.addAlignments :36-44
+    for (int k = 0; k < nch; k++) {
+      const OutChoice& ch = out.choices[oq.choice_first[comp] + k];
+      for (int s = 0; s < ch.n_sa; s++) {
+        const OutSA& sa = out.sas[ch.sa_first + s];
+        int mate = (oq.n_comp == 2) ? comp : s;
+        SeqView qv; qv.w = batch.packed + batch.seq_word_off[s0 + mate]; qv.len = batch.seq_len[s0 + mate]; qv.rc = sa.reversed;
+        SeqView rv = ref.contig(sa.contig, 0);
+        int end_len = (int)(qv.len * C.end_fraction);
+        long long base = C.contig_off[sa.contig] * 4;
+        // the other mate's reference span (contiguous alignments): positions covered by both get weight / 2
+        int o_lo = 0, o_hi = 0;
+        if (ch.n_sa == 2) {
+          const OutSA& ot = out.sas[ch.sa_first + (1 - s)];
+          const int32_t* ob = out.blocks + 4 * ot.block_first;
+          o_lo = ob[1]; o_hi = ob[4 * (ot.n_blocks - 1) + 1] + ob[4 * (ot.n_blocks - 1) + 3];
+        }
+        for (int b = 0; b < sa.n_blocks; b++) {
+          const int32_t* bl = out.blocks + 4 * (sa.block_first + b);
+          int a0 = bl[0], b0 = bl[1], al = bl[2], blen = bl[3];
+          if (al != blen) continue;  // indels are variant records, not reference-base depth
+          for (int i = 0; i < al; i++) {
+            int qa = a0 + i, rb = b0 + i;
+            if (qv.at(qa) != rv.at(rb)) continue;
+            double wgt = weight;
+            if (ch.n_sa == 2 && rb >= o_lo && rb < o_hi) wgt = wgt / 2.0;
+            int region = (qa < end_len || qa >= qv.len - end_len) ? 1 : 0;
+            int dir = sa.reversed ? 1 : 0;
+            atomicAdd(&C.planes[base + (long long)(region * 2 + dir) * rv.len + rb], (int32_t)(wgt * 100));
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- handle
+struct DevBuf {
+  void* p = nullptr; size_t cap = 0;
+  bool ensure(size_t bytes) {
+    if (bytes <= cap) return true;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); if (cudaMalloc(&p, bytes) != cudaSuccess) { p = nullptr; return false; } want = bytes; }
+    cap = want;
+    return true;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct xm_results { ResultsHost r; };
+
+struct xm_handle {
+  HostModel m;
+  int device = 0, sm_count = 148;
+  std::string err;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  // device mirror of the model
+  uint64_t mirrored_generation = ~0ull;
+  DevBuf d_words, d_word_off, d_len, d_gstart, d_tables, d_dup_off, d_dup_starts;
+  std::vector<DevBuf> d_buckets, d_positions;
+  RefD ref{}; IndexD ix{}; DupD dup{};
+  // batch staging + results + workspace
+  DevBuf d_packed, d_seq_word_off, d_seq_len, d_n_seqs, d_expected, d_per, d_first_seq, d_chunk;
+  DevBuf d_q, d_choices, d_sas, d_blocks, d_misc, d_ids_a, d_ids_b, d_ids_full, d_ws;
+  long long cap_choices = 0, cap_sas = 0, cap_blocks = 0;
+  size_t ws_budget = (size_t)24 << 30;
+  // counts
+  bool counts_enabled = false; double end_fraction = 0.1;
+  DevBuf d_planes, d_contig_off; long long n_plane_ints = 0;
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return XM_ERR_CUDA; } } while (0)
+
+static int mirror_model(xm_handle* h) {
+  HostModel& M = h->m;
+  if (h->mirrored_generation == M.generation) return XM_OK;
+  if (M.n_contigs < 1) { h->err = "reference not set"; return XM_ERR_STATE; }
+  if (!M.index_finished) { h->err = "index not set (xm_set_index_length + xm_finish_index, or xm_build_index)"; return XM_ERR_STATE; }
+  auto up = [&](DevBuf& b, const void* src, size_t bytes) -> bool {
+    if (!b.ensure(bytes ? bytes : 16)) return false;
+    if (bytes && cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    return true;
+  };
+  bool ok = up(h->d_words, M.words.data(), M.words.size() * 2) && up(h->d_word_off, M.word_off.data(), M.word_off.size() * 8) &&
+            up(h->d_len, M.len.data(), M.len.size() * 4) && up(h->d_gstart, M.gstart.data(), M.gstart.size() * 8);
+  size_t nt = (size_t)M.max_built + 1;
+  if (M.tables.size() < nt) M.tables.resize(nt);
+  h->d_buckets.resize(nt); h->d_positions.resize(nt);
+  std::vector<TableD> tabs(nt);
+  for (size_t i = 0; ok && i < nt; i++) {
+    const HostTable& T = M.tables[i];
+    tabs[i].capacity = T.capacity; tabs[i].max_count = T.max_count; tabs[i].buckets = nullptr; tabs[i].positions = nullptr;
+    if (!T.buckets.empty()) {
+      ok = up(h->d_buckets[i], T.buckets.data(), T.buckets.size() * 8) && up(h->d_positions[i], T.positions.data(), T.positions.size() * 4);
+      tabs[i].buckets = (const uint64_t*)h->d_buckets[i].p; tabs[i].positions = (const uint32_t*)h->d_positions[i].p;
+    }
+  }
+  ok = ok && up(h->d_tables, tabs.data(), nt * sizeof(TableD));
+  std::vector<int64_t> doff((size_t)M.n_contigs + 1, 0); std::vector<int32_t> dst;
+  for (int c = 0; c < M.n_contigs; c++) { if ((size_t)c < M.dup_starts.size()) dst.insert(dst.end(), M.dup_starts[(size_t)c].begin(), M.dup_starts[(size_t)c].end()); doff[(size_t)c + 1] = (int64_t)dst.size(); }
+  dst.push_back(0);
+  ok = ok && up(h->d_dup_off, doff.data(), doff.size() * 8) && up(h->d_dup_starts, dst.data(), dst.size() * 4);
+  if (!ok) { h->err = std::string("device upload failed: ") + cudaGetErrorString(cudaGetLastError()); return XM_ERR_CUDA; }
+  h->ref.n_contigs = M.n_contigs; h->ref.words = (const uint16_t*)h->d_words.p; h->ref.word_off = (const int64_t*)h->d_word_off.p;
+  h->ref.len = (const int32_t*)h->d_len.p; h->ref.gstart = (const int64_t*)h->d_gstart.p; h->ref.total_fr = M.total_fr;
+  h->ix.min_interesting = M.min_interesting; h->ix.max_built = M.max_built; h->ix.gapmers = M.gapmers; h->ix.tables = (const TableD*)h->d_tables.p;
+  h->dup.window = M.dup_window; h->dup.granularity = M.dup_granularity; h->dup.off = (const int64_t*)h->d_dup_off.p; h->dup.starts = (const int32_t*)h->d_dup_starts.p;
+  h->mirrored_generation = M.generation;
+  return XM_OK;
+}
+
+extern "C" {
+
+int xm_create(const xm_params* p, int device, xm_handle** out) {
+  if (!p || !out) return XM_ERR_ARG;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1 || device < 0 || device >= n) {
+    fprintf(stderr, "xmapper_b200: no CUDA device %d (this library has no CPU path)\n", device);
+    return XM_ERR_CUDA;
+  }
+  xm_handle* h = new xm_handle();
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete h; return XM_ERR_CUDA; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  h->sm_count = prop.multiProcessorCount;
+  cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3);
+  size_t stack = 32 * 1024;
+  if (const char* e = getenv("XM_STACK_BYTES")) stack = (size_t)atoll(e);
+  cudaDeviceSetLimit(cudaLimitStackSize, stack);
+  if (const char* e = getenv("XM_WS_BYTES")) h->ws_budget = (size_t)atoll(e);
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && h->ws_budget > free_b / 3) h->ws_budget = free_b / 3;
+  Params& q = h->m.prm;
+  q.mutation = p->mutation_penalty; q.ins_start = p->insertion_start_penalty; q.ins_ext = p->insertion_extension_penalty;
+  q.del_start = p->deletion_start_penalty; q.del_ext = p->deletion_extension_penalty; q.max_error_rate = p->max_error_rate;
+  q.unaligned = p->unaligned_penalty; q.ambiguity = p->ambiguity_penalty; q.span = p->max_penalty_span;
+  q.max_num_matches = p->max_num_matches; q.start_free = 0;
+  h->m.gapmers = p->enable_gapmers ? 1 : 0;
+  *out = h;
+  return XM_OK;
+}
+
+void xm_destroy(xm_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  DevBuf* bufs[] = {&h->d_words, &h->d_word_off, &h->d_len, &h->d_gstart, &h->d_tables, &h->d_dup_off, &h->d_dup_starts, &h->d_packed, &h->d_seq_word_off,
+                    &h->d_seq_len, &h->d_n_seqs, &h->d_expected, &h->d_per, &h->d_first_seq, &h->d_chunk, &h->d_q, &h->d_choices, &h->d_sas, &h->d_blocks,
+                    &h->d_misc, &h->d_ids_a, &h->d_ids_b, &h->d_ids_full, &h->d_ws, &h->d_planes, &h->d_contig_off};
+  for (DevBuf* b : bufs) b->release();
+  for (auto& b : h->d_buckets) b.release();
+  for (auto& b : h->d_positions) b.release();
+  if (h->stream) cudaStreamDestroy(h->stream);
+  cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3);
+  delete h;
+}
+const char* xm_last_error(const xm_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int xm_set_reference(xm_handle* h, int32_t n, const uint16_t* const* packed4, const int32_t* lengths) {
+  if (!h || n < 1 || !packed4 || !lengths) return XM_ERR_ARG;
+  long long total = 0;
+  for (int i = 0; i < n; i++) { if (lengths[i] < 1) { h->err = "contig of length < 1"; return XM_ERR_ARG; } total += lengths[i]; }
+  if (2 * total >= (1LL << 32)) { h->err = "reference too large for 32-bit global positions"; return XM_ERR_ARG; }
+  h->m.set_reference(n, packed4, lengths);
+  h->counts_enabled = false;
+  return XM_OK;
+}
+int xm_set_index_length(xm_handle* h, int32_t n_used, int32_t capacity, int32_t max_count, const int64_t* offsets, const uint8_t* overfull, const uint32_t* positions) {
+  if (!h || n_used < 0 || capacity < 1 || !offsets) return XM_ERR_ARG;
+  if (max_count > 32766) { h->err = "max_count > 32766"; return XM_ERR_ARG; }
+  h->m.set_index_length(n_used, capacity, max_count, offsets, overfull, positions);
+  return XM_OK;
+}
+int xm_finish_index(xm_handle* h, int32_t min_interesting, int32_t max_built) {
+  if (!h || min_interesting < 1 || max_built < 0) return XM_ERR_ARG;
+  h->m.finish_index(min_interesting, max_built);
+  return XM_OK;
+}
+int xm_build_index(xm_handle* h, int32_t max_used, int32_t n_threads) {
+  if (!h) return XM_ERR_ARG;
+  if (h->m.n_contigs < 1) { h->err = "reference not set"; return XM_ERR_STATE; }
+  if (!h->m.build_index(max_used, n_threads, h->err)) return XM_ERR_ARG;
+  return XM_OK;
+}
+int xm_get_index_length(xm_handle* h, int32_t n, int32_t* capacity, int32_t* max_count, int64_t* n_positions, int64_t* offsets, uint8_t* overfull, uint32_t* positions) {
+  if (!h || n < 0 || n > h->m.max_built || (size_t)n >= h->m.tables.size()) return XM_ERR_ARG;
+  int c, m; int64_t np;
+  h->m.get_index_length(n, c, m, np, offsets, overfull, positions);
+  if (capacity) *capacity = c;
+  if (max_count) *max_count = m;
+  if (n_positions) *n_positions = np;
+  return XM_OK;
+}
+int xm_index_info(xm_handle* h, int32_t* mi, int32_t* mb) { if (!h) return XM_ERR_ARG; if (mi) *mi = h->m.min_interesting; if (mb) *mb = h->m.max_built; return XM_OK; }
+int xm_set_duplications(xm_handle* h, int32_t window, double granularity, int32_t contig, int32_t n, const int32_t* starts) {
+  if (!h || window < 1 || contig < 0 || contig >= h->m.n_contigs || n < 0) return XM_ERR_ARG;
+  h->m.set_duplications(window, granularity, contig, n, starts);
+  return XM_OK;
+}
+int xm_build_duplications(xm_handle* h, int32_t min_len, int32_t max_len, int32_t min_copies, int32_t window) {
+  if (!h || window < 1) return XM_ERR_ARG;
+  if (!h->m.index_finished) { h->err = "index not set"; return XM_ERR_STATE; }
+  h->m.build_duplications(min_len, max_len, min_copies, window);
+  return XM_OK;
+}
+int xm_get_duplications(xm_handle* h, int32_t contig, int32_t* n, int32_t* starts) {
+  if (!h || contig < 0 || contig >= h->m.n_contigs) return XM_ERR_ARG;
+  auto& v = h->m.dup_starts[(size_t)contig];
+  if (n) *n = (int)v.size();
+  if (starts) for (size_t i = 0; i < v.size(); i++) starts[i] = v[i];
+  return XM_OK;
+}
+
+int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, int64_t n_words, const int64_t* d_seq_word_off, const int32_t* d_seq_len,
+                          const uint8_t* d_n_seqs, const double* d_expected, const double* d_per, int32_t max_seq_len, xm_results** out) {
+  if (!h || nq < 0 || !out) return XM_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  int rc = mirror_model(h);
+  if (rc != XM_OK) return rc;
+  (void)n_words;
+  cudaStream_t st = h->stream;
+  xm_results* R = new xm_results();
+  R->r.stats.assign(XM_STAT_COUNT, 0);
+  if (nq == 0) { R->r.assemble(0, nullptr, nullptr, nullptr, nullptr); *out = R; return XM_OK; }
+  // first_seq = exclusive scan of n_seqs
+  const int chunk = 4096;
+  int n_chunks = (nq + chunk - 1) / chunk;
+  if (!h->d_first_seq.ensure(((size_t)nq + 1) * 8) || !h->d_chunk.ensure((size_t)n_chunks * 8)) { h->err = "out of device memory"; return XM_ERR_CUDA; }
+  CK(cudaEventRecord(h->ev0, st));
+  xm_chunk_sums_kernel<<<(n_chunks + 127) / 128, 128, 0, st>>>(d_n_seqs, nq, chunk, (long long*)h->d_chunk.p);
+  std::vector<long long> sums((size_t)n_chunks);
+  CK(cudaMemcpyAsync(sums.data(), h->d_chunk.p, (size_t)n_chunks * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  long long acc = 0;
+  for (int i = 0; i < n_chunks; i++) { long long v = sums[(size_t)i]; sums[(size_t)i] = acc; acc += v; }
+  long long n_seqs_total = acc;
+  CK(cudaMemcpyAsync(h->d_chunk.p, sums.data(), (size_t)n_chunks * 8, cudaMemcpyHostToDevice, st));
+  xm_chunk_scan_kernel<<<(n_chunks + 127) / 128, 128, 0, st>>>(d_n_seqs, nq, chunk, (const long long*)h->d_chunk.p, (int64_t*)h->d_first_seq.p);
+  int launches = 2;
+
+  // result arena
+  long long want_c = (long long)nq * 2 + 4096, want_s = n_seqs_total * 2 + 4096, want_b = n_seqs_total * 6 + 16384;
+  if (h->cap_choices < want_c) { if (!h->d_choices.ensure((size_t)want_c * sizeof(OutChoice))) { h->err = "out of device memory"; return XM_ERR_CUDA; } h->cap_choices = want_c; }
+  if (h->cap_sas < want_s) { if (!h->d_sas.ensure((size_t)want_s * sizeof(OutSA))) { h->err = "out of device memory"; return XM_ERR_CUDA; } h->cap_sas = want_s; }
+  if (h->cap_blocks < want_b) { if (!h->d_blocks.ensure((size_t)want_b * 16)) { h->err = "out of device memory"; return XM_ERR_CUDA; } h->cap_blocks = want_b; }
+  if (!h->d_q.ensure((size_t)nq * sizeof(OutQuery)) || !h->d_misc.ensure(256) || !h->d_ids_a.ensure((size_t)nq * 4) || !h->d_ids_b.ensure((size_t)nq * 4) || !h->d_ids_full.ensure((size_t)nq * 4)) {
+    h->err = "out of device memory"; return XM_ERR_CUDA;
+  }
+  // misc: [0..2] used (u64) [3..9] stats (u64) then ints: ticket, n_need_more, n_out_full
+  CK(cudaMemsetAsync(h->d_misc.p, 0, 256, st));
+  unsigned long long* d_used = (unsigned long long*)h->d_misc.p;
+  unsigned long long* d_stats = d_used + 3;
+  int* d_ints = (int*)(d_used + 12);
+
+  LaunchD L;
+  L.ref = h->ref; L.ix = h->ix; L.dup = h->dup; L.prm = h->m.prm;
+  L.batch.n_queries = nq; L.batch.packed = d_packed; L.batch.seq_word_off = d_seq_word_off; L.batch.seq_len = d_seq_len;
+  L.batch.first_seq = (const int64_t*)h->d_first_seq.p; L.batch.expected_inner = d_expected; L.batch.per_penalty = d_per;
+  L.out.q = (OutQuery*)h->d_q.p; L.out.choices = (OutChoice*)h->d_choices.p; L.out.cap_choices = h->cap_choices;
+  L.out.sas = (OutSA*)h->d_sas.p; L.out.cap_sas = h->cap_sas; L.out.blocks = (int32_t*)h->d_blocks.p; L.out.cap_blocks = h->cap_blocks;
+  L.out.used = d_used; L.out.stats = d_stats;
+  L.ticket = d_ints; L.n_need_more = d_ints + 1; L.n_out_full = d_ints + 2;
+  L.out_full = (int32_t*)h->d_ids_full.p;
+
+  const int block = 128;
+  const int32_t* ids = nullptr;
+  int n_ids = nq;
+  int32_t* next_ids = (int32_t*)h->d_ids_a.p;
+  float align_ms_tier0 = 0;
+  for (int round = 0; round < 4; round++) {  // extra rounds only after growing the result arena
+    for (int tier = 0; tier < XM_NUM_TIERS && n_ids > 0; tier++) {
+      long long arena = tier_arena_bytes(tier, max_seq_len, 2);
+      long long max_threads = (long long)(h->ws_budget / (size_t)arena);
+      long long threads = (long long)h->sm_count * 512;
+      if (threads > max_threads) threads = max_threads;
+      if (threads > n_ids) threads = n_ids;
+      int blocks = (int)((threads + block - 1) / block);
+      if (blocks < 1) blocks = 1;
+      if ((long long)blocks * block * arena > (long long)h->ws_budget && blocks > 1) blocks = (int)(h->ws_budget / (size_t)(arena * block));
+      if (blocks < 1) { h->err = "workspace budget too small for one block"; return XM_ERR_CUDA; }
+      if (!h->d_ws.ensure((size_t)blocks * block * (size_t)arena)) { h->err = "out of device memory (workspace)"; return XM_ERR_CUDA; }
+      CK(cudaMemsetAsync(d_ints, 0, 8, st));  // ticket, n_need_more
+      L.ids = ids; L.n_ids = n_ids; L.need_more = next_ids; L.arenas = (char*)h->d_ws.p; L.arena_bytes = arena; L.last_tier = (tier == XM_NUM_TIERS - 1);
+      bool time_it = (round == 0 && tier == 0);
+      if (time_it) CK(cudaEventRecord(h->ev2, st));
+      xm_align_kernel<<<blocks, block, 0, st>>>(L);
+      if (time_it) CK(cudaEventRecord(h->ev3, st));
+      launches++;
+      CK(cudaGetLastError());
+      R->r.stats[XM_STAT_TIER0_QUERIES + tier] += n_ids;
+      int counts[3];
+      CK(cudaMemcpyAsync(counts, d_ints, 12, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (time_it) cudaEventElapsedTime(&align_ms_tier0, h->ev2, h->ev3);
+      ids = next_ids; n_ids = counts[1];
+      next_ids = (next_ids == (int32_t*)h->d_ids_a.p) ? (int32_t*)h->d_ids_b.p : (int32_t*)h->d_ids_a.p;
+    }
+    int counts[3];
+    CK(cudaMemcpy(counts, d_ints, 12, cudaMemcpyDeviceToHost));
+    if (counts[2] == 0) break;
+    // result arena overflow: grow (keeping what was written) and re-run the affected queries
+    unsigned long long used[3];
+    CK(cudaMemcpy(used, d_used, 24, cudaMemcpyDeviceToHost));
+    auto grow = [&](DevBuf& b, long long& cap, unsigned long long& u, size_t elem) -> bool {
+      unsigned long long keep = u < (unsigned long long)cap ? u : (unsigned long long)cap;
+      long long ncap = (long long)(2 * (u > (unsigned long long)cap ? u : (unsigned long long)cap)) + 4096;
+      void* np = nullptr;
+      if (cudaMalloc(&np, (size_t)ncap * elem) != cudaSuccess) return false;
+      cudaMemcpy(np, b.p, (size_t)keep * elem, cudaMemcpyDeviceToDevice);
+      cudaFree(b.p); b.p = np; b.cap = (size_t)ncap * elem; cap = ncap; u = keep;
+      return true;
+    };
+    if (!grow(h->d_choices, h->cap_choices, used[0], sizeof(OutChoice)) || !grow(h->d_sas, h->cap_sas, used[1], sizeof(OutSA)) || !grow(h->d_blocks, h->cap_blocks, used[2], 16)) {
+      h->err = "out of device memory (results)"; return XM_ERR_CUDA;
+    }
+    CK(cudaMemcpy(d_used, used, 24, cudaMemcpyHostToDevice));
+    L.out.choices = (OutChoice*)h->d_choices.p; L.out.cap_choices = h->cap_choices; L.out.sas = (OutSA*)h->d_sas.p; L.out.cap_sas = h->cap_sas;
+    L.out.blocks = (int32_t*)h->d_blocks.p; L.out.cap_blocks = h->cap_blocks;
+    // the out_full list becomes the id list of the next round (copy it, the kernel will append to it again)
+    CK(cudaMemcpy(h->d_ids_a.p, h->d_ids_full.p, (size_t)counts[2] * 4, cudaMemcpyDeviceToDevice));
+    CK(cudaMemset(d_ints + 2, 0, 4));
+    ids = (const int32_t*)h->d_ids_a.p; n_ids = counts[2]; next_ids = (int32_t*)h->d_ids_b.p;
+  }
+  if (h->counts_enabled) {
+    CountsD C; C.planes = (int32_t*)h->d_planes.p; C.contig_off = (const int64_t*)h->d_contig_off.p; C.end_fraction = h->end_fraction;
+    xm_counts_kernel<<<(nq + 127) / 128, 128, 0, st>>>(h->ref, L.batch, L.out, C, nq);
+    launches++;
+  }
+  CK(cudaEventRecord(h->ev1, st));
+  // D2H
+  unsigned long long misc[12];
+  CK(cudaMemcpyAsync(misc, h->d_misc.p, sizeof(misc), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  std::vector<OutQuery> oq((size_t)nq);
+  unsigned long long uc = misc[0] < (unsigned long long)h->cap_choices ? misc[0] : (unsigned long long)h->cap_choices;
+  unsigned long long us = misc[1] < (unsigned long long)h->cap_sas ? misc[1] : (unsigned long long)h->cap_sas;
+  unsigned long long ub = misc[2] < (unsigned long long)h->cap_blocks ? misc[2] : (unsigned long long)h->cap_blocks;
+  std::vector<OutChoice> choices((size_t)uc + 1); std::vector<OutSA> sas((size_t)us + 1); std::vector<int32_t> blocks(((size_t)ub + 1) * 4);
+  CK(cudaMemcpyAsync(oq.data(), h->d_q.p, (size_t)nq * sizeof(OutQuery), cudaMemcpyDeviceToHost, st));
+  if (uc) CK(cudaMemcpyAsync(choices.data(), h->d_choices.p, (size_t)uc * sizeof(OutChoice), cudaMemcpyDeviceToHost, st));
+  if (us) CK(cudaMemcpyAsync(sas.data(), h->d_sas.p, (size_t)us * sizeof(OutSA), cudaMemcpyDeviceToHost, st));
+  if (ub) CK(cudaMemcpyAsync(blocks.data(), h->d_blocks.p, (size_t)ub * 16, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  R->r.assemble(nq, oq.data(), choices.data(), sas.data(), blocks.data());
+  R->r.stats[XM_STAT_KERNEL_NS] = (int64_t)((double)ms * 1e6);
+  R->r.stats[XM_STAT_ALIGN_KERNEL_NS] = (int64_t)((double)align_ms_tier0 * 1e6);
+  R->r.stats[XM_STAT_LAUNCHES] = launches;
+  R->r.stats[XM_STAT_PROBES] = (int64_t)misc[3]; R->r.stats[XM_STAT_SEEDS] = (int64_t)misc[4]; R->r.stats[XM_STAT_HITS] = (int64_t)misc[5];
+  R->r.stats[XM_STAT_STRAIGHT] = (int64_t)misc[6]; R->r.stats[XM_STAT_PATH_CALLS] = (int64_t)misc[7]; R->r.stats[XM_STAT_PATH_STEPS] = (int64_t)misc[8];
+  R->r.stats[XM_STAT_PATH_CELLS] = (int64_t)misc[9];
+  R->r.stats[XM_STAT_D2H_BYTES] = (int64_t)((size_t)nq * sizeof(OutQuery) + uc * sizeof(OutChoice) + us * sizeof(OutSA) + ub * 16 + sizeof(misc));
+  *out = R;
+  for (int i = 0; i < nq; i++) if (oq[(size_t)i].status != 0) { h->err = "at least one query could not be aligned on the device (see q_status)"; return XM_ERR_QUERY; }
+  return XM_OK;
+}
+
+int xm_align_batch(xm_handle* h, int32_t nq, const uint16_t* packed4, const int64_t* seq_word_off, const int32_t* seq_len, const uint8_t* n_seqs,
+                   const double* expected_inner, const double* per_penalty, xm_results** out) {
+  if (!h || nq < 0 || !out || (nq > 0 && (!packed4 || !seq_word_off || !seq_len || !n_seqs))) return XM_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  long long n_seqs_total = 0;
+  for (int i = 0; i < nq; i++) { if (n_seqs[i] < 1 || n_seqs[i] > 2) { h->err = "n_seqs_per_query must be 1 or 2"; return XM_ERR_ARG; } n_seqs_total += n_seqs[i]; }
+  int max_len = 1;
+  for (long long s = 0; s < n_seqs_total; s++) if (seq_len[s] > max_len) max_len = seq_len[s];
+  int64_t n_words = nq > 0 ? seq_word_off[n_seqs_total] : 0;
+  std::vector<double> zeros;
+  if (!expected_inner || !per_penalty) { zeros.assign((size_t)nq + 1, 0.0); }
+  if (!h->d_packed.ensure((size_t)n_words * 2 + 16) || !h->d_seq_word_off.ensure(((size_t)n_seqs_total + 1) * 8) || !h->d_seq_len.ensure((size_t)n_seqs_total * 4 + 16) ||
+      !h->d_n_seqs.ensure((size_t)nq + 16) || !h->d_expected.ensure((size_t)nq * 8 + 16) || !h->d_per.ensure((size_t)nq * 8 + 16)) { h->err = "out of device memory"; return XM_ERR_CUDA; }
+  cudaStream_t st = h->stream;
+  if (nq > 0) {
+    CK(cudaMemcpyAsync(h->d_packed.p, packed4, (size_t)n_words * 2, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_seq_word_off.p, seq_word_off, ((size_t)n_seqs_total + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_seq_len.p, seq_len, (size_t)n_seqs_total * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_n_seqs.p, n_seqs, (size_t)nq, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_expected.p, expected_inner ? expected_inner : zeros.data(), (size_t)nq * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_per.p, per_penalty ? per_penalty : zeros.data(), (size_t)nq * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  int rc = xm_align_batch_device(h, nq, (const uint16_t*)h->d_packed.p, n_words, (const int64_t*)h->d_seq_word_off.p, (const int32_t*)h->d_seq_len.p,
+                                 (const uint8_t*)h->d_n_seqs.p, (const double*)h->d_expected.p, (const double*)h->d_per.p, max_len, out);
+  if (*out) (*out)->r.stats[XM_STAT_H2D_BYTES] = (int64_t)((size_t)n_words * 2 + ((size_t)n_seqs_total + 1) * 8 + (size_t)n_seqs_total * 4 + (size_t)nq * 17);
+  return rc;
+}
+
+int64_t xm_results_array(const xm_results* r, int which, const void** ptr) { if (!r || !ptr) return -1; return r->r.array(which, ptr); }
+void xm_release_results(xm_results* r) { delete r; }
+
+int xm_counts_enable(xm_handle* h, double query_end_fraction) {
+  if (!h || h->m.n_contigs < 1) return XM_ERR_STATE;
+  CK(cudaSetDevice(h->device));
+  std::vector<int64_t> off((size_t)h->m.n_contigs + 1, 0);
+  for (int c = 0; c < h->m.n_contigs; c++) off[(size_t)c + 1] = off[(size_t)c] + h->m.len[(size_t)c];
+  h->n_plane_ints = off[(size_t)h->m.n_contigs] * 4;
+  if (!h->d_planes.ensure((size_t)h->n_plane_ints * 4) || !h->d_contig_off.ensure(off.size() * 8)) { h->err = "out of device memory (count planes)"; return XM_ERR_CUDA; }
+  CK(cudaMemset(h->d_planes.p, 0, (size_t)h->n_plane_ints * 4));
+  CK(cudaMemcpy(h->d_contig_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice));
+  h->end_fraction = query_end_fraction; h->counts_enabled = true;
+  return XM_OK;
+}
+int xm_counts_device_ptr(xm_handle* h, void** d_ptr, int64_t* n_int32) {
+  if (!h || !h->counts_enabled) return XM_ERR_STATE;
+  if (d_ptr) *d_ptr = h->d_planes.p;
+  if (n_int32) *n_int32 = h->n_plane_ints;
+  return XM_OK;
+}
+int xm_counts_fetch(xm_handle* h, int32_t contig, int32_t* out) {
+  if (!h || !h->counts_enabled || contig < 0 || contig >= h->m.n_contigs || !out) return XM_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  long long off = 0;
+  for (int c = 0; c < contig; c++) off += h->m.len[(size_t)c];
+  CK(cudaMemcpy(out, (int32_t*)h->d_planes.p + off * 4, (size_t)h->m.len[(size_t)contig] * 16, cudaMemcpyDeviceToHost));
+  return XM_OK;
+}
+
+}  // extern "C"

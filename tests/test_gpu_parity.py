@@ -1,0 +1,93 @@
+"""Parity tests proper: the CUDA library through its C ABI vs the oracle, bit for bit (integers, blocks, doubles)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import parity
+import xm_oracle as xo
+from mapper_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+V = json.load(open(os.path.join(HERE, "golden", "junit_vectors.json")))
+
+
+def gpu_from_oracle(db, params, max_used, window, upload_index, upload_dups):
+    g = capi.XMapper(params, device=0)
+    parity.feed_from_oracle(g, db, max_used, window, upload_index, upload_dups)
+    if not upload_index:
+        g.build_index(max_used)
+    if not upload_dups:
+        g.build_duplications(-1, -1, 2, window)
+    return g
+
+
+def test_junit_api_cases_on_gpu():
+    """Every Api.alignOnce case of the reference's AlignerWorker_Test (host uploads its tables, as the Java host would)."""
+    ran = 0
+    for case in V["api_cases"]:
+        if any(ch not in "ACGT" for s in case["seqs"] for ch in s):
+            continue
+        db = xo.Oracle([("reference-0", case["reference"])], dup=dict(min_copies=2, window=1))
+        batch = parity.batch_from_texts([case["seqs"]], [case["expected_inner"]], [case["per_penalty"]])
+        g = gpu_from_oracle(db, case["params"], max(len(s) for s in case["seqs"]) + 2, 1, True, True)
+        got = g.align_batch(batch, strict=True)
+        want = db.align_batch(case["params"], batch)
+        parity.assert_same_results(want, got, case["name"])
+        n = got["comp_choice_off"][1] - got["comp_choice_off"][0] if len(got["comp_choice_off"]) == 2 else 0
+        assert n == case["expect"]["count"], case["name"]
+        g.close()
+        ran += 1
+    assert ran >= 25
+
+
+@pytest.mark.parametrize("paired", [False, True], ids=["single", "paired"])
+def test_random_reads_vs_oracle(paired):
+    ref = synth.random_reference(1000000, seed=41, n_contigs=3, repeat_fraction=0.06, repeat_len=(200, 2000))
+    db = xo.Oracle([(n, synth.codes_to_text(s)) for n, s in ref], sort_by_length=True, threads=8, dup=dict(min_copies=2, window=1000))
+    contigs = [db.contig(i) for i in range(db.num_contigs())]
+    batch = synth.simulate_reads(contigs, 30000, 150, seed=42 + paired, sub_rate=0.015, indel_rate=0.002, paired=paired)
+    g = gpu_from_oracle(db, synth.DEFAULT_PARAMS, 150, 1000, False, False)  # library builds index + duplications itself
+    got = g.align_batch(batch, strict=True)
+    want = db.align_batch(synth.DEFAULT_PARAMS, batch, threads=8)
+    parity.assert_same_results(want, got, "random")
+    assert got["stats"][capi.STAT["launches"]] >= 3
+    g.close()
+
+
+def test_edge_cases():
+    """Empty batch, reads shorter than any seed, reads hanging off contig ends, a read with N (rejected loudly)."""
+    ref = synth.random_reference(50000, seed=51, n_contigs=2)
+    db = xo.Oracle([(n, synth.codes_to_text(s)) for n, s in ref], sort_by_length=True, dup=dict(min_copies=2, window=1000))
+    g = gpu_from_oracle(db, synth.DEFAULT_PARAMS, 200, 1000, False, False)
+    empty = parity.batch_from_texts([])
+    r = g.align_batch(empty, strict=True)
+    assert len(r["q_status"]) == 0
+    c0 = synth.codes_to_text(db.contig(0)[1])
+    queries = [["ACGT"], [c0[:60]], [c0[-80:] + "ACGTACGTACGTAAAC"], ["TTTTGGGG" + c0[:90]], [c0[1000:1200]], [c0[2000:2100], c0[2300:2400]]]
+    batch = parity.batch_from_texts(queries, [0, 0, 0, 0, 0, 300], [1, 1, 1, 1, 1, 50])
+    got = g.align_batch(batch, strict=True)
+    want = db.align_batch(synth.DEFAULT_PARAMS, batch)
+    parity.assert_same_results(want, got, "edges")
+    bad = parity.batch_from_texts([[c0[100:150] + "N" + c0[151:220]]])
+    r = g.align_batch(bad)
+    assert r["q_status"][0] in (0, -2)
+    g.close()
+
+
+def test_library_index_builder_on_gpu_box():
+    ref = synth.random_reference(300000, seed=61, n_contigs=2, repeat_fraction=0.1, repeat_len=(100, 800))
+    db = xo.Oracle([(n, synth.codes_to_text(s)) for n, s in ref], sort_by_length=True, dup=dict(min_copies=2, window=1000))
+    built = db.build_through(100)
+    g = capi.XMapper(synth.DEFAULT_PARAMS, device=0)
+    parity.feed_reference(g, db)
+    g.build_index(100)
+    mi, mb = g.index_info()
+    assert mi == db.min_interesting()
+    for n in range(1, min(built, mb) + 1):
+        t0, t1 = db.table(n), g.get_index_length(n)
+        assert t0["capacity"] == t1["capacity"] and t0["max_count"] == t1["max_count"]
+        assert np.array_equal(t0["overfull"], t1["overfull"]) and np.array_equal(t0["positions"], t1["positions"])
+    g.close()
