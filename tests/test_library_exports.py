@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def declared_symbols():
     text = open(os.path.join(ROOT, "include", "xmapper_b200.h")).read()
-    return sorted(set(re.findall(r"\b(xm_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"^(?:int|void|int64_t|const char\*)\s+(xm_[a-z_]+)\s*\(", text, flags=re.M)))
 
 
 def test_header_symbols_are_exported():
