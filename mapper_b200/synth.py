@@ -153,3 +153,79 @@ def codes_to_text(codes):
 
 DEFAULT_PARAMS = dict(mutation=1.0, ins_start=1.5, ins_ext=0.6, del_start=1.5, del_ext=0.5, max_error_rate=0.1,
                       ambiguity=0.1, unaligned=0.1, max_penalty_span=0.5, max_num_matches=2147483647)  # M/Mapper.java:409-453
+
+
+def simulate_reads_fast(contigs, n_reads, read_len, seed, sub_rate=0.01, indel_rate=0.001, paired=False, inner_mean=300.0,
+                        inner_sd=30.0, per_penalty=50.0):
+    """Vectorised version of simulate_reads for fixed-length reads (same error model; different random stream).
+    Substitutions are applied with array ops; only reads that drew an indel event go through the Python loop."""
+    rng = np.random.default_rng(seed)
+    lens = np.array([len(c[1]) for c in contigs], dtype=np.int64)
+    starts = np.zeros(len(contigs) + 1, dtype=np.int64)
+    np.cumsum(lens, out=starts[1:])
+    genome = np.concatenate([c[1] for c in contigs])
+    pad = 16
+    n_mates = 2 if paired else 1
+    if paired:
+        inner = np.maximum(-100, rng.normal(inner_mean, inner_sd, size=n_reads)).astype(np.int64)
+        span = 2 * read_len + inner
+    else:
+        inner = np.zeros(n_reads, dtype=np.int64)
+        span = np.full(n_reads, read_len, dtype=np.int64)
+    cidx = rng.choice(len(contigs), size=n_reads, p=lens / lens.sum())
+    room = lens[cidx] - span - pad
+    assert (room > 0).all(), "contigs too short for the requested reads"
+    pos = (rng.random(n_reads) * room).astype(np.int64)
+    strand = rng.integers(0, 2, size=n_reads)
+    W = read_len + pad
+    out = np.zeros((n_reads, n_mates, read_len), dtype=np.uint8)
+    cols = np.arange(W, dtype=np.int64)
+    for mate in range(n_mates):
+        # fragment coordinates on the forward strand of the sampled contig; reads come from the fragment ends
+        frag_lo = starts[cidx] + pos
+        frag_hi = frag_lo + span
+        # mate 0 reads the fragment 5'->3' on its strand, mate 1 the reverse complement of the other end
+        from_left = (strand == 0) == (mate == 0)
+        idx = np.where(from_left[:, None], frag_lo[:, None] + cols[None, :], frag_hi[:, None] - 1 - cols[None, :])
+        win = genome[idx]
+        win = np.where(from_left[:, None], win, COMP[win])
+        # substitutions
+        n_sub = int(rng.binomial(n_reads * W, sub_rate))
+        where = rng.integers(0, n_reads * W, size=n_sub)
+        flat = win.reshape(-1)
+        flat[where] = CODES[(np.searchsorted(CODES, flat[where]) + rng.integers(1, 4, size=n_sub)) % 4]
+        win = flat.reshape(n_reads, W)
+        # indels
+        n_ind = rng.binomial(read_len, indel_rate, size=n_reads)
+        out[:, mate, :] = win[:, :read_len]
+        for i in np.nonzero(n_ind)[0]:
+            row = win[i]
+            pieces = []
+            prev = 0
+            for p in np.sort(rng.integers(1, read_len - 1, size=int(n_ind[i]))):
+                if p < prev:
+                    continue
+                ln = int(min(10, rng.geometric(0.5)))
+                pieces.append(row[prev:p])
+                if rng.random() < 0.5:
+                    pieces.append(CODES[rng.integers(0, 4, size=ln)])
+                    prev = p
+                else:
+                    prev = min(W, p + ln)
+            pieces.append(row[prev:])
+            r = np.concatenate(pieces)
+            if len(r) < read_len:
+                r = np.concatenate([r, CODES[rng.integers(0, 4, size=read_len - len(r))]])
+            out[i, mate, :] = r[:read_len]
+    reads2d = out.reshape(n_reads * n_mates, read_len)
+    Wd = (read_len + 3) // 4
+    m = np.zeros((n_reads * n_mates, Wd * 4), dtype=np.uint16)
+    m[:, :read_len] = reads2d
+    m = m.reshape(n_reads * n_mates, Wd, 4)
+    packed = (m[:, :, 0] | (m[:, :, 1] << 4) | (m[:, :, 2] << 8) | (m[:, :, 3] << 12)).reshape(-1).astype(np.uint16)
+    off = np.arange(n_reads * n_mates + 1, dtype=np.int64) * Wd
+    return dict(packed=packed, seq_word_off=off, seq_len=np.full(n_reads * n_mates, read_len, dtype=np.int32),
+                n_seqs=np.full(n_reads, n_mates, dtype=np.uint8),
+                expected_inner=np.full(n_reads, inner_mean if paired else 0.0, dtype=np.float64),
+                per_penalty=np.full(n_reads, per_penalty if paired else 1.0, dtype=np.float64),
+                truth=np.stack([cidx, pos, strand], axis=1))
