@@ -122,7 +122,8 @@ enum xm_array {
   XM_CHOICE_F64 = 4, XM_SA_F64 = 5,                                                     /* double */
   XM_CHOICE_INNER = 6, XM_SA_CONTIG = 7, XM_BLOCKS = 8, XM_Q_STATUS = 9,                /* int32 */
   XM_SA_REVERSED = 10,                                                                  /* uint8 */
-  XM_STATS = 11                                                                         /* int64: see xm_stat */
+  XM_STATS = 11,                                                                        /* int64: see xm_stat */
+  XM_Q_CYCLES = 12                                                                      /* int64: per-query SM clock ticks, only when XM_QCYCLES=1 (profiling aid) */
 };
 enum xm_stat {
   XM_STAT_KERNEL_NS = 0,        /* device time of all kernels of this batch (CUDA events) */
@@ -135,7 +136,8 @@ enum xm_stat {
   XM_STAT_PATH_CALLS = 9, XM_STAT_PATH_STEPS = 10, XM_STAT_PATH_CELLS = 11,
   XM_STAT_H2D_BYTES = 12, XM_STAT_D2H_BYTES = 13,
   XM_STAT_ALIGN_KERNEL_NS = 14, /* device time of the dominant kernel (xm_align_kernel, tier 0) */
-  XM_STAT_COUNT = 16
+  XM_STAT_TIER0_NS = 15, XM_STAT_TIER1_NS = 16, XM_STAT_TIER2_NS = 17, /* device time of the align kernel per workspace tier */
+  XM_STAT_COUNT = 20
 };
 int64_t xm_results_array(const xm_results* r, int which, const void** ptr);
 void xm_release_results(xm_results* r);

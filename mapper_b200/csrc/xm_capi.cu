@@ -31,6 +31,7 @@ struct LaunchD {
   int32_t* out_full; int* n_out_full;     // queries to re-run after growing the result arena
   char* arenas; long long arena_bytes;
   int last_tier;
+  long long* q_cycles;                    // optional per-query cost probe (XM_QCYCLES=1): clock64 ticks of the tier that finished it
 };
 
 __global__ void __launch_bounds__(128) xm_align_kernel(LaunchD L) {
@@ -42,6 +43,7 @@ __global__ void __launch_bounds__(128) xm_align_kernel(LaunchD L) {
     if (t >= L.n_ids) break;
     int qi = L.ids ? L.ids[t] : t;
     QueryIn q;
+    long long c0 = L.q_cycles ? clock64() : 0;
     long long s0 = L.batch.first_seq[qi];
     q.n_seqs = (int)(L.batch.first_seq[qi + 1] - s0);
     for (int s = 0; s < q.n_seqs; s++) { q.seq[s].w = L.batch.packed + L.batch.seq_word_off[s0 + s]; q.seq[s].len = L.batch.seq_len[s0 + s]; q.seq[s].rc = 0; }
@@ -59,6 +61,7 @@ __global__ void __launch_bounds__(128) xm_align_kernel(LaunchD L) {
     } else if (status == Q_OUT_FULL) { int k = atomicAdd(L.n_out_full, 1); L.out_full[k] = qi; }
     rec.status = status;
     L.out.q[qi] = rec;
+    if (L.q_cycles) L.q_cycles[qi] = clock64() - c0;
     if (status != Q_NEED_MORE && status != Q_OUT_FULL) {
       st[0] += w.st_probes; st[1] += w.st_seeds; st[2] += w.st_hits; st[3] += w.st_straight; st[4] += w.st_path_calls; st[5] += w.st_path_steps; st[6] += w.st_path_cells;
     }
@@ -170,7 +173,8 @@ struct xm_handle {
   RefD ref{}; IndexD ix{}; DupD dup{};
   // batch staging + results + workspace
   DevBuf d_packed, d_seq_word_off, d_seq_len, d_n_seqs, d_expected, d_per, d_first_seq, d_chunk;
-  DevBuf d_q, d_choices, d_sas, d_blocks, d_misc, d_ids_a, d_ids_b, d_ids_full, d_ws;
+  DevBuf d_q, d_choices, d_sas, d_blocks, d_misc, d_ids_a, d_ids_b, d_ids_full, d_ws, d_qcycles;
+  bool probe_cycles = false;
   long long cap_choices = 0, cap_sas = 0, cap_blocks = 0;
   size_t ws_budget = (size_t)24 << 30;
   // counts
@@ -239,6 +243,7 @@ int xm_create(const xm_params* p, int device, xm_handle** out) {
   if (const char* e = getenv("XM_STACK_BYTES")) stack = (size_t)atoll(e);
   cudaDeviceSetLimit(cudaLimitStackSize, stack);
   if (const char* e = getenv("XM_WS_BYTES")) h->ws_budget = (size_t)atoll(e);
+  if (const char* e = getenv("XM_QCYCLES")) h->probe_cycles = atoi(e) != 0;
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && h->ws_budget > free_b / 3) h->ws_budget = free_b / 3;
   Params& q = h->m.prm;
@@ -256,7 +261,7 @@ void xm_destroy(xm_handle* h) {
   cudaSetDevice(h->device);
   DevBuf* bufs[] = {&h->d_words, &h->d_word_off, &h->d_len, &h->d_gstart, &h->d_tables, &h->d_dup_off, &h->d_dup_starts, &h->d_packed, &h->d_seq_word_off,
                     &h->d_seq_len, &h->d_n_seqs, &h->d_expected, &h->d_per, &h->d_first_seq, &h->d_chunk, &h->d_q, &h->d_choices, &h->d_sas, &h->d_blocks,
-                    &h->d_misc, &h->d_ids_a, &h->d_ids_b, &h->d_ids_full, &h->d_ws, &h->d_planes, &h->d_contig_off};
+                    &h->d_misc, &h->d_ids_a, &h->d_ids_b, &h->d_ids_full, &h->d_ws, &h->d_qcycles, &h->d_planes, &h->d_contig_off};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : h->d_buckets) b.release();
   for (auto& b : h->d_positions) b.release();
@@ -371,12 +376,14 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
   L.out.used = d_used; L.out.stats = d_stats;
   L.ticket = d_ints; L.n_need_more = d_ints + 1; L.n_out_full = d_ints + 2;
   L.out_full = (int32_t*)h->d_ids_full.p;
+  L.q_cycles = nullptr;
+  if (h->probe_cycles) { if (!h->d_qcycles.ensure((size_t)nq * 8)) { h->err = "out of device memory"; return XM_ERR_CUDA; } L.q_cycles = (long long*)h->d_qcycles.p; }
 
   const int block = 128;
   const int32_t* ids = nullptr;
   int n_ids = nq;
   int32_t* next_ids = (int32_t*)h->d_ids_a.p;
-  float align_ms_tier0 = 0;
+  float align_ms_tier0 = 0, tier_ms[XM_NUM_TIERS] = {0};
   for (int round = 0; round < 4; round++) {  // extra rounds only after growing the result arena
     for (int tier = 0; tier < XM_NUM_TIERS && n_ids > 0; tier++) {
       long long arena = tier_arena_bytes(tier, max_seq_len, 2);
@@ -392,16 +399,16 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
       CK(cudaMemsetAsync(d_ints, 0, 8, st));  // ticket, n_need_more
       L.ids = ids; L.n_ids = n_ids; L.need_more = next_ids; L.arenas = (char*)h->d_ws.p; L.arena_bytes = arena; L.last_tier = (tier == XM_NUM_TIERS - 1);
       bool time_it = (round == 0 && tier == 0);
-      if (time_it) CK(cudaEventRecord(h->ev2, st));
+      CK(cudaEventRecord(h->ev2, st));
       xm_align_kernel<<<blocks, block, 0, st>>>(L);
-      if (time_it) CK(cudaEventRecord(h->ev3, st));
+      CK(cudaEventRecord(h->ev3, st));
       launches++;
       CK(cudaGetLastError());
       R->r.stats[XM_STAT_TIER0_QUERIES + tier] += n_ids;
       int counts[3];
       CK(cudaMemcpyAsync(counts, d_ints, 12, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
-      if (time_it) cudaEventElapsedTime(&align_ms_tier0, h->ev2, h->ev3);
+      { float t = 0; cudaEventElapsedTime(&t, h->ev2, h->ev3); tier_ms[tier] += t; if (time_it) align_ms_tier0 = t; }
       ids = next_ids; n_ids = counts[1];
       next_ids = (next_ids == (int32_t*)h->d_ids_a.p) ? (int32_t*)h->d_ids_b.p : (int32_t*)h->d_ids_a.p;
     }
@@ -457,6 +464,8 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
   R->r.stats[XM_STAT_KERNEL_NS] = (int64_t)((double)ms * 1e6);
   R->r.stats[XM_STAT_ALIGN_KERNEL_NS] = (int64_t)((double)align_ms_tier0 * 1e6);
   R->r.stats[XM_STAT_LAUNCHES] = launches;
+  for (int t = 0; t < XM_NUM_TIERS && t < 3; t++) R->r.stats[XM_STAT_TIER0_NS + t] = (int64_t)((double)tier_ms[t] * 1e6);
+  if (h->probe_cycles) { R->r.q_cycles.resize((size_t)nq); CK(cudaMemcpy(R->r.q_cycles.data(), h->d_qcycles.p, (size_t)nq * 8, cudaMemcpyDeviceToHost)); }
   R->r.stats[XM_STAT_PROBES] = (int64_t)misc[3]; R->r.stats[XM_STAT_SEEDS] = (int64_t)misc[4]; R->r.stats[XM_STAT_HITS] = (int64_t)misc[5];
   R->r.stats[XM_STAT_STRAIGHT] = (int64_t)misc[6]; R->r.stats[XM_STAT_PATH_CALLS] = (int64_t)misc[7]; R->r.stats[XM_STAT_PATH_STEPS] = (int64_t)misc[8];
   R->r.stats[XM_STAT_PATH_CELLS] = (int64_t)misc[9];

@@ -12,6 +12,7 @@ struct ResultsHost {
   std::vector<int32_t> choice_inner, sa_contig, blocks, q_status;
   std::vector<uint8_t> sa_reversed;
   std::vector<int64_t> stats;
+  std::vector<int64_t> q_cycles;  // debug probe (XM_QCYCLES=1)
 
   // q: n_queries records; choices/sas/blocks: host copies of the arena
   void assemble(int n_queries, const OutQuery* q, const OutChoice* choices, const OutSA* sas, const int32_t* blk) {
@@ -56,6 +57,7 @@ struct ResultsHost {
       case 9: *ptr = q_status.data(); return (int64_t)q_status.size();
       case 10: *ptr = sa_reversed.data(); return (int64_t)sa_reversed.size();
       case 11: *ptr = stats.data(); return (int64_t)stats.size();
+      case 12: *ptr = q_cycles.data(); return (int64_t)q_cycles.size();
     }
     return -1;
   }
