@@ -135,9 +135,12 @@ enum xm_stat {
   XM_STAT_STRAIGHT = 8,         /* StraightAligner calls */
   XM_STAT_PATH_CALLS = 9, XM_STAT_PATH_STEPS = 10, XM_STAT_PATH_CELLS = 11,
   XM_STAT_H2D_BYTES = 12, XM_STAT_D2H_BYTES = 13,
-  XM_STAT_ALIGN_KERNEL_NS = 14, /* device time of the dominant kernel (xm_align_kernel, tier 0) */
+  XM_STAT_ALIGN_KERNEL_NS = 14, /* device time of the first-pass align kernel launch */
   XM_STAT_TIER0_NS = 15, XM_STAT_TIER1_NS = 16, XM_STAT_TIER2_NS = 17, /* device time of the align kernel per workspace tier */
-  XM_STAT_COUNT = 20
+  XM_STAT_CYC_SEED = 18, XM_STAT_CYC_STRAIGHT = 19, XM_STAT_CYC_HBA = 20, XM_STAT_CYC_PATH = 21, XM_STAT_CYC_TABLES = 22, XM_STAT_CYC_SPARE = 23,
+  XM_STAT_CYC_TOTAL = 24,       /* SM clock ticks summed over queries, per phase (TOTAL only when XM_QCYCLES=1) */
+  XM_STAT_EASY_QUERIES = 25, XM_STAT_EASY_NS = 26, /* first-pass kernel: queries in, device time */
+  XM_STAT_COUNT = 28
 };
 int64_t xm_results_array(const xm_results* r, int which, const void** ptr);
 void xm_release_results(xm_results* r);

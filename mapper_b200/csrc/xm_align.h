@@ -28,7 +28,12 @@ struct MatcherD {  // M/HashBlock_Matcher.java state
   int loc_size;           // locations.size()
   uint32_t* materialized; // bit i: locations[i] != null
   int mat_words;
+  // direct-address tables of the materialised sections (HashBlock_Matcher.indexSection :40-77): entry = position
+  // relative to the section start, T_NO or T_MULTI.  A few slots per matcher; sections beyond them are scanned.
+  int16_t* tables; int table_entries, n_slots, slots_used;
+  int slot_section[8];
 };
+static const int16_t T_NO = -1, T_MULTI = -2;
 struct Analysis {  // M/AlignmentAnalysis.java
   MatcherD* matcher;
   int predicted, last_checked, confident;
@@ -37,17 +42,19 @@ struct Analysis {  // M/AlignmentAnalysis.java
 
 XM_INLINE DAln aln_null() { DAln a; a.valid = 0; a.n = 0; a.b = nullptr; a.penalty = 0; a.aligned = 0; a.ref_reversed = 0; return a; }
 
-XM_HD inline double block_penalty(const Params& p, const ACtx& c, const Blk& k) {  // AlignmentParameters.getPenalty(AlignedBlock) :106-126
+XM_FN double block_penalty(const Params& p, const ACtx& c, const Blk& k) {  // AlignmentParameters.getPenalty(AlignedBlock) :106-126
   double pen = 0;
   if (k.a_len == k.b_len) {
+    XM_NOUNROLL
     for (int i = 0; i < k.a_len; i++) pen += p.base_penalty(c.a.at(k.a_start + i), c.b.at(k.b_start + i));
   } else if (k.a_len > 0) { pen += p.ins_start; pen += p.ins_ext * k.a_len; }
   else { pen += p.del_start; pen += p.del_ext * k.b_len; }
   return pen;
 }
-XM_HD inline double block_penalty_range(const Params& p, const SeqView& a, const SeqView& b, const Blk& k, int start_b, int end_b) {  // :128-154
+XM_FN double block_penalty_range(const Params& p, const SeqView& a, const SeqView& b, const Blk& k, int start_b, int end_b) {  // :128-154
   double pen = 0;
   if (k.a_len == k.b_len) {
+    XM_NOUNROLL
     for (int i = 0; i < k.a_len; i++) { int bi = k.b_start + i; if (bi >= start_b && bi < end_b) pen += p.base_penalty(a.at(k.a_start + i), b.at(bi)); }
   } else if (k.b_start < end_b && k.b_start + k.b_len > start_b) {
     if (k.a_len > 0) { pen += p.ins_start; pen += p.ins_ext * k.a_len; } else { pen += p.del_start; pen += p.del_ext * k.b_len; }
@@ -55,9 +62,10 @@ XM_HD inline double block_penalty_range(const Params& p, const SeqView& a, const
   return pen;
 }
 // AlignmentParameters.newSequenceAlignment :73-95 — blocks must already live in scratch/store
-XM_HD inline DAln new_aln(const Params& p, const ACtx& c, Blk* blocks, int n, int ref_reversed) {
+XM_FN DAln new_aln(const Params& p, const ACtx& c, Blk* blocks, int n, int ref_reversed) {
   int aligned_len = 0;
   double total = 0;
+  XM_NOUNROLL
   for (int i = 0; i < n; i++) { total += block_penalty(p, c, blocks[i]); aligned_len += blocks[i].a_len; }
   if (n > 0 && p.start_free && blocks[0].b_len == 0) total -= p.ins_start;
   double aligned = total;
@@ -75,10 +83,11 @@ static const int M_NO = -1, M_MULTI = -2, M_UNKNOWN = -3;
 
 XM_HD inline int log4_floor_plus1(int x) {  // (int)(Math.log(x) / Math.log(4) + 1) for x >= 1, x not a power of 4 boundary-sensitive: exact integers
   int k = 0; long long p = 4;
+  XM_NOUNROLL
   while (p <= (long long)x) { k++; p *= 4; }
   return k + 1;
 }
-XM_HD inline MatcherD* matcher_new(WS& w, const ACtx& c, const Sec& rsec, int section_len) {  // :14-29
+XM_FN MatcherD* matcher_new(WS& w, const ACtx& c, const Sec& rsec, int section_len) {  // :14-29
   MatcherD* m = (MatcherD*)w.salloc(sizeof(MatcherD));
   if (!m) return nullptr;
   if (section_len < 1) section_len = 1;
@@ -94,12 +103,25 @@ XM_HD inline MatcherD* matcher_new(WS& w, const ACtx& c, const Sec& rsec, int se
   m->mat_words = words;
   m->materialized = (uint32_t*)w.salloc((long long)words * 4);
   if (!m->materialized) return nullptr;
+  XM_NOUNROLL
   for (int i = 0; i < words; i++) m->materialized[i] = 0;
+  m->tables = nullptr; m->table_entries = 0; m->n_slots = 0; m->slots_used = 0;
+  if (section_len >= 3 && section_len < 32000 && m->block_len <= 7) {
+    int entries = 1 << (2 * m->block_len);
+    int slots = imin(8, m->max_section_index + 1);
+    long long bytes = (long long)slots * entries * 2 + 16;
+    if (slots > 0 && w.scratch_top + bytes + 4096 <= w.scratch_size / 2) {  // optional: without room the sections are scanned instead
+      char* p = (char*)w.salloc(bytes);
+      p += (16 - ((uintptr_t)p & 15)) & 15;
+      m->tables = (int16_t*)p; m->table_entries = entries; m->n_slots = slots;
+    }
+  }
   return m;
 }
 XM_HD inline int matcher_encode(const SeqView& s, int index, int block_len) {  // encodeBlock :79-91
   if (index + block_len > s.len) return M_UNKNOWN;
   int sum = 0;
+  XM_NOUNROLL
   for (int i = 0; i < block_len; i++) {
     uint8_t h = s.at(index + i);
     if (bp_is_ambiguous(h)) return M_UNKNOWN;
@@ -107,12 +129,14 @@ XM_HD inline int matcher_encode(const SeqView& s, int index, int block_len) {  /
   }
   return sum;
 }
-// value of section[encoded] after indexSection(sectionIndex) :40-77
-XM_HD inline int matcher_section_value(const MatcherD& m, const SeqView& ref, int section_index, int target) {
+// indexSection(sectionIndex) :40-77, visiting every (position, encoding) the reference stores
+template <class F>
+XM_INLINE void matcher_scan_encodings(const MatcherD& m, const SeqView& ref, int section_index, F&& f) {
   int max_poss = (1 << (2 * m.block_len)) - 1;
-  int prev = M_UNKNOWN, value = M_NO;
+  int prev = M_UNKNOWN;
   int start = m.ref_start + section_index * m.section_len;
   int end = imin(start + m.section_len, m.ref_start + m.ref_len - m.block_len);
+  XM_NOUNROLL
   for (int i = start; i < end; i++) {
     int enc;
     if (prev == M_UNKNOWN) enc = matcher_encode(ref, i, m.block_len);
@@ -122,9 +146,44 @@ XM_HD inline int matcher_section_value(const MatcherD& m, const SeqView& ref, in
       else enc = ((prev * 4) & max_poss) + (nc == 1 ? 0 : nc == 2 ? 1 : nc == 4 ? 2 : 3);
     }
     if (enc == M_UNKNOWN) continue;
-    if (enc == target) { if (value == M_NO) value = i; else value = M_MULTI; }
+    f(i - start, enc);
     prev = enc;
   }
+}
+// value of section[encoded] after indexSection(sectionIndex)
+XM_FN int matcher_section_value(WS& w, MatcherD& m, const SeqView& ref, int section_index, int target) {
+  int start = m.ref_start + section_index * m.section_len;
+  if (m.tables != nullptr) {
+    int slot = -1;
+    XM_NOUNROLL
+    for (int i = 0; i < m.slots_used; i++) if (m.slot_section[i] == section_index) { slot = i; break; }
+    if (slot < 0 && m.slots_used < m.n_slots) {
+      PhaseClock pc_(&w.st_cyc[4]);
+      slot = m.slots_used++;
+      m.slot_section[slot] = section_index;
+      int16_t* t = m.tables + (long long)slot * m.table_entries;
+#if defined(__CUDA_ARCH__)
+      {  // lanes clear the table together (16 bytes per lane per round)
+        uint4 fill = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        uint4* t4 = (uint4*)t;
+        int n16 = m.table_entries / 8;
+        XM_NOUNROLL
+        for (int i = (int)(threadIdx.x & 31); i < n16; i += 32) t4[i] = fill;
+        __syncwarp();
+      }
+#else
+      XM_NOUNROLL
+      for (int i = 0; i < m.table_entries; i++) t[i] = T_NO;
+#endif
+      matcher_scan_encodings(m, ref, section_index, [&](int rel, int enc) { t[enc] = (t[enc] == T_NO) ? (int16_t)rel : T_MULTI; });
+    }
+    if (slot >= 0) {
+      int16_t v = m.tables[(long long)slot * m.table_entries + target];
+      return v == T_NO ? M_NO : v == T_MULTI ? M_MULTI : start + (int)v;
+    }
+  }
+  int value = M_NO;
+  matcher_scan_encodings(m, ref, section_index, [&](int rel, int enc) { if (enc == target) value = (value == M_NO) ? start + rel : M_MULTI; });
   return value;
 }
 XM_HD inline bool matcher_get_section(WS& w, MatcherD& m, int index) {  // getSection :203-215; false = null entry
@@ -134,12 +193,14 @@ XM_HD inline bool matcher_get_section(WS& w, MatcherD& m, int index) {  // getSe
   m.materialized[index >> 5] |= (1u << (index & 31));
   return true;
 }
-XM_HD inline int matcher_scan_section(const MatcherD& m, const ACtx& c, int query_index, int section_index) {  // :143-171
+XM_FN int matcher_scan_section(const MatcherD& m, const ACtx& c, int query_index, int section_index) {  // :143-171
   int result = M_NO;
   int start = m.ref_start + section_index * m.section_len, end = start + m.section_len;
+  XM_NOUNROLL
   for (int i = start; i < end; i++) {
     bool ok = !(i + m.block_len > m.ref_start + m.ref_len);
     // canPositionsMatch reads query/reference without bounds checks; out-of-range reads throw in the reference
+    XM_NOUNROLL
     for (int k = 0; ok && k < m.block_len; k++) {
       if (query_index + k >= c.a.len || i + k >= c.b.len) { ok = false; break; }
       if (!bp_can_match(c.a.at(query_index + k), c.b.at(i + k))) ok = false;
@@ -148,7 +209,7 @@ XM_HD inline int matcher_scan_section(const MatcherD& m, const ACtx& c, int quer
   }
   return result;
 }
-XM_HD inline int matcher_lookup(WS& w, MatcherD& m, const ACtx& c, int query_index, int min_ref, int max_ref) {  // :98-141
+XM_FN int matcher_lookup(WS& w, MatcherD& m, const ACtx& c, int query_index, int min_ref, int max_ref) {  // :98-141
   if (min_ref < 0) return M_UNKNOWN;
   if (max_ref > c.b.len) return M_UNKNOWN;
   int enc = matcher_encode(c.a, query_index, m.block_len);
@@ -156,12 +217,13 @@ XM_HD inline int matcher_lookup(WS& w, MatcherD& m, const ACtx& c, int query_ind
   int matched = M_NO;
   int min_sec = imax(0, (min_ref - m.ref_start) / m.section_len);
   int max_sec = imin(m.max_section_index, (max_ref - m.ref_start) / m.section_len);
+  XM_NOUNROLL
   for (int si = min_sec; si <= max_sec; si++) {
     bool have = matcher_get_section(w, m, si);
     if (w.status != 0) return M_UNKNOWN;
     int looked;
     if (m.section_len < 3) looked = matcher_scan_section(m, c, query_index, si);
-    else { if (have) looked = matcher_section_value(m, c.b, si, enc); else return M_UNKNOWN; }
+    else { if (have) looked = matcher_section_value(w, m, c.b, si, enc); else return M_UNKNOWN; }
     if (looked == M_UNKNOWN) return M_UNKNOWN;
     if (looked == M_MULTI) return M_MULTI;
     if (looked == M_NO) continue;
@@ -181,23 +243,26 @@ struct PathState {
   int diagonal, step, reverse, may_extend;
   int start_x, start_y, goal_x, goal_y;
   PNode* nodes; uint8_t* flags;  // flags: 1 present, 2 reachedMain, 4 reachedOther
+  const uint8_t* qa; const uint8_t* rb;  // the two sections, one code per byte
   PHeapEnt* heap; int heap_n, heap_cap; uint32_t seq;
   double active, max_interesting;
 };
-XM_INLINE uint8_t pa_qa(const PathState& s, int i) { return s.ctx.a.at(s.start_a + i); }
-XM_INLINE uint8_t pa_rb(const PathState& s, int j) { return s.ctx.b.at(s.start_b + j); }
+XM_INLINE uint8_t pa_qa(const PathState& s, int i) { return s.qa[i]; }
+XM_INLINE uint8_t pa_rb(const PathState& s, int j) { return s.rb[j]; }
 XM_INLINE bool pa_heap_less(const PHeapEnt& a, const PHeapEnt& b) { return a.pri < b.pri || (a.pri == b.pri && a.seq < b.seq); }
-XM_HD inline void pa_heap_push(WS& w, PathState& s, double pri, int x, int y) {
+XM_FN void pa_heap_push(WS& w, PathState& s, double pri, int x, int y) {
   if (s.heap_n >= s.heap_cap) { w.fail(Q_NEED_MORE); return; }
   PHeapEnt e; e.pri = pri; e.seq = s.seq++; e.x = (int16_t)x; e.y = (int16_t)y;
   int i = s.heap_n++;
+  XM_NOUNROLL
   while (i > 0) { int p = (i - 1) >> 1; if (pa_heap_less(e, s.heap[p])) { s.heap[i] = s.heap[p]; i = p; } else break; }
   s.heap[i] = e;
 }
-XM_HD inline PHeapEnt pa_heap_pop(PathState& s) {
+XM_FN PHeapEnt pa_heap_pop(PathState& s) {
   PHeapEnt top = s.heap[0];
   PHeapEnt e = s.heap[--s.heap_n];
   int i = 0;
+  XM_NOUNROLL
   while (true) {
     int l = 2 * i + 1, r = l + 1;
     if (l >= s.heap_n) break;
@@ -242,7 +307,7 @@ XM_INLINE bool pa_get(const PathState& s, int x, int y, int& idx) {
   idx = x * s.H + y;
   return (s.flags[idx] & 1) != 0;
 }
-XM_HD inline void pa_update(WS& w, PathState& s, int x, int y) {  // update :555-571 + computeUpdated :573-719
+XM_FN void pa_update(WS& w, PathState& s, int x, int y) {  // update :555-571 + computeUpdated :573-719
   if (x <= 0 || x > s.A) return;
   if (y <= 0 || y > s.B) return;
   const Params& p = s.prm;
@@ -303,7 +368,8 @@ XM_INLINE bool pa_can_remove(const Blk& b) {  // canRemoveSection :358-366
   if ((b.a_start <= 0 && b.a_len <= 0) || (b.b_start <= 0 && b.b_len <= 0)) return true;
   return false;
 }
-XM_HD inline DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Params& p, Analysis& an) {  // PathAligner.align :55-293
+XM_FN DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Params& p, Analysis& an) {  // PathAligner.align :55-293
+  PhaseClock pc_(&w.st_cyc[3]);
   long long mark = w.scratch_top;
   PathState* sp = (PathState*)w.salloc(sizeof(PathState));
   if (!sp) return aln_null();
@@ -314,11 +380,25 @@ XM_HD inline DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, c
   s.A = q.length(); s.B = r.length(); s.W = s.A + 2; s.H = s.B + 2;
   s.diagonal = s.start_b - (s.start_a + an.predicted);
   s.active = 0; s.seq = 0; s.heap_n = 0;
+  {  // unpack both sections once (lanes split the bases on the device)
+    uint8_t* qa = (uint8_t*)w.salloc(s.A + 1); uint8_t* rb = (uint8_t*)w.salloc(s.B + 1);
+    if (w.status != 0) { w.scratch_top = mark; return aln_null(); }
+#if defined(__CUDA_ARCH__)
+    for (int k = (int)(threadIdx.x & 31); k < s.A; k += 32) qa[k] = c.a.at(s.start_a + k);
+    for (int k = (int)(threadIdx.x & 31); k < s.B; k += 32) rb[k] = c.b.at(s.start_b + k);
+    __syncwarp();
+#else
+    for (int k = 0; k < s.A; k++) qa[k] = c.a.at(s.start_a + k);
+    for (int k = 0; k < s.B; k++) rb[k] = c.b.at(s.start_b + k);
+#endif
+    s.qa = qa; s.rb = rb;
+  }
   w.st_path_calls++; w.st_path_cells += (unsigned long long)s.A * (unsigned long long)s.B;
   {  // chooseSearchReverse :17-53
     int sum_mis = 0, num_mis = 0, sum_mat = 0, num_mat = 0;
     int si = imax(s.start_a, s.start_b - an.predicted), ei = imin(s.end_a, s.end_b - an.predicted);
     int length = ei - si;
+    XM_NOUNROLL
     for (int i = 0; i < length; i++) {
       int j = i - s.diagonal;
       if (j >= 0 && j < s.B) {
@@ -340,19 +420,33 @@ XM_HD inline DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, c
   if (s.heap_cap > 3 * cells + 16) s.heap_cap = (int)(3 * cells + 16);
   s.heap = (PHeapEnt*)w.salloc((long long)s.heap_cap * (long long)sizeof(PHeapEnt));
   if (w.status != 0 || s.heap_cap < 8) { w.fail(Q_NEED_MORE); w.scratch_top = mark; return aln_null(); }
+#if defined(__CUDA_ARCH__)
+  {  // lanes clear the lattice flags together; salloc keeps s.flags 8-byte aligned
+    unsigned long long* f8 = (unsigned long long*)s.flags;
+    long long n8 = (cells + 7) >> 3;
+    XM_NOUNROLL
+    for (long long i = (long long)(threadIdx.x & 31); i < n8; i += 32) f8[i] = 0ull;
+    __syncwarp();
+  }
+#else
+  XM_NOUNROLL
   for (long long i = 0; i < cells; i++) s.flags[i] = 0;
+#endif
 
   if (s.B >= s.A) {
     double sisp = p.starting_ins_start();
     if (!s.may_extend) sisp = XM_DISALLOWED;
     int cnt = imax(0, s.B - s.A) + 1;
+    XM_NOUNROLL
     for (int i = 0; i < cnt; i++) { PNode n; n.pen = 0; n.ins_x = sisp; n.ins_y = XM_DISALLOWED; pa_put(w, s, s.start_x, s.start_y + i * s.step, n, 0); }
   } else {
     int cnt = imax(0, s.A - s.B) + 1;
+    XM_NOUNROLL
     for (int i = 0; i < cnt; i++) { PNode n; n.pen = 0; n.ins_x = XM_DISALLOWED; n.ins_y = XM_DISALLOWED; pa_put(w, s, s.start_x + i * s.step, s.start_y, n, 0); }
   }
   if (s.may_extend) {
     int cnt = j2i(an.max_ins / p.del_ext);
+    XM_NOUNROLL
     for (int i = 1; i < cnt; i++) {
       int xa = s.start_x + i * s.step;
       PNode n; n.pen = i * p.unaligned; n.ins_x = XM_DISALLOWED; n.ins_y = XM_DISALLOWED;
@@ -368,6 +462,7 @@ XM_HD inline DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, c
     }
   }
   int last_x = -1, last_y = -1;
+  XM_NOUNROLL
   while (w.status == 0) {
     if (s.heap_n == 0) { w.fail(Q_INTERNAL); break; }  // priorities.poll() == null -> NullPointerException
     PHeapEnt e = pa_heap_pop(s);
@@ -386,6 +481,7 @@ XM_HD inline DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, c
   if (!tb) { w.scratch_top = mark; return aln_null(); }
   int nb = 0;
   int i = last_x, j = last_y, idx;
+  XM_NOUNROLL
   while (i != s.start_x && j != s.start_y) {
     if (!pa_get(s, i, j, idx)) { w.fail(Q_INTERNAL); break; }
     PNode node = s.nodes[idx];
@@ -393,6 +489,7 @@ XM_HD inline DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, c
     if (node.pen == node.ins_x) {
       int old_i = i;
       i -= s.step;
+      XM_NOUNROLL
       while (i != s.start_x) {
         if (!pa_get(s, i, j, idx)) { w.fail(Q_INTERNAL); break; }
         const PNode& o = s.nodes[idx];
@@ -404,6 +501,7 @@ XM_HD inline DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, c
     } else if (node.pen == node.ins_y) {
       int old_j = j;
       j -= s.step;
+      XM_NOUNROLL
       while (j != s.start_y) {
         if (!pa_get(s, i, j, idx)) { w.fail(Q_INTERNAL); break; }
         const PNode& o = s.nodes[idx];
@@ -415,6 +513,7 @@ XM_HD inline DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, c
     } else {
       int old_i = i, old_j = j;
       i -= s.step; j -= s.step;
+      XM_NOUNROLL
       while (i != s.start_x && j != s.start_y) {
         if (!pa_get(s, i, j, idx)) { w.fail(Q_INTERNAL); break; }
         const PNode& o = s.nodes[idx];
@@ -432,7 +531,9 @@ XM_HD inline DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, c
   if (!s.reverse) { for (int a = 0, b = nb - 1; a < b; a++, b--) { Blk t = tb[a]; tb[a] = tb[b]; tb[b] = t; } }
   if (nb < 1) { w.scratch_top = mark; return aln_null(); }
   // justify :307-352
+  XM_NOUNROLL
   for (int m = 1; m < nb - 1; m++) {
+    XM_NOUNROLL
     while (true) {
       Blk left = tb[m - 1], mid = tb[m], right = tb[m + 1];
       if ((mid.a_len > 0) == (mid.b_len > 0)) break;
@@ -447,6 +548,7 @@ XM_HD inline DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, c
     }
   }
   int first = 0;
+  XM_NOUNROLL
   while (true) {
     if (first >= nb) { w.fail(Q_INTERNAL); w.scratch_top = mark; return aln_null(); }  // sections.get(0) on an empty list
     if (!pa_can_remove(tb[first])) break;
@@ -457,6 +559,7 @@ XM_HD inline DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, c
   // keep the result blocks at the bottom of this call's scratch frame
   w.scratch_top = mark;
   Blk* out = (Blk*)w.salloc((long long)n_out * (long long)sizeof(Blk));
+  XM_NOUNROLL
   for (int a = 0; a < n_out; a++) out[a] = tb[first + a];  // tb lies above `out` in the same frame: forward copy is safe
   DAln res = new_aln(p, c, out, n_out, c.a_reversed_obj);
   if (res.aligned > max_int) { w.scratch_top = mark; return aln_null(); }
@@ -477,10 +580,14 @@ XM_HD inline DAln straight_alignment(WS& w, const ACtx& c, const Sec& q, const S
   b->a_start = qs; b->b_start = rs; b->a_len = qe - qs; b->b_len = re - rs;
   return new_aln(p, c, b, 1, c.a_reversed_obj);
 }
-XM_HD inline DAln straight_align(WS& w, int stage, const ACtx& c, const Sec& q, const Sec& r, const Params& p, Analysis& an) {  // StraightAligner.align :13-71
+// EASY = the first-pass kernel: it completes a query only when every alignMatch is settled by the outermost
+// StraightAligner; the first time the cascade would go deeper the query is handed to the full kernel (Q_HARD).
+template <bool EASY>
+XM_FN DAln straight_align_t(WS& w, int stage, const ACtx& c, const Sec& q, const Sec& r, const Params& p, Analysis& an) {  // StraightAligner.align :13-71
   an.last_checked = an.predicted;
   w.st_straight++;
-  DAln simple = straight_alignment(w, c, q, r, p, an);
+  DAln simple;
+  { PhaseClock pc_(&w.st_cyc[1]); simple = straight_alignment(w, c, q, r, p, an); }
   if (!simple.valid) return simple;
   double sp = simple.aligned;
   double max_interesting = q.length() * p.max_error_rate;
@@ -493,28 +600,32 @@ XM_HD inline DAln straight_align(WS& w, int stage, const ACtx& c, const Sec& q, 
   double rate = simple.aligned / q.length();
   Params sub = p;
   sub.max_error_rate = dmin(rate, p.max_error_rate);
+  if (EASY) { w.fail(Q_HARD); return aln_null(); }
   DAln a = cascade(w, stage + 1, c, q, r, sub, an);
   if (w.status != 0) return aln_null();
   if (!a.valid || a.aligned >= sp) { if (sp <= max_interesting) return simple; }
   return a;
 }
+XM_INLINE DAln straight_align(WS& w, int stage, const ACtx& c, const Sec& q, const Sec& r, const Params& p, Analysis& an) { return straight_align_t<false>(w, stage, c, q, r, p, an); }
 
 struct CountMapD {  // M/CountMap.java with a small open list instead of HashMap
   int most_key, most_count, have;
   int* keys; int* vals; int n, cap;
 };
 XM_HD inline void countmap_put(WS& w, CountMapD& m, int key, int val) {
+  XM_NOUNROLL
   for (int i = 0; i < m.n; i++) if (m.keys[i] == key) { m.vals[i] = val; return; }
   if (m.n >= m.cap) { w.fail(Q_NEED_MORE); return; }
   m.keys[m.n] = key; m.vals[m.n] = val; m.n++;
 }
-XM_HD inline void countmap_add(WS& w, CountMapD& m, int key, int value) {
+XM_FN void countmap_add(WS& w, CountMapD& m, int key, int value) {
   if (key == m.most_key || m.most_count == 0) {
     m.most_count += value; m.most_key = key;
     if (m.have) countmap_put(w, m, m.most_key, m.most_count);
   } else {
     if (!m.have) { m.have = 1; countmap_put(w, m, m.most_key, m.most_count); }
     int count = value;
+    XM_NOUNROLL
     for (int i = 0; i < m.n; i++) if (m.keys[i] == key) { count = m.vals[i] + value; break; }
     countmap_put(w, m, key, count);
     if (count > m.most_count) { m.most_key = key; m.most_count = count; }
@@ -576,8 +687,9 @@ XM_HD inline double max_ext_many_deletions(int n, double total, const Params& p)
 
 struct PenaltyAnalysisD { double min_possible, max_ins, max_del; int offset_most, num_best; };
 
-XM_HD inline PenaltyAnalysisD hba_analyze(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Params& p, Analysis& an) {  // analyzePenalty :94-283
+XM_FN PenaltyAnalysisD hba_analyze(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Params& p, Analysis& an) {  // analyzePenalty :94-283
   PenaltyAnalysisD res; res.min_possible = 0; res.max_ins = 0; res.max_del = 0; res.offset_most = 0; res.num_best = 0;
+  PhaseClock pc_(&w.st_cyc[2]);
   MatcherD* matcher = an.matcher;
   double max_interesting = p.max_error_rate * q.length();
   int num_mis = 0;
@@ -597,6 +709,7 @@ XM_HD inline PenaltyAnalysisD hba_analyze(WS& w, const ACtx& c, const Sec& q, co
   if (w.status != 0) return res;
   int bl = matcher->block_len;
   int max_block_start = q.end - bl;
+  XM_NOUNROLL
   for (int bs = q.start; bs <= max_block_start; bs++) {
     if (w.status != 0) return res;
     if (bs >= max_nonmatch_end) {
@@ -611,11 +724,13 @@ XM_HD inline PenaltyAnalysisD hba_analyze(WS& w, const ACtx& c, const Sec& q, co
       int other = position;
       int reverse_count = imin(bs - max_nonmatch_end, other);
       bool found = false;
+      XM_NOUNROLL
       for (int i = 1; i <= reverse_count; i++) {
         if (!bp_can_match(c.a.at(bs - i), c.b.at(other - i))) { num_mis++; found = true; max_nonmatch_end = bs + bl; break; }
       }
       if (!found) {
         int fwd = q.end - bs;
+        XM_NOUNROLL
         for (int i = bl; i < fwd; i++) {
           int ia = bs + i, ib = other + i;
           uint8_t ca = c.a.at(ia);
@@ -625,6 +740,7 @@ XM_HD inline PenaltyAnalysisD hba_analyze(WS& w, const ACtx& c, const Sec& q, co
         if (!found) max_nonmatch_end = q.end;
         int num_other = 0;
         int fwd2 = max_nonmatch_end - bs - bl;
+        XM_NOUNROLL
         for (int i = bl; i < fwd2; i++) {
           int ia = bs + i;
           int res2 = matcher_lookup(w, *matcher, c, ia, ia + min_off, ia + max_off + 1);
@@ -653,10 +769,11 @@ XM_HD inline PenaltyAnalysisD hba_analyze(WS& w, const ACtx& c, const Sec& q, co
   return res;
 }
 
-XM_HD inline DAln hba_align(WS& w, int stage, const ACtx& c, const Sec& q, const Sec& r_in, const Params& p, Analysis& an_in) {  // HashBlock_Aligner.align :21-81 (tail recursion as a loop)
+XM_FN DAln hba_align(WS& w, int stage, const ACtx& c, const Sec& q, const Sec& r_in, const Params& p, Analysis& an_in) {  // HashBlock_Aligner.align :21-81 (tail recursion as a loop)
   Sec r = r_in;
   Analysis cur = an_in;       // the analysis object of the current recursion level
   Analysis* anp = &an_in;     // first level mutates the caller's object (hashBlock_matcher assignment)
+  XM_NOUNROLL
   while (true) {
     double max_interesting = p.max_error_rate * q.length();
     if (q.length() > r.length()) return cascade(w, stage + 1, c, q, r, p, *anp);
@@ -682,7 +799,7 @@ XM_HD inline DAln hba_align(WS& w, int stage, const ACtx& c, const Sec& q, const
   }
 }
 
-XM_HD inline DAln block_align_piece(WS& w, const ACtx& c, const Sec& q, const Sec& r, double max_penalty, const Params& p, bool first_piece, const Analysis& parent) {  // alignPiece :215-249
+XM_FN DAln block_align_piece(WS& w, const ACtx& c, const Sec& q, const Sec& r, double max_penalty, const Params& p, bool first_piece, const Analysis& parent) {  // alignPiece :215-249
   if (max_penalty < 0) return aln_null();
   Sec rsub = r;
   if (parent.confident) {
@@ -700,7 +817,7 @@ XM_HD inline DAln block_align_piece(WS& w, const ACtx& c, const Sec& q, const Se
   child.confident = 0;
   return cascade(w, ST_BLOCK + 1, c, q, rsub, sub, child);
 }
-XM_HD inline DAln block_try_merge(WS& w, const ACtx& c, const DAln& left, const DAln& right, const Params& p) {  // doTryMerge :158-212
+XM_FN DAln block_try_merge(WS& w, const ACtx& c, const DAln& left, const DAln& right, const Params& p) {  // doTryMerge :158-212
   if (aln_end_b(left) != aln_start_b(right)) return aln_null();
   const Blk& l = left.b[left.n - 1];
   const Blk& rr = right.b[0];
@@ -711,13 +828,15 @@ XM_HD inline DAln block_try_merge(WS& w, const ACtx& c, const DAln& left, const 
   Blk* b = (Blk*)w.salloc((long long)n * (long long)sizeof(Blk));
   if (!b) return aln_null();
   int k = 0;
+  XM_NOUNROLL
   for (int i = 0; i < left.n - 1; i++) b[k++] = left.b[i];
   Blk mid; mid.a_start = l.a_start; mid.b_start = l.b_start; mid.a_len = l.a_len + rr.a_len; mid.b_len = l.b_len + rr.b_len;
   b[k++] = mid;
+  XM_NOUNROLL
   for (int i = 1; i < right.n; i++) b[k++] = right.b[i];
   return new_aln(p, c, b, n, left.ref_reversed);
 }
-XM_HD inline DAln block_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Params& p, Analysis& an) {  // BlockAligner.align :17-36
+XM_FN DAln block_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Params& p, Analysis& an) {  // BlockAligner.align :17-36
   double max_interesting = p.max_error_rate * q.length();
   // initialAlignments :39-96
   double max_initial = p.max_error_rate * c.a.len;
@@ -730,12 +849,15 @@ XM_HD inline DAln block_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, 
   DAln* cur = (DAln*)w.salloc((long long)num_blocks * (long long)sizeof(DAln));
   DAln* nxt = (DAln*)w.salloc((long long)num_blocks * (long long)sizeof(DAln));
   if (w.status != 0) return aln_null();
+  XM_NOUNROLL
   for (int i = 0; i < num_blocks; i++) cur[i] = aln_null();
   double used = 0;
   int remaining = num_blocks;
+  XM_NOUNROLL
   while (true) {
     bool failed = false, failed_then_found = false;
     int start_pos = q.start;
+    XM_NOUNROLL
     for (int i = 0; i < num_blocks; i++) {
       int end_pos = q.start + (int)((long long)q.length() * (i + 1) / num_blocks);
       if (!cur[i].valid) {
@@ -753,10 +875,13 @@ XM_HD inline DAln block_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, 
   }
   int n = num_blocks;
   bool even = false;
+  XM_NOUNROLL
   while (n > 1) {  // joinAlignments :99-144
     double used_pen = 0;
+    XM_NOUNROLL
     for (int i = 0; i < n; i++) used_pen += cur[i].aligned;
     int m = 0;
+    XM_NOUNROLL
     for (int i = 0; i < n; i += 2) {
       DAln merge;
       DAln left = cur[i];
@@ -788,6 +913,7 @@ XM_HD inline DAln cascade(WS& w, int stage, const ACtx& c, const Sec& q, const S
     case ST_STRAIGHT1: case ST_STRAIGHT2: case ST_STRAIGHT3: return straight_align(w, stage, c, q, r, p, an);
     case ST_SKIP: {  // SkipHighAmbiguity_Aligner.align :13-28
       int amb = 0;
+      XM_NOUNROLL
       for (int i = r.start; i < r.end; i++) if (bp_is_ambiguous(c.b.at(i))) amb++;
       if (amb >= r.length() / 4) return aln_null();
       return cascade(w, stage + 1, c, q, r, p, an);
@@ -822,7 +948,8 @@ XM_INLINE int sa_start_a(const SAStore& s) { return s.blk[0].a_start; }
 XM_INLINE int sa_end_a(const SAStore& s) { return s.blk[s.n_blk - 1].a_start + s.blk[s.n_blk - 1].a_len; }
 
 // QueryMatch_Aligner.alignMatch(SequenceMatch, parameters) :412-462. c describes a and b.
-XM_HD inline DAln qma_align_match(WS& w, const ACtx& c, const SM& sm, const Params& p, double per_penalty) {
+template <bool EASY>
+XM_FN DAln qma_align_match(WS& w, const ACtx& c, const SM& sm, const Params& p, double per_penalty) {
   int a_len = c.a.len, b_len = c.b.len;
   int sb = imax(0, sm.offset), eb = imin(sm.offset + a_len, b_len);
   Sec q; q.start = sb - sm.offset; q.end = eb - sm.offset;
@@ -841,6 +968,7 @@ XM_HD inline DAln qma_align_match(WS& w, const ACtx& c, const SM& sm, const Para
   Analysis an; an.matcher = nullptr; an.last_checked = 0;
   an.max_ins = max_interesting - p.ins_start; an.max_del = max_interesting - p.del_start;
   an.predicted = best_offset; an.confident = sm.from_hash ? 1 : 0;
+  if (EASY) return straight_align_t<true>(w, ST_STRAIGHT1, c, q, r, p, an);
   return cascade(w, ST_STRAIGHT1, c, q, r, p, an);
 }
 XM_HD inline bool sa_store_from(WS& w, SAStore& out, const DAln& a, int contig, int a_mate, int a_rev) {
@@ -848,11 +976,13 @@ XM_HD inline bool sa_store_from(WS& w, SAStore& out, const DAln& a, int contig, 
   out.penalty = a.penalty; out.aligned = a.aligned;
   out.blk = (Blk*)store_alloc(w, (long long)a.n * (long long)sizeof(Blk));
   if (!out.blk) return false;
+  XM_NOUNROLL
   for (int i = 0; i < a.n; i++) out.blk[i] = a.b[i];
   return true;
 }
 XM_HD inline int sa_len_a_before(const SAStore& s, int index_b) {  // SequenceAlignment.getLengthABefore :98-117
   int total = 0;
+  XM_NOUNROLL
   for (int i = 0; i < s.n_blk; i++) {
     const Blk& b = s.blk[i];
     if (index_b <= b.b_start) break;
@@ -865,6 +995,7 @@ XM_HD inline int sa_len_a_before(const SAStore& s, int index_b) {  // SequenceAl
 }
 XM_HD inline int sa_len_a_after(const SAStore& s, int index_b) {  // :119-139
   int total = 0;
+  XM_NOUNROLL
   for (int i = 0; i < s.n_blk; i++) {
     const Blk& b = s.blk[i];
     if (index_b >= b.b_start + b.b_len) continue;
@@ -876,20 +1007,22 @@ XM_HD inline int sa_len_a_after(const SAStore& s, int index_b) {  // :119-139
   return total;
 }
 XM_HD inline int sa_insert_a_or_b(const SAStore& s) { int t = 0; for (int i = 0; i < s.n_blk; i++) if (s.blk[i].a_len != s.blk[i].b_len) t += s.blk[i].a_len + s.blk[i].b_len; return t; }
-XM_HD inline double sa_penalty_range(WS& w, const Params& p, const SAStore& s, int start_b, int end_b) {  // getPenalty(alignment, startB, endB) :97-103
+XM_FN double sa_penalty_range(WS& w, const Params& p, const SAStore& s, int start_b, int end_b) {  // getPenalty(alignment, startB, endB) :97-103
   SeqView a = w.query_view(s.a_mate, s.a_rev);
   SeqView b = w.ref->contig(s.contig, 0);
   double t = 0;
+  XM_NOUNROLL
   for (int i = 0; i < s.n_blk; i++) t += block_penalty_range(p, a, b, s.blk[i], start_b, end_b);
   return t;
 }
 // extract :365-405 — cuts [query_start, query_end) of the joined alignment for the read (mate, rev)
-XM_HD inline bool qma_extract(WS& w, const Params& p, const DAln& joined, int query_start, int query_end, int mate, int rev, int contig, bool reverse, SAStore& out) {
+XM_FN bool qma_extract(WS& w, const Params& p, const DAln& joined, int query_start, int query_end, int mate, int rev, int contig, bool reverse, SAStore& out) {
   int ref_reversed = (joined.ref_reversed != 0) != reverse ? 1 : 0;
   long long mark = w.scratch_top;
   Blk* blocks = (Blk*)w.salloc((long long)joined.n * (long long)sizeof(Blk));
   if (!blocks) return false;
   int n = 0;
+  XM_NOUNROLL
   for (int i = 0; i < joined.n; i++) {
     const Blk& b = joined.b[i];
     if (b.a_start >= query_end) break;
@@ -917,7 +1050,8 @@ XM_HD inline int qmx_distance(const WS& w, const QMX& m, const SM& a, const SM& 
 }
 
 // doAlign :94-272; returns stored alignment or nullptr
-XM_HD inline QAStore* qma_do_align(WS& w, QMA& A, const QMX& match, double extra_spacing, int q_total_len_for_spacing) {
+template <bool EASY>
+XM_FN QAStore* qma_do_align(WS& w, QMA& A, const QMX& match, double extra_spacing, int q_total_len_for_spacing) {
   const Params& P = A.prm;
   int spacing_i = 0;
   if (match.n >= 2) spacing_i = qmx_distance(w, match, match.comp[0], match.comp[1]);
@@ -932,6 +1066,7 @@ XM_HD inline QAStore* qma_do_align(WS& w, QMA& A, const QMX& match, double extra
   }
   double multiplier = 1, bonus = 0;
   int match_total_len = 0;
+  XM_NOUNROLL
   for (int i = 0; i < match.n; i++) match_total_len += w.query.seq[match.comp[i].mate].len;
   double max_allowed = next_up(match_total_len * P.max_error_rate);
   if (inner > 0) { double mp = spacing_penalty + match.priority * P.mutation; if (mp > max_allowed) return nullptr; }
@@ -953,6 +1088,7 @@ XM_HD inline QAStore* qma_do_align(WS& w, QMA& A, const QMX& match, double extra
     bool joinable = suffix_start >= 0;
     if (joinable) {
       int end2 = imin(s2.len, s1.len - offset);
+      XM_NOUNROLL
       for (int i2 = 0; i2 < end2; i2++) if (s1.at(i2 + offset) != s2.at(i2)) { joinable = false; break; }
     }
     if (joinable) {
@@ -960,16 +1096,18 @@ XM_HD inline QAStore* qma_do_align(WS& w, QMA& A, const QMX& match, double extra
       int jl = s1.len + (s2.len - suffix_start);
       uint16_t* jw = (uint16_t*)w.salloc((long long)((jl + 3) / 4 + 1) * 2);
       if (!jw) return nullptr;
+      XM_NOUNROLL
       for (int i = 0; i < (jl + 3) / 4 + 1; i++) jw[i] = 0;
+      XM_NOUNROLL
       for (int i = 0; i < jl; i++) {
         uint8_t code = i < s1.len ? s1.at(i) : s2.at(suffix_start + (i - s1.len));
         jw[i >> 2] = (uint16_t)(jw[i >> 2] | ((uint16_t)code << ((i & 3) << 2)));
       }
       // computeJoinedAlignment :321-331
-      ACtx jc; jc.a.w = jw; jc.a.len = jl; jc.a.rc = 0; jc.a_reversed_obj = 0; jc.b = w.ref->contig(m1.contig, 0);
+      ACtx jc; jc.a.w = jw; jc.a.len = jl; jc.a.rc = 0; jc.a.bytes = nullptr; jc.a_reversed_obj = 0; jc.b = w.ref->contig(m1.contig, 0);
       SM jm; jm.mate = -1; jm.rev = 0; jm.contig = m1.contig; jm.offset = imin(m1.offset, m2.offset); jm.from_hash = 1;
       Params sub = P; sub.max_error_rate = next_up(sub.max_error_rate);
-      DAln ja = qma_align_match(w, jc, jm, sub, w.query.per_penalty);
+      DAln ja = qma_align_match<EASY>(w, jc, jm, sub, w.query.per_penalty);
       if (w.status != 0) return nullptr;
       // splitAlignment :332-363
       if (!ja.valid) { w.scratch_top = mark; w.store_top = store_mark; return nullptr; }
@@ -1000,19 +1138,22 @@ XM_HD inline QAStore* qma_do_align(WS& w, QMA& A, const QMX& match, double extra
       double est_unique = qtl - est_overlap;
       max_total = divide_round_up(max_allowed - spacing_penalty, qtl) * est_unique * 2;
     } else max_total = max_allowed - spacing_penalty;
+    XM_NOUNROLL
     while (true) {
       int num_bases = 0;
+      XM_NOUNROLL
       for (int i = 0; i < match.n; i++) if (remaining[i]) num_bases += w.query.seq[match.comp[i].mate].len;
       if (num_bases < 1) break;
       double avg = divide_round_up(max_total - comps_penalty, (double)num_bases);
       Params prem = P; prem.max_error_rate = avg;
       bool found = false;
+      XM_NOUNROLL
       for (int i = first; i != last; i += stepi) {
         if (remaining[i]) {
           const SM& sm = match.comp[i];
           ACtx c; c.a = w.query_view(sm.mate, sm.rev); c.a_reversed_obj = sm.rev; c.b = w.ref->contig(sm.contig, 0);
           long long m2 = w.scratch_top;
-          DAln sa = qma_align_match(w, c, sm, prem, w.query.per_penalty);
+          DAln sa = qma_align_match<EASY>(w, c, sm, prem, w.query.per_penalty);
           if (w.status != 0) return nullptr;
           if (sa.valid) {
             if (!sa_store_from(w, qa->sa[i], sa, sm.contig, sm.mate, sm.rev)) return nullptr;
@@ -1062,8 +1203,9 @@ XM_HD inline QAStore* qma_do_align(WS& w, QMA& A, const QMX& match, double extra
   qa->inner = match.n > 1 ? sa_start_b(qa->sa[1]) - sa_end_b(qa->sa[0]) : 0;
   return qa;
 }
-XM_HD inline QAStore* qma_align(WS& w, QMA& A, const QMX& match, double extra_spacing, int q_total_len) {  // align :39-54
-  QAStore* a = qma_do_align(w, A, match, extra_spacing, q_total_len);
+template <bool EASY>
+XM_FN QAStore* qma_align(WS& w, QMA& A, const QMX& match, double extra_spacing, int q_total_len) {  // align :39-54
+  QAStore* a = qma_do_align<EASY>(w, A, match, extra_spacing, q_total_len);
   if (a != nullptr) {
     if (a->total < A.best_penalty) {
       A.best_penalty = a->total;
@@ -1078,16 +1220,19 @@ XM_HD inline QAStore* qma_align(WS& w, QMA& A, const QMX& match, double extra_sp
 }
 XM_INLINE int32_t qa_hash(const QAStore& q) {  // QueryAlignment.hashCode :226-233
   int32_t h = 0;
+  XM_NOUNROLL
   for (int i = 0; i < q.n_sa; i++) h = wadd(wmul(h, 1001), q.sa[i].blk[0].b_start - q.sa[i].blk[0].a_start);
   return h;
 }
 XM_HD inline bool qa_equals(const QAStore& a, const QAStore& b) {  // QueryAlignment.equals :235-256 + SequenceAlignment.equals + AlignedBlock.equals
   if (a.spacing != b.spacing || a.multiplier != b.multiplier || a.bonus != b.bonus || a.total != b.total) return false;
   if (a.inner != b.inner || a.n_sa != b.n_sa) return false;
+  XM_NOUNROLL
   for (int i = 0; i < a.n_sa; i++) {
     const SAStore& x = a.sa[i]; const SAStore& y = b.sa[i];
     if (x.n_blk != y.n_blk || x.ref_reversed != y.ref_reversed) return false;
     if (x.contig != y.contig || x.a_mate != y.a_mate || x.a_rev != y.a_rev) return false;
+    XM_NOUNROLL
     for (int k = 0; k < x.n_blk; k++) {
       const Blk& p = x.blk[k]; const Blk& q = y.blk[k];
       if (p.a_start != q.a_start || p.b_start != q.b_start || p.a_len != q.a_len || p.b_len != q.b_len) return false;
@@ -1096,7 +1241,7 @@ XM_HD inline bool qa_equals(const QAStore& a, const QAStore& b) {  // QueryAlign
   return true;
 }
 // getBestAlignments :71-83 + withoutDuplicates :86-92 (java.util.HashSet iteration order). Writes indices into out (scratch), returns count.
-XM_HD inline int qma_best(WS& w, QMA& A, QAStore**& out) {
+XM_FN int qma_best(WS& w, QMA& A, QAStore**& out) {
   double max_anywhere = A.q_len * A.prm.max_error_rate;
   double cutoff = A.best_penalty + A.prm.span;
   if (cutoff > max_anywhere) cutoff = max_anywhere;
@@ -1104,6 +1249,7 @@ XM_HD inline int qma_best(WS& w, QMA& A, QAStore**& out) {
   QAStore** best = (QAStore**)w.salloc((long long)(A.n_good > 0 ? A.n_good : 1) * (long long)sizeof(QAStore*));
   out = best;
   if (!best) return 0;
+  XM_NOUNROLL
   for (int i = 0; i < A.n_good; i++) if (A.good[i]->total <= cutoff) best[nb++] = A.good[i];
   if (nb <= 1) return nb;
   int cap = imax((int)((float)nb / .75f) + 1, 16);
@@ -1113,19 +1259,24 @@ XM_HD inline int qma_best(WS& w, QMA& A, QAStore**& out) {
   uint8_t* drop = (uint8_t*)w.salloc(nb);
   QAStore** sorted = (QAStore**)w.salloc((long long)nb * (long long)sizeof(QAStore*));
   if (w.status != 0) return 0;
+  XM_NOUNROLL
   for (int i = 0; i < nb; i++) {
     uint32_t h = (uint32_t)qa_hash(*best[i]); h ^= (h >> 16);
     bucket[i] = (int)(h & (uint32_t)(n - 1));
     drop[i] = 0;
+    XM_NOUNROLL
     for (int j = 0; j < i; j++) if (!drop[j] && bucket[j] == bucket[i] && qa_hash(*best[j]) == qa_hash(*best[i]) && qa_equals(*best[j], *best[i])) { drop[i] = 1; break; }
   }
   int m = 0;
   // emit in ascending bucket order, insertion order within a bucket
   int prev_bucket = -1;
+  XM_NOUNROLL
   while (true) {
     int nbk = -1;
+    XM_NOUNROLL
     for (int i = 0; i < nb; i++) if (!drop[i] && bucket[i] > prev_bucket && (nbk < 0 || bucket[i] < nbk)) nbk = bucket[i];
     if (nbk < 0) break;
+    XM_NOUNROLL
     for (int i = 0; i < nb; i++) if (!drop[i] && bucket[i] == nbk) sorted[m++] = best[i];
     prev_bucket = nbk;
   }
@@ -1146,27 +1297,33 @@ XM_HD inline bool dup_may_contain(const WS& w, int contig, int start_index, int 
   if (lo == hi) return false;
   // floorEntry(endIndex)
   long long a = lo, b = hi;  // first index with starts > end_index
+  XM_NOUNROLL
   while (a < b) { long long mid = (a + b) >> 1; if (d.starts[mid] > end_index) b = mid; else a = mid + 1; }
   if (a > lo) { int wnd = d.starts[a - 1] / d.window; if (wnd >= ws && wnd <= we) return true; }
   // ceilingEntry(startIndex)
   a = lo; b = hi;  // first index with starts >= start_index
+  XM_NOUNROLL
   while (a < b) { long long mid = (a + b) >> 1; if (d.starts[mid] >= start_index) b = mid; else a = mid + 1; }
   if (a < hi) { int wnd = d.starts[a] / d.window; if (wnd >= ws && wnd <= we) return true; }
   return false;
 }
 XM_HD inline bool qa_has_indel(const QAStore& q) { for (int i = 0; i < q.n_sa; i++) if (q.sa[i].n_blk > 1) return true; return false; }
 XM_HD inline bool qa_has_ambiguous(const WS& w, const QAStore& q) {
+  XM_NOUNROLL
   for (int i = 0; i < q.n_sa; i++) {
     const SAStore& s = q.sa[i];
     SeqView a = w.query_view(s.a_mate, s.a_rev), b = w.ref->contig(s.contig, 0);
+    XM_NOUNROLL
     for (int k = 0; k < s.n_blk; k++) {
+      XM_NOUNROLL
       for (int t = 0; t < s.blk[k].a_len; t++) if (bp_is_ambiguous(a.at(s.blk[k].a_start + t))) return true;
+      XM_NOUNROLL
       for (int t = 0; t < s.blk[k].b_len; t++) if (bp_is_ambiguous(b.at(s.blk[k].b_start + t))) return true;
     }
   }
   return false;
 }
-XM_HD inline bool quickly_confident(WS& w, const QAStore* best, const QMX& bm) {  // quicklyConfidentInBestAlignment :494-587
+XM_FN bool quickly_confident(WS& w, const QAStore* best, const QMX& bm) {  // quicklyConfidentInBestAlignment :494-587
   if (best == nullptr) return false;
   if (qa_has_indel(*best)) return false;
   int contig = bm.comp[0].contig;
@@ -1203,34 +1360,40 @@ XM_HD inline QMX qmx_from_qm(const WS& w, const QM& q) {
 }
 
 // emits one component's choices into the result arena
-XM_HD inline void emit_component(WS& w, OutArena& out, OutQuery& oq, int comp_index, QAStore** list, int n) {
+XM_FN void emit_component(WS& w, OutArena& out, OutQuery& oq, int comp_index, QAStore** list, int n) {
   oq.n_choice[comp_index] = n;
   if (n == 0) { oq.choice_first[comp_index] = 0; return; }
   long long n_sa = 0, n_blk = 0;
+  XM_NOUNROLL
   for (int i = 0; i < n; i++) { n_sa += list[i]->n_sa; for (int s = 0; s < list[i]->n_sa; s++) n_blk += list[i]->sa[s].n_blk; }
   long long c0 = (long long)xm_atomic_add(&out.used[0], (unsigned long long)n);
   long long s0 = (long long)xm_atomic_add(&out.used[1], (unsigned long long)n_sa);
   long long b0 = (long long)xm_atomic_add(&out.used[2], (unsigned long long)n_blk);
   if (c0 + n > out.cap_choices || s0 + n_sa > out.cap_sas || b0 + n_blk > out.cap_blocks) { w.fail(Q_OUT_FULL); return; }
   oq.choice_first[comp_index] = c0;
+  XM_NOUNROLL
   for (int i = 0; i < n; i++) {
     const QAStore& q = *list[i];
     OutChoice& oc = out.choices[c0 + i];
     oc.spacing = q.spacing; oc.multiplier = q.multiplier; oc.bonus = q.bonus; oc.total = q.total; oc.inner = q.inner; oc.n_sa = q.n_sa; oc.sa_first = s0;
+    XM_NOUNROLL
     for (int s = 0; s < q.n_sa; s++) {
       const SAStore& sa = q.sa[s];
       OutSA& os = out.sas[s0++];
       os.penalty = sa.penalty; os.aligned = sa.aligned; os.contig = sa.contig; os.reversed = sa.ref_reversed; os.n_blocks = sa.n_blk; os.pad = 0; os.block_first = b0;
+      XM_NOUNROLL
       for (int k = 0; k < sa.n_blk; k++) { int32_t* d = out.blocks + 4 * (b0++); d[0] = sa.blk[k].a_start; d[1] = sa.blk[k].b_start; d[2] = sa.blk[k].a_len; d[3] = sa.blk[k].b_len; }
     }
   }
 }
 
 // AlignerWorker.alignToAncestralReference :306-484 (+ getUnpairedAlignments :602-644). Results go to `out`.
+template <bool EASY>
 XM_HD inline void align_query(WS& w, OutArena& out, OutQuery& oq) {
   oq.n_comp = 1; oq.n_choice[0] = 0; oq.n_choice[1] = 0; oq.choice_first[0] = 0; oq.choice_first[1] = 0;
   const Params& P = w.prm;
   int nseq = w.query.n_seqs;
+  XM_NOUNROLL
   for (int i = 0; i < nseq; i++) if (w.query.seq[i].len < 1) { w.fail(Q_INTERNAL); return; }
   double max_interesting = w.query.length() * P.max_error_rate;
   int max_inner = j2i(max_interesting * w.query.per_penalty + w.query.expected_inner);
@@ -1248,15 +1411,17 @@ XM_HD inline void align_query(WS& w, OutArena& out, OutQuery& oq) {
   int filt = pc_optimistic_best(w);
   if (w.status != 0) return;
   int n_best = 0, best_i = -1;
+  XM_NOUNROLL
   for (int i = 0; i < w.n_assembled; i++) if (w.assembled[i].priority == filt) { n_best++; best_i = i; }
   if (n_best == 1) {
     opt_qm = w.assembled[best_i]; have_opt = true;
     QMX x = qmx_from_qm(w, opt_qm);
-    optimistic = qma_align(w, A, x, 0, w.query.length());
+    optimistic = qma_align<EASY>(w, A, x, 0, w.query.length());
     if (w.status != 0) return;
     if (quickly_confident(w, optimistic, x)) { QAStore* l[1] = {optimistic}; emit_component(w, out, oq, 0, l, 1); return; }
   }
   if (optimistic != nullptr) {
+    XM_NOUNROLL
     while (true) {
       double possible = penalty_lower_bound(w, num_mis);
       if (possible > optimistic->total + P.span) { QAStore* l[1] = {optimistic}; emit_component(w, out, oq, 0, l, 1); return; }
@@ -1265,6 +1430,7 @@ XM_HD inline void align_query(WS& w, OutArena& out, OutQuery& oq) {
       int k = num_mis;
       num_mis++;
       bool done = false;
+      XM_NOUNROLL
       for (int i = 0; i < w.n_assembled; i++) {
         if (w.assembled[i].priority != k) continue;
         if (!qm_same_position(opt_qm, opt_n, w.assembled[i], nseq)) { done = true; break; }
@@ -1274,6 +1440,7 @@ XM_HD inline void align_query(WS& w, OutArena& out, OutQuery& oq) {
   }
   double best_penalty = (double)JMAX;
   int cand = 0;
+  XM_NOUNROLL
   while (true) {
     double est = penalty_lower_bound(w, cand);
     if (est > best_penalty + P.span) break;
@@ -1281,11 +1448,12 @@ XM_HD inline void align_query(WS& w, OutArena& out, OutQuery& oq) {
     pc_find_good_up_to(w, cand);
     if (w.status != 0) return;
     // the candidate list is a filtered view of w.assembled, which alignMatch does not modify
+    XM_NOUNROLL
     for (int i = 0; i < w.n_assembled; i++) {
       if (w.assembled[i].priority != cand) continue;
       QAStore* a;
       if (have_opt && qm_same_position(w.assembled[i], nseq, opt_qm, opt_n)) a = optimistic;
-      else { QMX x = qmx_from_qm(w, w.assembled[i]); a = qma_align(w, A, x, 0, w.query.length()); }
+      else { QMX x = qmx_from_qm(w, w.assembled[i]); a = qma_align<EASY>(w, A, x, 0, w.query.length()); }
       if (w.status != 0) return;
       if (a != nullptr) { if (best_penalty > a->total) best_penalty = a->total; }
     }
@@ -1299,9 +1467,10 @@ XM_HD inline void align_query(WS& w, OutArena& out, OutQuery& oq) {
   if (nb < 1 && nseq > 1) {
     w.scratch_top = mark;
     if (pc_find_partially_good(w)) {
+      XM_NOUNROLL
       for (int i = 0; i < w.n_assembled && w.status == 0; i++) {
         QMX x = qmx_from_qm(w, w.assembled[i]);
-        QAStore* a = qma_align(w, A, x, 0, w.query.length());
+        QAStore* a = qma_align<EASY>(w, A, x, 0, w.query.length());
         if (a != nullptr) { if (best_penalty > a->total) best_penalty = a->total; }
       }
     }
@@ -1314,6 +1483,7 @@ XM_HD inline void align_query(WS& w, OutArena& out, OutQuery& oq) {
     // getUnpairedAlignments :602-644
     w.scratch_top = mark;
     oq.n_comp = 2;
+    XM_NOUNROLL
     for (int si = 0; si < nseq; si++) {
       int slen = w.query.seq[si].len;
       double max_sub = slen * P.max_error_rate;
@@ -1324,6 +1494,7 @@ XM_HD inline void align_query(WS& w, OutArena& out, OutQuery& oq) {
       qma_init(w, S, P, slen, cap_good);
       if (w.status != 0) return;
       int cur = -1, ci;
+      XM_NOUNROLL
       while ((ci = list_next(w, w.mp[si], l, cur)) >= 0) {
         SM sm = counter_match(w.mp[si], w.mp[si].counters[ci]);
         int min_inner;
@@ -1333,7 +1504,7 @@ XM_HD inline void align_query(WS& w, OutArena& out, OutQuery& oq) {
         double sp = inner / w.query.per_penalty;
         if (sp > max_sub) continue;
         QMX x; x.n = 1; x.comp[0] = sm; x.comp[1] = sm; x.priority = -1; x.hint = 0;
-        qma_align(w, S, x, inner, slen);
+        qma_align<EASY>(w, S, x, inner, slen);
         if (w.status != 0) return;
       }
       long long m2 = w.scratch_top;
@@ -1351,11 +1522,17 @@ XM_HD inline void align_query(WS& w, OutArena& out, OutQuery& oq) {
 }
 
 // Carves the per-thread workspace out of a flat arena and resets all per-query state.
+// fills the 256-entry pair-penalty table (Params::pen_tab) with the reference's formula
+XM_HD inline void fill_pen_tab(const Params& prm, double* tab, int first, int step) {
+  for (int i = first; i < 256; i += step) tab[i] = prm.base_penalty_formula((uint8_t)(i >> 4), (uint8_t)(i & 15));
+}
 XM_HD inline bool ws_init(WS& w, char* arena, long long arena_bytes, const RefD* ref, const IndexD* ix, const DupD* dup, const Params& prm, const QueryIn& q) {
   w.ref = ref; w.ix = ix; w.dup = dup; w.prm = prm; w.query = q;
   w.status = 0; w.next_list_id = 1;
   w.pc_have_prev = 0; w.pc_found_nonempty = 0; w.n_assembled = 0;
   w.st_probes = w.st_seeds = w.st_hits = w.st_straight = w.st_path_calls = w.st_path_steps = w.st_path_cells = 0;
+  XM_NOUNROLL
+  for (int i = 0; i < 6; i++) w.st_cyc[i] = 0;
   long long top = 0;
   auto take = [&](long long bytes) -> char* { bytes = (bytes + 15) & ~15LL; char* p = arena + top; top += bytes; return p; };
   int max_len = imax(q.seq[0].len, q.n_seqs > 1 ? q.seq[1].len : 0);
@@ -1365,7 +1542,7 @@ XM_HD inline bool ws_init(WS& w, char* arena, long long arena_bytes, const RefD*
   long long per_mate_rows = (long long)levels * (long long)sizeof(RowWin);
   if (per_mate_rows * q.n_seqs > fixed) levels = (int)(fixed / q.n_seqs / (long long)sizeof(RowWin));
   if (levels < 4) return false;
-  long long rest = arena_bytes - (long long)levels * (long long)sizeof(RowWin) * q.n_seqs - 256;
+  long long rest = arena_bytes - (long long)levels * (long long)sizeof(RowWin) * q.n_seqs - 256 - 2 * (long long)(q.seq[0].len + q.seq[1].len + 64);
   if (rest < 4096) return false;
   // split of the remainder: counters 12%, history+pending 6%, assembled 8%, store 24%, scratch 50%
   int cap_counters = (int)(rest * 12 / 100 / q.n_seqs / (long long)(sizeof(Counter) + sizeof(int)));
@@ -1373,11 +1550,26 @@ XM_HD inline bool ws_init(WS& w, char* arena, long long arena_bytes, const RefD*
   int cap_pend = (int)(rest * 3 / 100 / q.n_seqs / (long long)sizeof(HB));
   int cap_asm = (int)(rest * 8 / 100 / (long long)sizeof(QM));
   if (cap_counters < 8 || cap_hist < 8 || cap_pend < 4 || cap_asm < 8) return false;
+  XM_NOUNROLL
   for (int i = 0; i < q.n_seqs; i++) {
     MatePath& m = w.mp[i];
     m.mate = i; m.path_is_rc = (i > 0) ? 1 : 0;
-    m.q = q.seq[i]; m.q.rc = m.path_is_rc;
+    {  // unpack the read in both orientations, one code per byte (lanes split the bases on the device)
+      int len = q.seq[i].len;
+      uint8_t* f = (uint8_t*)take(len + 1); uint8_t* r = (uint8_t*)take(len + 1);
+      SeqView pv = q.seq[i]; pv.rc = 0; pv.bytes = nullptr;
+#if defined(__CUDA_ARCH__)
+      for (int k = (int)(threadIdx.x & 31); k < len; k += 32) { uint8_t c = pv.at(k); f[k] = c; r[len - 1 - k] = bp_complement(c); }
+      __syncwarp();
+#else
+      for (int k = 0; k < len; k++) { uint8_t c = pv.at(k); f[k] = c; r[len - 1 - k] = bp_complement(c); }
+#endif
+      w.qbytes[i][0] = f; w.qbytes[i][1] = r;
+      w.query.seq[i].bytes = nullptr;
+    }
+    m.q = w.query_view(i, m.path_is_rc);
     m.rows = (RowWin*)take((long long)levels * (long long)sizeof(RowWin)); m.max_levels = levels;
+    XM_NOUNROLL
     for (int l = 0; l < levels; l++) { m.rows[l].mpc = -1; m.rows[l].low = -1; m.rows[l].head = 0; m.rows[l].cnt = 0; }
     m.counters = (Counter*)take((long long)cap_counters * (long long)sizeof(Counter)); m.n_counters = 0; m.cap_counters = cap_counters;
     m.good = (int*)take((long long)cap_counters * 4); m.n_good = 0;

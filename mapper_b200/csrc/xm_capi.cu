@@ -16,6 +16,7 @@
 using namespace xm;
 
 // ---------------------------------------------------------------- kernels
+#define XM_BLOCK 128
 struct BatchD {
   int n_queries;
   const uint16_t* packed; const int64_t* seq_word_off; const int32_t* seq_len; const int64_t* first_seq;  // first_seq: n_queries+1
@@ -34,39 +35,55 @@ struct LaunchD {
   long long* q_cycles;                    // optional per-query cost probe (XM_QCYCLES=1): clock64 ticks of the tier that finished it
 };
 
-__global__ void __launch_bounds__(128) xm_align_kernel(LaunchD L) {
-  long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  char* arena = L.arenas + tid * L.arena_bytes;
-  unsigned long long st[7] = {0, 0, 0, 0, 0, 0, 0};
+// EASY = true: first pass over every query (small arenas, no cascade code in the image); false: the full aligner
+// over the queries the first pass handed on.
+template <bool EASY>
+__global__ void __launch_bounds__(XM_BLOCK, 4) xm_align_kernel(LaunchD L) {
+  const int lane = threadIdx.x & 31;
+  long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  char* arena = L.arenas + warp * L.arena_bytes;
+  __shared__ double s_pen[256];
+  fill_pen_tab(L.prm, s_pen, threadIdx.x, blockDim.x);
+  __syncthreads();
+  L.prm.pen_tab = s_pen;
+  unsigned long long st[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   while (true) {
-    int t = atomicAdd(L.ticket, 1);
+    int t = 0;
+    if (lane == 0) t = atomicAdd(L.ticket, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
     if (t >= L.n_ids) break;
     int qi = L.ids ? L.ids[t] : t;
     QueryIn q;
     long long c0 = L.q_cycles ? clock64() : 0;
     long long s0 = L.batch.first_seq[qi];
     q.n_seqs = (int)(L.batch.first_seq[qi + 1] - s0);
-    for (int s = 0; s < q.n_seqs; s++) { q.seq[s].w = L.batch.packed + L.batch.seq_word_off[s0 + s]; q.seq[s].len = L.batch.seq_len[s0 + s]; q.seq[s].rc = 0; }
+    for (int s = 0; s < q.n_seqs; s++) { q.seq[s].w = L.batch.packed + L.batch.seq_word_off[s0 + s]; q.seq[s].len = L.batch.seq_len[s0 + s]; q.seq[s].rc = 0; q.seq[s].bytes = nullptr; }
     if (q.n_seqs < 2) { q.seq[1] = q.seq[0]; q.seq[1].len = 0; }
     q.expected_inner = q.n_seqs > 1 ? L.batch.expected_inner[qi] : 0.0;
     q.per_penalty = q.n_seqs > 1 ? L.batch.per_penalty[qi] : 1.0;
     WS w;
     OutQuery rec; rec.status = 0; rec.n_comp = 1; rec.n_choice[0] = 0; rec.n_choice[1] = 0; rec.choice_first[0] = 0; rec.choice_first[1] = 0;
     if (!ws_init(w, arena, L.arena_bytes, &L.ref, &L.ix, &L.dup, L.prm, q)) w.status = Q_NEED_MORE;
-    else align_query(w, L.out, rec);
+    else align_query<EASY>(w, L.out, rec);
+    __syncwarp();
     int status = w.status;
+    if (status == Q_HARD) status = Q_NEED_MORE;
     if (status == Q_NEED_MORE) {
       if (L.last_tier) status = Q_WORKSPACE;
-      else { int k = atomicAdd(L.n_need_more, 1); L.need_more[k] = qi; }
-    } else if (status == Q_OUT_FULL) { int k = atomicAdd(L.n_out_full, 1); L.out_full[k] = qi; }
+      else if (lane == 0) { int k = atomicAdd(L.n_need_more, 1); L.need_more[k] = qi; }
+    } else if (status == Q_OUT_FULL) { if (lane == 0) { int k = atomicAdd(L.n_out_full, 1); L.out_full[k] = qi; } }
     rec.status = status;
-    L.out.q[qi] = rec;
-    if (L.q_cycles) L.q_cycles[qi] = clock64() - c0;
+    if (lane == 0) {
+      L.out.q[qi] = rec;
+      if (L.q_cycles) L.q_cycles[qi] = clock64() - c0;
+    }
     if (status != Q_NEED_MORE && status != Q_OUT_FULL) {
       st[0] += w.st_probes; st[1] += w.st_seeds; st[2] += w.st_hits; st[3] += w.st_straight; st[4] += w.st_path_calls; st[5] += w.st_path_steps; st[6] += w.st_path_cells;
+      for (int i = 0; i < 6; i++) st[7 + i] += w.st_cyc[i];
+      if (L.q_cycles) st[13] += (unsigned long long)(clock64() - c0);
     }
   }
-  for (int i = 0; i < 7; i++) if (st[i]) atomicAdd(&L.out.stats[i], st[i]);
+  if (lane == 0) for (int i = 0; i < 14; i++) if (st[i]) atomicAdd(&L.out.stats[i], st[i]);
 }
 
 // first_seq[q] = exclusive prefix sum of n_seqs_per_query (single block scan is enough off the hot path; uses a
@@ -113,7 +130,7 @@ __global__ void xm_counts_kernel(RefD ref, BatchD batch, OutArena out, CountsD C
       for (int s = 0; s < ch.n_sa; s++) {
         const OutSA& sa = out.sas[ch.sa_first + s];
         int mate = (oq.n_comp == 2) ? comp : s;
-        SeqView qv; qv.w = batch.packed + batch.seq_word_off[s0 + mate]; qv.len = batch.seq_len[s0 + mate]; qv.rc = sa.reversed;
+        SeqView qv; qv.w = batch.packed + batch.seq_word_off[s0 + mate]; qv.len = batch.seq_len[s0 + mate]; qv.rc = sa.reversed; qv.bytes = nullptr;
         SeqView rv = ref.contig(sa.contig, 0);
         int end_len = (int)(qv.len * C.end_fraction);
         long long base = C.contig_off[sa.contig] * 4;
@@ -162,7 +179,7 @@ struct xm_results { ResultsHost r; };
 
 struct xm_handle {
   HostModel m;
-  int device = 0, sm_count = 148;
+  int device = 0, sm_count = 148, blocks_per_sm = 4;
   std::string err;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
@@ -237,6 +254,8 @@ int xm_create(const xm_params* p, int device, xm_handle** out) {
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   h->sm_count = prop.multiProcessorCount;
+  { int nb = 0; if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, xm_align_kernel<false>, XM_BLOCK, 0) == cudaSuccess && nb > 0) h->blocks_per_sm = nb; }
+  if (const char* e = getenv("XM_BLOCKS_PER_SM")) { int v = atoi(e); if (v > 0) h->blocks_per_sm = v; }
   cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3);
   size_t stack = 32 * 1024;
@@ -250,7 +269,7 @@ int xm_create(const xm_params* p, int device, xm_handle** out) {
   q.mutation = p->mutation_penalty; q.ins_start = p->insertion_start_penalty; q.ins_ext = p->insertion_extension_penalty;
   q.del_start = p->deletion_start_penalty; q.del_ext = p->deletion_extension_penalty; q.max_error_rate = p->max_error_rate;
   q.unaligned = p->unaligned_penalty; q.ambiguity = p->ambiguity_penalty; q.span = p->max_penalty_span;
-  q.max_num_matches = p->max_num_matches; q.start_free = 0;
+  q.max_num_matches = p->max_num_matches; q.start_free = 0; q.pen_tab = nullptr;
   h->m.gapmers = p->enable_gapmers ? 1 : 0;
   *out = h;
   return XM_OK;
@@ -361,11 +380,11 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
   if (!h->d_q.ensure((size_t)nq * sizeof(OutQuery)) || !h->d_misc.ensure(256) || !h->d_ids_a.ensure((size_t)nq * 4) || !h->d_ids_b.ensure((size_t)nq * 4) || !h->d_ids_full.ensure((size_t)nq * 4)) {
     h->err = "out of device memory"; return XM_ERR_CUDA;
   }
-  // misc: [0..2] used (u64) [3..9] stats (u64) then ints: ticket, n_need_more, n_out_full
+  // misc: [0..2] used (u64) [3..16] stats (u64) then ints: ticket, n_need_more, n_out_full
   CK(cudaMemsetAsync(h->d_misc.p, 0, 256, st));
   unsigned long long* d_used = (unsigned long long*)h->d_misc.p;
   unsigned long long* d_stats = d_used + 3;
-  int* d_ints = (int*)(d_used + 12);
+  int* d_ints = (int*)(d_used + 20);
 
   LaunchD L;
   L.ref = h->ref; L.ix = h->ix; L.dup = h->dup; L.prm = h->m.prm;
@@ -379,36 +398,38 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
   L.q_cycles = nullptr;
   if (h->probe_cycles) { if (!h->d_qcycles.ensure((size_t)nq * 8)) { h->err = "out of device memory"; return XM_ERR_CUDA; } L.q_cycles = (long long*)h->d_qcycles.p; }
 
-  const int block = 128;
+  const int block = XM_BLOCK, warps_per_block = XM_BLOCK / 32;
   const int32_t* ids = nullptr;
   int n_ids = nq;
   int32_t* next_ids = (int32_t*)h->d_ids_a.p;
-  float align_ms_tier0 = 0, tier_ms[XM_NUM_TIERS] = {0};
+  float align_ms_tier0 = 0, easy_ms = 0, tier_ms[XM_NUM_TIERS] = {0};
   for (int round = 0; round < 4; round++) {  // extra rounds only after growing the result arena
-    for (int tier = 0; tier < XM_NUM_TIERS && n_ids > 0; tier++) {
-      long long arena = tier_arena_bytes(tier, max_seq_len, 2);
-      long long max_threads = (long long)(h->ws_budget / (size_t)arena);
-      long long threads = (long long)h->sm_count * 512;
-      if (threads > max_threads) threads = max_threads;
-      if (threads > n_ids) threads = n_ids;
-      int blocks = (int)((threads + block - 1) / block);
+    for (int tier = (round == 0 ? -1 : 0); tier < XM_NUM_TIERS && n_ids > 0; tier++) {  // tier -1: the first-pass kernel
+      long long resident = (long long)h->sm_count * h->blocks_per_sm * warps_per_block;
+      long long arena = tier < 0 ? easy_arena_bytes(max_seq_len, 2) : tier_arena_bytes(tier, max_seq_len, 2, (long long)h->ws_budget, resident);
+      long long max_warps = (long long)(h->ws_budget / (size_t)arena);
+      long long warps = (long long)h->sm_count * h->blocks_per_sm * warps_per_block;  // one resident wave: the kernel is persistent (ticket loop)
+      if (warps > max_warps) warps = max_warps;
+      if (warps > n_ids) warps = n_ids;
+      int blocks = (int)((warps + warps_per_block - 1) / warps_per_block);
       if (blocks < 1) blocks = 1;
-      if ((long long)blocks * block * arena > (long long)h->ws_budget && blocks > 1) blocks = (int)(h->ws_budget / (size_t)(arena * block));
+      if ((long long)blocks * warps_per_block * arena > (long long)h->ws_budget && blocks > 1) blocks = (int)(h->ws_budget / (size_t)(arena * warps_per_block));
       if (blocks < 1) { h->err = "workspace budget too small for one block"; return XM_ERR_CUDA; }
-      if (!h->d_ws.ensure((size_t)blocks * block * (size_t)arena)) { h->err = "out of device memory (workspace)"; return XM_ERR_CUDA; }
+      if (!h->d_ws.ensure((size_t)blocks * warps_per_block * (size_t)arena)) { h->err = "out of device memory (workspace)"; return XM_ERR_CUDA; }
       CK(cudaMemsetAsync(d_ints, 0, 8, st));  // ticket, n_need_more
       L.ids = ids; L.n_ids = n_ids; L.need_more = next_ids; L.arenas = (char*)h->d_ws.p; L.arena_bytes = arena; L.last_tier = (tier == XM_NUM_TIERS - 1);
-      bool time_it = (round == 0 && tier == 0);
+      bool time_it = (round == 0 && tier == -1);
       CK(cudaEventRecord(h->ev2, st));
-      xm_align_kernel<<<blocks, block, 0, st>>>(L);
+      if (tier < 0) xm_align_kernel<true><<<blocks, block, 0, st>>>(L);
+      else xm_align_kernel<false><<<blocks, block, 0, st>>>(L);
       CK(cudaEventRecord(h->ev3, st));
       launches++;
       CK(cudaGetLastError());
-      R->r.stats[XM_STAT_TIER0_QUERIES + tier] += n_ids;
+      if (tier < 0) R->r.stats[XM_STAT_EASY_QUERIES] += n_ids; else R->r.stats[XM_STAT_TIER0_QUERIES + tier] += n_ids;
       int counts[3];
       CK(cudaMemcpyAsync(counts, d_ints, 12, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
-      { float t = 0; cudaEventElapsedTime(&t, h->ev2, h->ev3); tier_ms[tier] += t; if (time_it) align_ms_tier0 = t; }
+      { float t = 0; cudaEventElapsedTime(&t, h->ev2, h->ev3); if (tier < 0) easy_ms += t; else tier_ms[tier] += t; if (time_it) align_ms_tier0 = t; }
       ids = next_ids; n_ids = counts[1];
       next_ids = (next_ids == (int32_t*)h->d_ids_a.p) ? (int32_t*)h->d_ids_b.p : (int32_t*)h->d_ids_a.p;
     }
@@ -445,7 +466,7 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
   }
   CK(cudaEventRecord(h->ev1, st));
   // D2H
-  unsigned long long misc[12];
+  unsigned long long misc[20];
   CK(cudaMemcpyAsync(misc, h->d_misc.p, sizeof(misc), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   float ms = 0;
@@ -465,10 +486,12 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
   R->r.stats[XM_STAT_ALIGN_KERNEL_NS] = (int64_t)((double)align_ms_tier0 * 1e6);
   R->r.stats[XM_STAT_LAUNCHES] = launches;
   for (int t = 0; t < XM_NUM_TIERS && t < 3; t++) R->r.stats[XM_STAT_TIER0_NS + t] = (int64_t)((double)tier_ms[t] * 1e6);
+  R->r.stats[XM_STAT_EASY_NS] = (int64_t)((double)easy_ms * 1e6);
   if (h->probe_cycles) { R->r.q_cycles.resize((size_t)nq); CK(cudaMemcpy(R->r.q_cycles.data(), h->d_qcycles.p, (size_t)nq * 8, cudaMemcpyDeviceToHost)); }
   R->r.stats[XM_STAT_PROBES] = (int64_t)misc[3]; R->r.stats[XM_STAT_SEEDS] = (int64_t)misc[4]; R->r.stats[XM_STAT_HITS] = (int64_t)misc[5];
   R->r.stats[XM_STAT_STRAIGHT] = (int64_t)misc[6]; R->r.stats[XM_STAT_PATH_CALLS] = (int64_t)misc[7]; R->r.stats[XM_STAT_PATH_STEPS] = (int64_t)misc[8];
   R->r.stats[XM_STAT_PATH_CELLS] = (int64_t)misc[9];
+  for (int i = 0; i < 7; i++) R->r.stats[XM_STAT_CYC_SEED + i] = (int64_t)misc[10 + i];
   R->r.stats[XM_STAT_D2H_BYTES] = (int64_t)((size_t)nq * sizeof(OutQuery) + uc * sizeof(OutChoice) + us * sizeof(OutSA) + ub * 16 + sizeof(misc));
   *out = R;
   for (int i = 0; i < nq; i++) if (oq[(size_t)i].status != 0) { h->err = "at least one query could not be aligned on the device (see q_status)"; return XM_ERR_QUERY; }

@@ -47,7 +47,7 @@ struct HostModel {
   bool dup_set = false;
   uint64_t generation = 0;  // bumped on every change so the device mirror knows to refresh
 
-  SeqView contig_view(int c, int rc) const { SeqView v; v.w = words.data() + word_off[c]; v.len = len[c]; v.rc = rc; return v; }
+  SeqView contig_view(int c, int rc) const { SeqView v; v.w = words.data() + word_off[c]; v.len = len[c]; v.rc = rc; v.bytes = nullptr; return v; }
 
   void set_reference(int n, const uint16_t* const* packed4, const int32_t* lengths) {
     n_contigs = n; words.clear(); word_off.assign(n, 0); len.assign(lengths, lengths + n); gstart.assign(2 * (size_t)n + 1, 0);
@@ -292,14 +292,27 @@ struct HostModel {
 // Workspace tiers: bytes of per-query arena. Queries that exhaust a tier are re-run from scratch in the next one
 // (the algorithm is deterministic), so small arenas keep the common case at full occupancy.
 static const int XM_NUM_TIERS = 3;
-inline long long tier_arena_bytes(int tier, int max_seq_len, int n_seqs_max) {
+// Workspace per warp of the first-pass ("easy") kernel: pyramid rows, counters, candidate lists and a handful of
+// single-block alignments; no lattice.
+inline long long easy_arena_bytes(int max_seq_len, int n_seqs_max) {
   long long rows = (long long)(max_seq_len + 2) * (long long)sizeof(RowWin) * n_seqs_max;
-  long long grid = (long long)(max_seq_len + 2) * (long long)(max_seq_len * 2 + 64) * 26;  // full-read PathAligner grid
-  switch (tier) {
-    case 0: return std::max<long long>(24 * 1024, std::min<long long>(rows / 4 + 16 * 1024, 96 * 1024));
-    case 1: return std::max<long long>(256 * 1024, rows * 2 + grid / 4);
-    default: return std::max<long long>(4 * 1024 * 1024, rows * 4 + grid * 4);
-  }
+  long long b = std::max<long long>(64 * 1024, rows / 2 + 32 * 1024);
+  return (b + 255) & ~255LL;
+}
+// Workspace per WARP (one warp owns one query at a time).  Tier 0 is sized to hold a PathAligner lattice over the
+// whole read (so that almost nothing is re-run) whenever one resident wave of such arenas fits the budget; otherwise
+// it shrinks towards "a lattice over a BlockAligner piece".  Each further tier is 4x larger (fewer warps).
+inline long long tier_arena_bytes(int tier, int max_seq_len, int n_seqs_max, long long budget = 24LL << 30, long long resident_warps = 148 * 16) {
+  long long rows = (long long)(max_seq_len + 2) * (long long)sizeof(RowWin) * n_seqs_max;
+  long long grid = (long long)(max_seq_len + 2) * (long long)(max_seq_len * 2 + 64) * 26;  // full-read PathAligner grid + heap share
+  long long small = std::max<long long>(256 * 1024, rows * 2 + grid / 4);
+  long long full = rows * 2 + grid * 5 / 2;
+  long long a0 = full;
+  if (a0 * resident_warps > budget) a0 = std::max<long long>(small, budget / std::max<long long>(1, resident_warps));
+  long long b = a0;
+  for (int i = 0; i < tier; i++) b *= 4;
+  if (tier == 2) b = std::max<long long>(b, rows * 4 + grid * 16);
+  return (b + 255) & ~255LL;  // arenas are carved back to back: keep every one 256-byte aligned
 }
 
 }  // namespace xm

@@ -45,7 +45,7 @@ XM_INLINE HB base_block(uint8_t code, int index) {  // HashBlock(char,int) + has
   return b;
 }
 
-XM_HD inline HB merge_blocks(const HB& L, const HB& R, int level) {  // HashBlock(seq,start,len,l,r) :20-44 + mergeHashes :192-259
+XM_FN HB merge_blocks(const HB& L, const HB& R, int level) {  // HashBlock(seq,start,len,l,r) :20-44 + mergeHashes :192-259
   HB b;
   b.start = L.start; b.len = R.end() - L.start; b.used = b.len;
   b.fwd = merge_hash(L.len, L.fwd, R.len, R.fwd);
@@ -81,7 +81,7 @@ XM_HD inline HB merge_blocks(const HB& L, const HB& R, int level) {  // HashBloc
 XM_INLINE int ext_char_to_int(uint8_t c) { return c == 1 ? 1 : c == 2 ? 2 : c == 4 ? 3 : c == 8 ? 4 : 0; }
 
 // HashBlock.withGapAndExtension :67-150. false = null
-XM_HD inline bool with_gap_and_extension(const HB& b, const SeqView& seq, HB& out) {
+XM_FN bool with_gap_and_extension(const HB& b, const SeqView& seq, HB& out) {
   if (b.gap_dir == 0) { out = b; return true; }
   int target = b.len + (jabs(b.fwd > b.rev ? b.fwd : b.rev) % 3) + b.extra;
   int gap = b.len / 2;
@@ -91,11 +91,13 @@ XM_HD inline bool with_gap_and_extension(const HB& b, const SeqView& seq, HB& ou
   if (b.gap_dir < 0) {
     int ext_end = b.start - gap, ext_start = ext_end - ext;
     if (ext_start < 0) return false;
+    XM_NOUNROLL
     for (int i = ext_end - 1; i >= ext_start; i--) h = wadd(wmul(h, 7654337), ext_char_to_int(seq.at(i)));
     r.start = ext_start; r.len = ext + gap + b.len;
   } else {
     int ext_start = b.end() + gap, ext_end = ext_start + ext;
     if (ext_end > seq.len) return false;
+    XM_NOUNROLL
     for (int i = ext_start; i < ext_end; i++) h = wadd(wmul(h, 7654337), ext_char_to_int(bp_complement(seq.at(i))));
     r.start = b.start; r.len = b.len + gap + ext;
   }
@@ -141,6 +143,17 @@ struct MatePath {
 
 struct DAlnStore;  // xm_align.h
 
+#if defined(__CUDA_ARCH__)
+#define XM_CLK() ((unsigned long long)clock64())
+#else
+#define XM_CLK() 0ull
+#endif
+struct PhaseClock {  // adds the ticks between construction and destruction to *slot
+  unsigned long long* slot; unsigned long long t0;
+  XM_INLINE PhaseClock(unsigned long long* s) : slot(s), t0(XM_CLK()) {}
+  XM_INLINE ~PhaseClock() { *slot += XM_CLK() - t0; }
+};
+
 struct WS {
   const RefD* ref; const IndexD* ix; const DupD* dup;
   Params prm; QueryIn query;
@@ -155,6 +168,7 @@ struct WS {
   // alignment store (xm_align.h)
   char* store; long long store_size, store_top;
   unsigned long long st_probes, st_seeds, st_hits, st_straight, st_path_calls, st_path_steps, st_path_cells;
+  unsigned long long st_cyc[6];  // SM clock ticks per phase (device only): 0 seed step, 1 straight score, 2 HashBlock_Aligner analysis, 3 PathAligner, 4 matcher table builds, 5 spare
 
   XM_INLINE void fail(int s) { if (status == 0) { status = s; XM_T("FAIL status=%d\n", s); } }
   XM_INLINE void* salloc(long long bytes) {
@@ -162,7 +176,8 @@ struct WS {
     if (scratch_top + bytes > scratch_size) { fail(Q_NEED_MORE); return nullptr; }
     void* p = scratch + scratch_top; scratch_top += bytes; return p;
   }
-  XM_INLINE SeqView query_view(int mate, int rev) const { SeqView v = query.seq[mate]; v.rc = rev; return v; }
+  uint8_t* qbytes[2][2];  // [mate][reverse-complemented]: one code per byte
+  XM_INLINE SeqView query_view(int mate, int rev) const { SeqView v = query.seq[mate]; v.rc = rev; v.bytes = qbytes[mate][rev]; return v; }
 };
 
 XM_INLINE int sm_start_b(const WS& w, const SM& m) { return imax(0, m.offset); }
@@ -184,7 +199,7 @@ XM_HD inline void row_push(RowWin& r, const HB& b) {
 }
 
 // HashBlock_ParentRow.maybeMakeBlock :69-127 (single blocks only)
-XM_HD inline void row_maybe_make(WS& w, MatePath& m, int level) {
+XM_FN void row_maybe_make(WS& w, MatePath& m, int level) {
   RowWin& r = m.rows[level];
   HB left, right;
   if (!row_get_after(w, m, level - 1, r.mpc, left)) { r.mpc = m.q.len; return; }
@@ -207,10 +222,12 @@ XM_HD inline bool row_get_after(WS& w, MatePath& m, int level, int p, HB& out) {
   if (level >= m.max_levels) { w.fail(Q_NEED_MORE); return false; }
   RowWin& r = m.rows[level];
   if (p < r.low) { r.mpc = p; r.low = p; r.cnt = 0; r.head = 0; }
+  XM_NOUNROLL
   for (int i = 0; i < r.cnt; i++) {
     const HB& b = r.ring[(r.head + i) % ROW_W];
     if (b.start > p) { out = b; return true; }
   }
+  XM_NOUNROLL
   while (true) {  // HashBlock_ParentRow.getAfter :44-59
     if (w.status != 0) return false;
     if (r.mpc >= m.q.len) return false;
@@ -311,6 +328,7 @@ XM_HD inline bool path_advance(WS& w, MatePath& m) {  // advanceToNextPosition :
 }
 XM_HD inline bool path_next_interesting_block(WS& w, MatePath& m, HB& out) {  // getNextInterestingBlock :27-50 + :68-96
   if (!m.cur_valid) return false;
+  XM_NOUNROLL
   while (true) {
     if (!path_advance(w, m)) return false;
     HB ext;
@@ -329,6 +347,7 @@ XM_HD inline bool path_next_interesting_block(WS& w, MatePath& m, HB& out) {  //
 // ---------------- Counting_HashBlockPath ----------------
 XM_HD inline void counter_update(MatePath& m, Counter& c, const WS& w) {  // HashBlockMatch_Counter.update :50-55,83-97
   int blen = w.ref->len[c.contig];
+  XM_NOUNROLL
   while (c.hist_processed < m.n_hist) {
     const Hist& h = m.history[c.hist_processed];
     if (!(c.has_last && h.ident == c.last_matched_ident)) {
@@ -355,9 +374,10 @@ XM_HD inline void counting_add_match(WS& w, MatePath& m, const SM& full, const H
     }
   }
 }
-XM_HD inline void counting_update_matches(WS& w, MatePath& m, const SM& sm, const HB& qb, int qb_num_matches) {  // updateMatches :193-252
+XM_FN void counting_update_matches(WS& w, MatePath& m, const SM& sm, const HB& qb, int qb_num_matches) {  // updateMatches :193-252
   int set = sm.rev ? 0 : 1;  // reversed matches live in "forwardMatchCounters" (:197-200)
   int cur = -1, lower = -1, higher = -1;
+  XM_NOUNROLL
   for (int i = 0; i < m.n_counters; i++) {
     const Counter& c = m.counters[i];
     if (c.set != set || c.contig != sm.contig) continue;
@@ -390,15 +410,17 @@ XM_INLINE bool counter_key_less(const Counter& a, const Counter& b) {
 }
 XM_HD inline int counters_next_sorted(const MatePath& m, int n, int after) {  // smallest key greater than counters[after] among [0, n)
   int best = -1;
+  XM_NOUNROLL
   for (int i = 0; i < n; i++) {
     if (after >= 0 && !counter_key_less(m.counters[after], m.counters[i])) continue;
     if (best < 0 || counter_key_less(m.counters[i], m.counters[best])) best = i;
   }
   return best;
 }
-XM_HD inline void counting_try_ensure_good(WS& w, MatePath& m) {  // :292-308
+XM_FN void counting_try_ensure_good(WS& w, MatePath& m) {  // :292-308
   if (!m.found_good && m.n_counters <= m.q.len) {
     int after = -1;
+    XM_NOUNROLL
     while (true) {
       int i = counters_next_sorted(m, m.n_counters, after);
       if (i < 0) break;
@@ -410,6 +432,7 @@ XM_HD inline void counting_try_ensure_good(WS& w, MatePath& m) {  // :292-308
 }
 XM_HD inline bool counting_next_block(WS& w, MatePath& m, HB& out) {  // getNextInterestingBlock :344-368
   m.pa_valid = 0;
+  XM_NOUNROLL
   while (true) {
     HB b;
     if (!path_next_interesting_block(w, m, b)) {
@@ -427,12 +450,14 @@ XM_HD inline bool counting_next_block(WS& w, MatePath& m, HB& out) {  // getNext
     return true;
   }
 }
-XM_HD inline bool counting_step(WS& w, MatePath& m) {  // step :40-179
+XM_FN bool counting_step(WS& w, MatePath& m) {  // step :40-179
   if (m.done || w.status != 0) return false;
+  PhaseClock pc_(&w.st_cyc[0]);
   HB qb;
   const TableD* t = nullptr;
   uint64_t word = 0;
   int count = 0;
+  XM_NOUNROLL
   while (true) {  // getNextInterestingMatch :371-388 + matchBlock (Readable_HashBlock_Database.java:22-38)
     if (!counting_next_block(w, m, qb)) {
       if (w.status != 0) return false;
@@ -457,6 +482,7 @@ XM_HD inline bool counting_step(WS& w, MatePath& m) {  // step :40-179
   bool invert = !qb.primary();
   const uint32_t* pos = (count > 0) ? t->positions + (word >> 24) : nullptr;
   int qlen = m.q.len;
+  XM_NOUNROLL
   for (int k = 0; k < count; k++) {
     int seq_id, rstart;
     w.ref->decode((int64_t)pos[k], seq_id, rstart);
@@ -464,6 +490,7 @@ XM_HD inline bool counting_step(WS& w, MatePath& m) {  // step :40-179
     int contig = seq_id >> 1, on_rc = seq_id & 1;
     SeqView cms = w.ref->contig(contig, on_rc);
     int mism = 0, mat = 0;
+    XM_NOUNROLL
     for (int d = 1; d < 20; d++) {  // :98-153
       int qi = qb.start - d;
       if (qi >= 0 && qi < qlen) {
@@ -500,8 +527,9 @@ XM_HD inline bool counting_step(WS& w, MatePath& m) {  // step :40-179
 // kind 0: good[0..G) with priority <= k     (findGoodPositionsHavingPriorityUpTo :406-433)
 // kind 2: good[0..G) with numDistinct <= k  (getBestMatches :471-493)
 // kind 1: all counters [0..G) in key order  (getAllPositions :435-452)
-XM_HD inline int list_next(WS& w, MatePath& m, const CL& l, int& cursor) {  // cursor starts at -1; returns counter index or -1
+XM_FN int list_next(WS& w, MatePath& m, const CL& l, int& cursor) {  // cursor starts at -1; returns counter index or -1
   if (l.kind == 1) { int i = counters_next_sorted(m, l.G, cursor); cursor = i; return i; }
+  XM_NOUNROLL
   for (int i = cursor + 1; i < l.G; i++) {
     Counter& c = m.counters[m.good[i]];
     bool take;
@@ -512,13 +540,15 @@ XM_HD inline int list_next(WS& w, MatePath& m, const CL& l, int& cursor) {  // c
   cursor = l.G;
   return -1;
 }
-XM_HD inline int list_size(WS& w, MatePath& m, const CL& l) {
+XM_FN int list_size(WS& w, MatePath& m, const CL& l) {
   if (l.kind == 1) return l.G;
   int n = 0, cur = -1;
+  XM_NOUNROLL
   while (list_next(w, m, l, cur) >= 0) n++;
   return n;
 }
-XM_HD inline CL counting_find_good_up_to(WS& w, MatePath& m, int priority) {  // :406-433
+XM_FN CL counting_find_good_up_to(WS& w, MatePath& m, int priority) {  // :406-433
+  XM_NOUNROLL
   while (true) {
     if (m.n_nonoverlap_visited >= wadd(priority, 1)) break;
     if (!counting_step(w, m)) break;
@@ -533,11 +563,12 @@ XM_HD inline CL counting_all_positions(WS& w, MatePath& m) {
   if (!m.pa_valid) { CL l; l.id = w.next_list_id++; l.kind = 1; l.G = m.n_counters; l.k = 0; l.size = m.n_counters; m.pa = l; m.pa_valid = 1; }
   return m.pa;
 }
-XM_HD inline CL counting_best_matches(WS& w, MatePath& m) {  // getBestMatches :471-493 + getNumGoodDistinctMismatches :458-470
+XM_FN CL counting_best_matches(WS& w, MatePath& m) {  // getBestMatches :471-493 + getNumGoodDistinctMismatches :458-470
   CL l; l.id = w.next_list_id++; l.kind = 2; l.G = 0; l.k = 0; l.size = 0;
   if (m.n_blocks_anywhere < 1) return l;
   if (m.min_num_distinct < 0) {
     int mn = m.n_nonoverlap_visited - 1;
+    XM_NOUNROLL
     for (int i = 0; i < m.n_good; i++) { Counter& c = m.counters[m.good[i]]; counter_update(m, c, w); if (mn >= c.num_distinct) mn = c.num_distinct; }
     m.min_num_distinct = mn;
   }
@@ -554,10 +585,11 @@ XM_HD inline int pc_count_priority(WS& w, const QM& q) {  // countPriority :314-
   return c1.priority + c2.priority;
 }
 // matchWithoutCache :136-246 + assembleQueryMatches :248-265
-XM_HD inline void pc_match_without_cache(WS& w, const CL* lists, int n_lists) {
+XM_FN void pc_match_without_cache(WS& w, const CL* lists, int n_lists) {
   w.n_assembled = 0;
   if (n_lists == 1) {
     int cur = -1, ci;
+    XM_NOUNROLL
     while ((ci = list_next(w, w.mp[0], lists[0], cur)) >= 0) {
       if (w.n_assembled >= w.cap_assembled) { w.fail(Q_NEED_MORE); return; }
       QM q; q.c[0] = ci; q.c[1] = -1; q.priority = w.mp[0].counters[ci].priority; q.hint = 0;
@@ -575,6 +607,7 @@ XM_HD inline void pc_match_without_cache(WS& w, const CL* lists, int n_lists) {
   if (w.status != 0) return;
   { int cur = -1, ci, k = 0; while ((ci = list_next(w, A, lists[first_ci], cur)) >= 0 && k < na) a_idx[k++] = ci; na = k; }
   int cur = -1, cb;
+  XM_NOUNROLL
   while ((cb = list_next(w, B, lists[second_ci], cur)) >= 0) {
     const Counter& c = B.counters[cb];
     bool b_rev = (c.set == 0);
@@ -585,16 +618,19 @@ XM_HD inline void pc_match_without_cache(WS& w, const CL* lists, int n_lists) {
     if (other_earlier) { s0 = c.offset - max_reverse; s1 = c.offset + w.pc_max_offset_between; }
     else { s0 = c.offset - w.pc_max_offset_between; s1 = c.offset + max_reverse; }
     int nn = 0;
+    XM_NOUNROLL
     for (int k = 0; k < na; k++) {
       const Counter& a = A.counters[a_idx[k]];
       bool a_qrev = ((a.set == 0) == (first_ci % 2 == 0));
       if (a_qrev != b_qrev || a.contig != c.contig) continue;
       if (a.offset < s0 || a.offset > s1) continue;
       int j = nn++;  // insertion sort by offset ascending
+      XM_NOUNROLL
       while (j > 0 && A.counters[near[j - 1]].offset > a.offset) { near[j] = near[j - 1]; j--; }
       near[j] = a_idx[k];
     }
     bool desc = b_qrev && nn > 1;
+    XM_NOUNROLL
     for (int t = 0; t < nn; t++) {
       int ai = near[desc ? nn - 1 - t : t];
       if (w.n_assembled >= w.cap_assembled) { w.fail(Q_NEED_MORE); w.scratch_top = mark; return; }
@@ -614,13 +650,15 @@ XM_HD inline void pc_match(WS& w, const CL* lists, int n_lists) {  // match :116
   if (same) for (int i = 0; i < n_lists; i++) if (w.pc_prev_ids[i] != lists[i].id) { same = false; break; }
   if (!same) {
     pc_match_without_cache(w, lists, n_lists);
+    XM_NOUNROLL
     for (int i = 0; i < n_lists; i++) w.pc_prev_ids[i] = lists[i].id;
     w.pc_have_prev = 1;
   }
 }
-XM_HD inline void pc_find_good_up_to(WS& w, int k) {  // findGoodPositionsWithPriorityUpTo :52-82
+XM_FN void pc_find_good_up_to(WS& w, int k) {  // findGoodPositionsWithPriorityUpTo :52-82
   CL lists[2];
   int n = w.query.n_seqs;
+  XM_NOUNROLL
   for (int i = 0; i < n; i++) {
     lists[i] = counting_find_good_up_to(w, w.mp[i], k);
     if (lists[i].size >= 1) w.pc_found_nonempty = 1;
@@ -629,10 +667,12 @@ XM_HD inline void pc_find_good_up_to(WS& w, int k) {  // findGoodPositionsWithPr
   pc_match(w, lists, n);
 }
 // optimisticGetBestMatches :84-98; returns the priority to filter on (filterMatchesHavingMinPriority selects the MAX, §9-5)
-XM_HD inline int pc_optimistic_best(WS& w) {
+XM_FN int pc_optimistic_best(WS& w) {
   CL lists[2];
   int n = w.query.n_seqs;
+  XM_NOUNROLL
   for (int i = 0; i < n; i++) {
+    XM_NOUNROLL
     while (true) {
       CL best = counting_best_matches(w, w.mp[i]);
       if (best.size == 1 || !counting_step(w, w.mp[i])) { lists[i] = best; break; }
@@ -641,14 +681,16 @@ XM_HD inline int pc_optimistic_best(WS& w) {
   }
   pc_match(w, lists, n);
   int mn = -1;
+  XM_NOUNROLL
   for (int i = 0; i < w.n_assembled; i++) if (mn < 0 || mn < w.assembled[i].priority) mn = w.assembled[i].priority;
   return mn;
 }
-XM_HD inline bool pc_find_partially_good(WS& w) {  // findPartiallyGoodPositions :26-50; false = empty list
+XM_FN bool pc_find_partially_good(WS& w) {  // findPartiallyGoodPositions :26-50; false = empty list
   if (w.query.n_seqs != 2) return false;
   if (!w.pc_found_nonempty) return false;
   CL lists[2];
   bool good = false, bad = false;
+  XM_NOUNROLL
   for (int i = 0; i < 2; i++) {
     CL here = counting_find_good_up_to(w, w.mp[i], JMAX);
     if (here.size == 0) { bad = true; here = counting_all_positions(w, w.mp[i]); } else good = true;
@@ -669,6 +711,7 @@ XM_HD inline SM qm_comp(const WS& w, const QM& q, int i) {
 }
 XM_INLINE bool qm_same_position(const QM& a, int na, const QM& b, int nb) {  // samePosition :83-95 (counters are unique per position)
   if (na != nb) return false;
+  XM_NOUNROLL
   for (int i = 0; i < na; i++) if (a.c[i] != b.c[i]) return false;
   return true;
 }

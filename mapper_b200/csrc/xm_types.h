@@ -9,9 +9,15 @@
 #if defined(__CUDACC__)
 #define XM_HD __host__ __device__
 #define XM_INLINE __host__ __device__ __forceinline__
+// XM_FN: a function that must exist ONCE in the kernel image.  The per-query code is large and every warp is in a
+// different phase of a different query, so code size is paid for in instruction-cache misses (ncu: stall_no_instruction).
+#define XM_FN __host__ __device__ __noinline__
+#define XM_NOUNROLL _Pragma("unroll 1")
 #else
 #define XM_HD
 #define XM_INLINE inline
+#define XM_FN inline
+#define XM_NOUNROLL
 #endif
 
 #if defined(XM_TRACE) && !defined(__CUDA_ARCH__)
@@ -28,6 +34,7 @@ enum : int {
   Q_OK = 0,
   Q_NEED_MORE = 1,        // workspace tier exhausted: the host re-runs the query in the next tier
   Q_OUT_FULL = 2,         // result arena exhausted: the host grows it and re-runs the query
+  Q_HARD = 3,             // first-pass kernel only: the cascade must go past the outer StraightAligner; re-run by the full kernel
   Q_AMBIGUOUS_QUERY = -2,
   Q_INDEX_TOO_SHORT = -3,
   Q_WORKSPACE = -5,
@@ -77,6 +84,7 @@ struct Params {
   double mutation, ins_start, ins_ext, del_start, del_ext, max_error_rate, unaligned, ambiguity, span;
   int max_num_matches;
   int start_free;  // StartingInsertionStartFree
+  const double* pen_tab;  // 256 entries [q << 4 | r] of the formula below, filled once per kernel launch (device: shared memory)
   XM_INLINE double starting_ins_start() const { return start_free ? 0.0 : ins_start; }
   XM_INLINE double min_possible_nonzero() const {
     double r = mutation;
@@ -84,10 +92,11 @@ struct Params {
     r = dmin(r, del_start + del_ext);
     return r;
   }
-  XM_INLINE double base_penalty(uint8_t q, uint8_t r) const {  // :156-180
+  XM_INLINE double base_penalty_formula(uint8_t q, uint8_t r) const {  // :156-180
     if (!bp_can_match(r, q)) return mutation;
     return ambiguity * ((bp_num_choices((uint8_t)(q | r)) - 1.0) / 3.0);
   }
+  XM_INLINE double base_penalty(uint8_t q, uint8_t r) const { return pen_tab[((int)q << 4) | (int)r]; }
 };
 
 // A sequence seen through QV's packed layout; rc != 0 is a ReverseComplementSequence view (QV/ReverseComplementSequence.java:14-17)
@@ -95,7 +104,9 @@ struct SeqView {
   const uint16_t* w;
   int len;
   int rc;
+  const uint8_t* bytes;  // optional: the same view unpacked to one code per byte (queries; filled by ws_init)
   XM_INLINE uint8_t at(int i) const {
+    if (bytes) return bytes[i];
     int j = rc ? len - 1 - i : i;
     uint8_t c = (uint8_t)((w[j >> 2] >> ((j & 3) << 2)) & 15);
     return rc ? bp_complement(c) : c;
@@ -110,7 +121,7 @@ struct RefD {
   const int32_t* len;        // n_contigs
   const int64_t* gstart;     // 2*n_contigs+1: global start of sequence id s (even: forward, odd: reverse complement)
   int64_t total_fr;
-  XM_INLINE SeqView contig(int c, int rc) const { SeqView v; v.w = words + word_off[c]; v.len = len[c]; v.rc = rc; return v; }
+  XM_INLINE SeqView contig(int c, int rc) const { SeqView v; v.w = words + word_off[c]; v.len = len[c]; v.rc = rc; v.bytes = nullptr; return v; }
   // QV/SequenceDatabase.decodePosition :170-209 — last sequence whose start <= encoded
   XM_INLINE void decode(int64_t g, int& seq_id, int& off) const {
     int lo = 0, hi = 2 * n_contigs;  // invariant: gstart[lo] <= g < gstart[hi]
@@ -159,9 +170,14 @@ struct OutArena {
   unsigned long long* stats;   // [0] probes [1] seeds [2] hits [3] straight [4] path calls [5] path steps [6] path cells
 };
 
+// On the device one WARP owns a query and all 32 lanes execute the per-query code in lock step on identical
+// values (warp-uniform control flow; data-parallel inner loops are split across lanes where marked).  Side effects
+// that must happen once per query are issued by lane 0 and their result is broadcast.
 XM_INLINE unsigned long long xm_atomic_add(unsigned long long* p, unsigned long long v) {
 #if defined(__CUDA_ARCH__)
-  return atomicAdd(p, v);
+  unsigned long long o = 0;
+  if ((threadIdx.x & 31) == 0) o = atomicAdd(p, v);
+  return __shfl_sync(0xffffffffu, o, 0);
 #else
   unsigned long long o = *p; *p = o + v; return o;
 #endif

@@ -12,7 +12,7 @@ using namespace xm;
 
 namespace {
 struct CParams { double mutation, ins_start, ins_ext, del_start, del_ext, max_error_rate, unaligned, ambiguity, span; int32_t max_num_matches, enable_gapmers; };
-struct Emu { HostModel m; std::string err; };
+struct Emu { HostModel m; std::string err; double pen[256]; };
 }
 
 extern "C" {
@@ -23,6 +23,8 @@ void* xe_create(const CParams* p) {
   q.mutation = p->mutation; q.ins_start = p->ins_start; q.ins_ext = p->ins_ext; q.del_start = p->del_start; q.del_ext = p->del_ext;
   q.max_error_rate = p->max_error_rate; q.unaligned = p->unaligned; q.ambiguity = p->ambiguity; q.span = p->span;
   q.max_num_matches = p->max_num_matches; q.start_free = 0;
+  fill_pen_tab(q, e->pen, 0, 1);
+  q.pen_tab = e->pen;
   e->m.gapmers = p->enable_gapmers;
   return e;
 }
@@ -76,17 +78,38 @@ void* xe_align_batch(void* h, int nq, const uint16_t* packed, const int64_t* seq
   unsigned long long used[3] = {0, 0, 0};
   std::vector<unsigned long long> stats(8, 0);
   std::vector<int> tier_count(XM_NUM_TIERS, 0);
+  int n_easy = 0;
   std::mutex mu;
   int nt = std::max(1, threads);
   auto work = [&](int t) {
     std::vector<std::vector<char>> arenas((size_t)XM_NUM_TIERS);
+    std::vector<char> easy_arena;
+    int leasy = 0;
     unsigned long long lstats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int ltier[XM_NUM_TIERS] = {0, 0, 0};
     for (int qi = t; qi < nq; qi += nt) {
       QueryIn q; q.n_seqs = n_seqs[qi];
-      for (int s = 0; s < q.n_seqs; s++) { int64_t sid = first[(size_t)qi] + s; q.seq[s].w = packed + seq_word_off[sid]; q.seq[s].len = seq_len[sid]; q.seq[s].rc = 0; }
+      for (int s = 0; s < q.n_seqs; s++) { int64_t sid = first[(size_t)qi] + s; q.seq[s].w = packed + seq_word_off[sid]; q.seq[s].len = seq_len[sid]; q.seq[s].rc = 0; q.seq[s].bytes = nullptr; }
+      if (q.n_seqs < 2) { q.seq[1] = q.seq[0]; q.seq[1].len = 0; }
       q.expected_inner = q.n_seqs > 1 ? expected_inner[qi] : 0; q.per_penalty = q.n_seqs > 1 ? per_penalty[qi] : 1;
       int status = Q_NEED_MORE;
+      {  // first pass: the EASY instantiation in its small arena, exactly as the library's first kernel runs it
+        long long bytes = easy_arena_bytes(max_len, 2);
+        if ((long long)easy_arena.size() < bytes) easy_arena.resize((size_t)bytes);
+        WS w;
+        OutArena out; out.q = oq.data(); out.choices = choices.data(); out.cap_choices = capc; out.sas = sas.data(); out.cap_sas = caps;
+        out.blocks = blocks.data(); out.cap_blocks = capb; out.stats = nullptr;
+        OutQuery rec; rec.status = 0; rec.n_comp = 1; rec.n_choice[0] = rec.n_choice[1] = 0; rec.choice_first[0] = rec.choice_first[1] = 0;
+        if (ws_init(w, easy_arena.data(), bytes, &ref, &ix, &dup, M.prm, q)) {
+          std::lock_guard<std::mutex> lock(mu);
+          out.used = used;
+          align_query<true>(w, out, rec);
+          if (w.status != Q_HARD && w.status != Q_NEED_MORE) {
+            status = w.status; rec.status = status; oq[(size_t)qi] = rec; leasy++;
+            lstats[0] += w.st_probes; lstats[1] += w.st_seeds; lstats[2] += w.st_hits; lstats[3] += w.st_straight;
+          }
+        }
+      }
       for (int tier = 0; tier < XM_NUM_TIERS && tier <= max_tier && status == Q_NEED_MORE; tier++) {
         long long bytes = tier_arena_bytes(tier, max_len, 2);
         if ((long long)arenas[(size_t)tier].size() < bytes) arenas[(size_t)tier].resize((size_t)bytes);
@@ -99,7 +122,7 @@ void* xe_align_batch(void* h, int nq, const uint16_t* packed, const int64_t* seq
         {
           std::lock_guard<std::mutex> lock(mu);  // the bump counters are plain integers on the host
           out.used = used;
-          align_query(w, out, rec);
+          align_query<false>(w, out, rec);
         }
         status = w.status;
         rec.status = status;
@@ -114,12 +137,14 @@ void* xe_align_batch(void* h, int nq, const uint16_t* packed, const int64_t* seq
     std::lock_guard<std::mutex> lock(mu);
     for (int i = 0; i < 8; i++) stats[(size_t)i] += lstats[i];
     for (int i = 0; i < XM_NUM_TIERS; i++) tier_count[(size_t)i] += ltier[i];
+    n_easy += leasy;
   };
   if (nt == 1) work(0);
   else { std::vector<std::thread> th; for (int t = 0; t < nt; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
   ResultsHost* R = new ResultsHost();
   R->assemble(nq, oq.data(), choices.data(), sas.data(), blocks.data());
-  R->stats.assign(16, 0);
+  R->stats.assign(32, 0);
+  R->stats[25] = n_easy;
   R->stats[2] = tier_count[0]; R->stats[3] = tier_count[1]; R->stats[4] = tier_count[2];
   R->stats[5] = (int64_t)stats[0]; R->stats[6] = (int64_t)stats[1]; R->stats[7] = (int64_t)stats[2]; R->stats[8] = (int64_t)stats[3];
   R->stats[9] = (int64_t)stats[4]; R->stats[10] = (int64_t)stats[5]; R->stats[11] = (int64_t)stats[6];

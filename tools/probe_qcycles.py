@@ -28,8 +28,10 @@ for it in range(2):
     r = g.align_batch(batch)
 st = r["stats"]
 S = capi.STAT
+print("easy pass queries:", int(st[S["easy"]]), "ms:", st[S["easy_ns"]] / 1e6)
 print("tiers queries:", [int(st[S["tier%d" % t]]) for t in range(3)], "tier ms:", [st[S["tier%d_ns" % t]] / 1e6 for t in range(3)], "total kernel ms:", st[S["kernel_ns"]] / 1e6)
 print("probes %d seeds %d hits %d straight %d path_calls %d path_steps %d path_cells %d" % tuple(int(st[S[k]]) for k in ["probes", "seeds", "hits", "straight", "path_calls", "path_steps", "path_cells"]))
+print("phase cycles (sum over queries): " + "  ".join("%s=%.3e" % (k, float(st[S["cyc_" + k]])) for k in ["seed", "straight", "hba", "path", "tables", "spare", "total"]))
 cy = r["q_cycles"].astype(np.float64)
 nq = len(cy)
 # classify reads by result shape
