@@ -1535,14 +1535,18 @@ XM_HD inline bool ws_init(WS& w, char* arena, long long arena_bytes, const RefD*
   for (int i = 0; i < 6; i++) w.st_cyc[i] = 0;
   long long top = 0;
   auto take = [&](long long bytes) -> char* { bytes = (bytes + 15) & ~15LL; char* p = arena + top; top += bytes; return p; };
-  int max_len = imax(q.seq[0].len, q.n_seqs > 1 ? q.seq[1].len : 0);
-  // pyramid rows: a block's level never exceeds its length, so max_len + 2 levels always suffice; small tiers take fewer
-  long long fixed = arena_bytes / 4;
-  int levels = max_len + 2;
-  long long per_mate_rows = (long long)levels * (long long)sizeof(RowWin);
-  if (per_mate_rows * q.n_seqs > fixed) levels = (int)(fixed / q.n_seqs / (long long)sizeof(RowWin));
-  if (levels < 4) return false;
-  long long rest = arena_bytes - (long long)levels * (long long)sizeof(RowWin) * q.n_seqs - 256 - 2 * (long long)(q.seq[0].len + q.seq[1].len + 64);
+  // pyramids: a block's level never exceeds its length, so len + 2 levels always suffice; ~4 blocks per base are
+  // typical, 8 are provisioned when the arena allows (pyr_build asks for the next tier when a read needs more)
+  long long pyr_total = 0;
+  long long pyr_bytes[2] = {0, 0};
+  XM_NOUNROLL
+  for (int i = 0; i < q.n_seqs; i++) { pyr_bytes[i] = pyr_arena_bytes(q.seq[i].len); pyr_total += pyr_bytes[i]; }
+  if (pyr_total > arena_bytes / 2) {
+    XM_NOUNROLL
+    for (int i = 0; i < q.n_seqs; i++) pyr_bytes[i] = (long long)((double)pyr_bytes[i] * (double)(arena_bytes / 2) / (double)pyr_total) & ~15LL;
+    pyr_total = arena_bytes / 2;
+  }
+  long long rest = arena_bytes - pyr_total - 512 - 2 * (long long)(q.seq[0].len + (q.n_seqs > 1 ? q.seq[1].len : 0) + 64);
   if (rest < 4096) return false;
   // split of the remainder: counters 12%, history+pending 6%, assembled 8%, store 24%, scratch 50%
   int cap_counters = (int)(rest * 12 / 100 / q.n_seqs / (long long)(sizeof(Counter) + sizeof(int)));
@@ -1568,9 +1572,21 @@ XM_HD inline bool ws_init(WS& w, char* arena, long long arena_bytes, const RefD*
       w.query.seq[i].bytes = nullptr;
     }
     m.q = w.query_view(i, m.path_is_rc);
-    m.rows = (RowWin*)take((long long)levels * (long long)sizeof(RowWin)); m.max_levels = levels;
+    {
+      int len = q.seq[i].len;
+      Pyr& P = m.pyr;
+      P.cap_levels = len + 2;
+      long long lev_bytes = ((long long)(P.cap_levels + 1) * 4 + 15) & ~15LL;
+      long long cap = (pyr_bytes[i] - lev_bytes - 64) / 20;
+      if (cap < len + 8) return false;
+      if (cap > 32000) cap = 32000;
+      cap &= ~7LL;
+      P.cap_blocks = (int)cap;
+      P.level_off = (int32_t*)take(lev_bytes);
+      P.blk = (HB16*)take(cap * 16); P.child = (int16_t*)take(cap * 2); P.up = (int16_t*)take(cap * 2);
+      P.n_levels = 0;
+    }
     XM_NOUNROLL
-    for (int l = 0; l < levels; l++) { m.rows[l].mpc = -1; m.rows[l].low = -1; m.rows[l].head = 0; m.rows[l].cnt = 0; }
     m.counters = (Counter*)take((long long)cap_counters * (long long)sizeof(Counter)); m.n_counters = 0; m.cap_counters = cap_counters;
     m.good = (int*)take((long long)cap_counters * 4); m.n_good = 0;
     m.history = (Hist*)take((long long)cap_hist * (long long)sizeof(Hist)); m.n_hist = 0; m.cap_hist = cap_hist;
@@ -1588,6 +1604,8 @@ XM_HD inline bool ws_init(WS& w, char* arena, long long arena_bytes, const RefD*
   long long scratch_bytes = (arena_bytes - top - 64) & ~15LL;
   if (scratch_bytes < 1024) return false;
   w.scratch = take(scratch_bytes); w.scratch_size = scratch_bytes; w.scratch_top = 0;
+  XM_NOUNROLL
+  for (int i = 0; i < q.n_seqs; i++) if (!pyr_build(w, w.mp[i])) break;  // sets w.status itself (next tier, or ambiguous query)
   return true;
 }
 

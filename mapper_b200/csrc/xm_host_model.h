@@ -295,15 +295,15 @@ static const int XM_NUM_TIERS = 3;
 // Workspace per warp of the first-pass ("easy") kernel: pyramid rows, counters, candidate lists and a handful of
 // single-block alignments; no lattice.
 inline long long easy_arena_bytes(int max_seq_len, int n_seqs_max) {
-  long long rows = (long long)(max_seq_len + 2) * (long long)sizeof(RowWin) * n_seqs_max;
-  long long b = std::max<long long>(64 * 1024, rows / 2 + 32 * 1024);
+  long long rows = pyr_arena_bytes(max_seq_len) * n_seqs_max;
+  long long b = std::max<long long>(64 * 1024, rows + 48 * 1024 + 8 * (long long)max_seq_len);
   return (b + 255) & ~255LL;
 }
 // Workspace per WARP (one warp owns one query at a time).  Tier 0 is sized to hold a PathAligner lattice over the
 // whole read (so that almost nothing is re-run) whenever one resident wave of such arenas fits the budget; otherwise
 // it shrinks towards "a lattice over a BlockAligner piece".  Each further tier is 4x larger (fewer warps).
 inline long long tier_arena_bytes(int tier, int max_seq_len, int n_seqs_max, long long budget = 24LL << 30, long long resident_warps = 148 * 16) {
-  long long rows = (long long)(max_seq_len + 2) * (long long)sizeof(RowWin) * n_seqs_max;
+  long long rows = pyr_arena_bytes(max_seq_len) * n_seqs_max;
   long long grid = (long long)(max_seq_len + 2) * (long long)(max_seq_len * 2 + 64) * 26;  // full-read PathAligner grid + heap share
   long long small = std::max<long long>(256 * 1024, rows * 2 + grid / 4);
   long long full = rows * 2 + grid * 5 / 2;

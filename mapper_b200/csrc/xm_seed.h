@@ -81,24 +81,64 @@ XM_FN HB merge_blocks(const HB& L, const HB& R, int level) {  // HashBlock(seq,s
 XM_INLINE int ext_char_to_int(uint8_t c) { return c == 1 ? 1 : c == 2 ? 2 : c == 4 ? 3 : c == 8 ? 4 : 0; }
 
 // HashBlock.withGapAndExtension :67-150. false = null
+// h = fold(h * 7654337 + value(base)) over n bases starting at `from`, stepping `dir` (HashBlock.java:107-135).
+// Integer wrap-around arithmetic is a ring, so on the device 32 lanes each take one base of a 32-base chunk,
+// weight it with the matching power of the multiplier and add the chunk up with shuffles: same 32-bit result.
+XM_HD inline int32_t ext_hash(const SeqView& seq, int from, int n, int dir, bool complement) {
+  int32_t h = 0;
+#if defined(__CUDA_ARCH__)
+  constexpr uint32_t M1 = 7654337u, M2 = M1 * M1, M4 = M2 * M2, M8 = M4 * M4, M16 = M8 * M8, M32 = M16 * M16;
+  const int lane = (int)(threadIdx.x & 31);
+  XM_NOUNROLL
+  for (int base = 0; base < n; base += 32) {
+    const int cnt = imin(32, n - base);
+    uint32_t term = 0;
+    if (lane < cnt) {
+      uint8_t c = seq.at(from + dir * (base + lane));
+      if (complement) c = bp_complement(c);
+      const int e = cnt - 1 - lane;
+      uint32_t pw = 1u;
+      if (e & 1) pw *= M1;
+      if (e & 2) pw *= M2;
+      if (e & 4) pw *= M4;
+      if (e & 8) pw *= M8;
+      if (e & 16) pw *= M16;
+      term = (uint32_t)ext_char_to_int(c) * pw;
+    }
+    term += __shfl_xor_sync(0xffffffffu, term, 16);
+    term += __shfl_xor_sync(0xffffffffu, term, 8);
+    term += __shfl_xor_sync(0xffffffffu, term, 4);
+    term += __shfl_xor_sync(0xffffffffu, term, 2);
+    term += __shfl_xor_sync(0xffffffffu, term, 1);
+    uint32_t pc = (cnt == 32) ? M32 : 1u;
+    if (cnt != 32) { if (cnt & 1) pc *= M1; if (cnt & 2) pc *= M2; if (cnt & 4) pc *= M4; if (cnt & 8) pc *= M8; if (cnt & 16) pc *= M16; }
+    h = (int32_t)((uint32_t)h * pc + term);
+  }
+#else
+  for (int k = 0; k < n; k++) {
+    uint8_t c = seq.at(from + dir * k);
+    if (complement) c = bp_complement(c);
+    h = wadd(wmul(h, 7654337), ext_char_to_int(c));
+  }
+#endif
+  return h;
+}
 XM_FN bool with_gap_and_extension(const HB& b, const SeqView& seq, HB& out) {
   if (b.gap_dir == 0) { out = b; return true; }
   int target = b.len + (jabs(b.fwd > b.rev ? b.fwd : b.rev) % 3) + b.extra;
   int gap = b.len / 2;
   int ext = target - gap;
-  int32_t h = 0;
+  int32_t h;
   HB r;
   if (b.gap_dir < 0) {
     int ext_end = b.start - gap, ext_start = ext_end - ext;
     if (ext_start < 0) return false;
-    XM_NOUNROLL
-    for (int i = ext_end - 1; i >= ext_start; i--) h = wadd(wmul(h, 7654337), ext_char_to_int(seq.at(i)));
+    h = ext_hash(seq, ext_end - 1, ext, -1, false);
     r.start = ext_start; r.len = ext + gap + b.len;
   } else {
     int ext_start = b.end() + gap, ext_end = ext_start + ext;
     if (ext_end > seq.len) return false;
-    XM_NOUNROLL
-    for (int i = ext_start; i < ext_end; i++) h = wadd(wmul(h, 7654337), ext_char_to_int(bp_complement(seq.at(i))));
+    h = ext_hash(seq, ext_start, ext, 1, true);
     r.start = b.start; r.len = b.len + gap + ext;
   }
   r.fwd = wadd(b.fwd, h); r.rev = wadd(b.rev, h);
@@ -109,8 +149,20 @@ XM_FN bool with_gap_and_extension(const HB& b, const SeqView& seq, HB& out) {
 }
 
 // ---------------- workspace ----------------
-static const int ROW_W = 8;
-struct RowWin { int mpc, low, head, cnt; HB ring[ROW_W]; };
+// The query's hash-block pyramid (HashBlock_Pyramid / HashBlock_ParentRow), built EAGERLY and in full when the
+// workspace is set up: a block is a pure function of the bases it covers, so the reference's lazily grown rows and this
+// table hold the same blocks.  Level L+1 = merge(b[i], b[i+1]) of the consecutive level-L blocks that satisfy
+// shouldMergeBlocks (HashBlock_ParentRow.java:69-127,200-208); on the device the 32 lanes take 32 pairs per round and
+// compact the survivors with a ballot.  child/up are the links the seed walk follows instead of searching.
+XM_INLINE long long pyr_arena_bytes(int len) { return (((long long)(len + 3) * 4 + 15) & ~15LL) + 64 + 20LL * (8LL * len + 64); }
+struct HB16 { int16_t start, len; int32_t fwd, rev; uint8_t flags; int8_t gap_dir; int16_t extra; };
+struct Pyr {
+  HB16* blk;          // all levels back to back, each level ascending by start
+  int16_t* child;     // per block: index within the level below of its left parent (level 0: -1)
+  int16_t* up;        // per block: index within the level above of the block it is the left parent of, or -1
+  int32_t* level_off; // n_levels + 1
+  int n_levels, cap_blocks, cap_levels;
+};
 
 struct Counter {  // M/HashBlockMatch_Counter.java
   int set, contig, offset;  // set 0 = reversed matches ("forwardMatchCounters"), 1 = the others
@@ -127,7 +179,7 @@ struct QM { int c[2]; int priority; int hint; };          // M/QueryMatch.java, 
 struct MatePath {
   SeqView q;  // sequence the path walks (mate 2: reverse complement of the read, AlignerWorker.java:317-318)
   int mate, path_is_rc;
-  RowWin* rows; int max_levels;
+  Pyr pyr; int cur_idx;  // cur_idx: index of cur within level batch_index (-1: cur is not a pyramid block)
   // HashBlockPath
   int batch_index, cur_valid; HB cur; int have_gapmer; HB gapmer;
   int have_prev, have_prevprev; int32_t prev_fwd, prevprev_fwd; long long gapmer_serial;
@@ -186,61 +238,135 @@ XM_INLINE SM counter_match(const MatePath& m, const Counter& c) {
   SM s; s.mate = m.mate; s.rev = (c.set == 0) ? 1 : 0; s.contig = c.contig; s.offset = c.offset; s.from_hash = 1; return s;
 }
 
-// ---------------- rows ----------------
-XM_HD bool row_get_after(WS& w, MatePath& m, int level, int p, HB& out);
-
-XM_HD inline void row_push(RowWin& r, const HB& b) {
-  if (r.cnt == ROW_W) {  // evict the oldest: the window is now complete only for starts > its start
-    int es = r.ring[r.head].start;
-    if (es > r.low) r.low = es;
-    r.head = (r.head + 1) % ROW_W; r.cnt--;
-  }
-  r.ring[(r.head + r.cnt) % ROW_W] = b; r.cnt++;
+// ---------------- pyramid ----------------
+XM_INLINE HB16 base_block16(uint8_t code, int index) {  // HashBlock(char,int) + hashChar :60-65,171-188
+  HB16 b;
+  b.start = (int16_t)index; b.len = 1; b.gap_dir = 0; b.extra = 0;
+  b.fwd = (code == 1) ? 0 : (code == 2) ? 1 : (code == 4) ? 2 : 3;
+  bool rml = (b.fwd / 2 == 0), nrml = (b.fwd % 2 == 0);
+  b.flags = (uint8_t)((rml ? 1 : 2) | (nrml ? 4 : 8));
+  b.rev = 3 - b.fwd;
+  return b;
 }
-
-// HashBlock_ParentRow.maybeMakeBlock :69-127 (single blocks only)
-XM_FN void row_maybe_make(WS& w, MatePath& m, int level) {
-  RowWin& r = m.rows[level];
-  HB left, right;
-  if (!row_get_after(w, m, level - 1, r.mpc, left)) { r.mpc = m.q.len; return; }
-  r.mpc = left.start;
-  if (row_get_after(w, m, level - 1, left.start, right)) {
-    if (left.end() >= right.start && (left.rmr() || right.rml())) row_push(r, merge_blocks(left, right, level));  // shouldMergeBlocks :200-208
+XM_HD inline HB16 merge_blocks16(const HB16& L, const HB16& R) {  // HashBlock(seq,start,len,l,r) :20-44 + mergeHashes :192-259
+  HB16 b;
+  int blen = (R.start + R.len) - L.start;
+  b.start = L.start; b.len = (int16_t)blen;
+  b.fwd = merge_hash(L.len, L.fwd, R.len, R.fwd);
+  b.rev = merge_hash(R.len, R.rev, L.len, L.rev);
+  bool rml = true, rmr = true, nrml = true, nrmr = true;
+  int anchor = 0;  // 0 none, 1 left, 2 right
+  if (L.fwd != R.rev) anchor = (L.fwd > R.rev) ? 2 : 1;
+  if (anchor != 0 && b.fwd != b.rev) {
+    const HB16& A = (anchor == 2) ? R : L;
+    const HB16& O = (anchor == 2) ? L : R;
+    bool is_reverse = b.fwd < b.rev;
+    bool invert = is_reverse == (anchor == 2);
+    bool aL = (A.flags & 4) != 0, aR = (A.flags & 8) != 0;
+    if (aL && aR) { if (anchor == 2) aR = false; else aL = false; }
+    bool oL = (O.flags & 4) != 0, oR = (O.flags & 8) != 0;
+    if (oL && oR) { if (anchor == 1) oL = false; else oR = false; }  // "other == rightParent" <=> anchor is left
+    rml = aL != invert; rmr = aR != invert; nrml = oL != invert; nrmr = oR != invert;
   }
+  if (L.len != R.len) { rml = (L.len > R.len); rmr = !rml; nrml = !rml; nrmr = !nrml; }
+  if (b.fwd != b.rev) {
+    if (rml && rmr) { rml = (b.fwd > b.rev); rmr = !rml; }
+    if (nrml && nrmr) { nrml = rml; nrmr = !nrml; }
+  }
+  b.flags = (uint8_t)((rml ? 1 : 0) | (rmr ? 2 : 0) | (nrml ? 4 : 0) | (nrmr ? 8 : 0));
+  b.gap_dir = 0;
+  if (rml != rmr) b.gap_dir = rml ? 1 : -1;
+  else if (L.fwd != R.rev) b.gap_dir = (L.fwd > R.rev) ? 1 : -1;
+  b.extra = (int16_t)((L.len + R.len - blen) / 4);
+  return b;
 }
-
-XM_HD inline bool row_get_after(WS& w, MatePath& m, int level, int p, HB& out) {
-  if (w.status != 0) return false;
-  if (level == 0) {  // HashBlock_BaseRow.get :27-59
-    int idx = p + 1;
-    if (idx >= m.q.len) return false;
-    uint8_t code = m.q.at(idx);
-    if (bp_is_ambiguous(code)) { w.fail(Q_AMBIGUOUS_QUERY); return false; }
-    out = base_block(code, idx);
-    return true;
-  }
-  if (level >= m.max_levels) { w.fail(Q_NEED_MORE); return false; }
-  RowWin& r = m.rows[level];
-  if (p < r.low) { r.mpc = p; r.low = p; r.cnt = 0; r.head = 0; }
+XM_INLINE HB pyr_block(const Pyr& P, int level, int idx) {
+  const HB16 c = P.blk[P.level_off[level] + idx];
+  HB b;
+  b.start = c.start; b.len = c.len; b.used = c.len; b.fwd = c.fwd; b.rev = c.rev; b.gap_dir = c.gap_dir; b.flags = c.flags; b.extra = c.extra;
+  b.ident = ((long long)level << 40) | (long long)c.start;
+  return b;
+}
+XM_INLINE int pyr_level_size(const Pyr& P, int level) { return (level >= 0 && level < P.n_levels) ? P.level_off[level + 1] - P.level_off[level] : 0; }
+// first block of `level` whose start > p (HashBlock_ParentRow.getAfter :44-59 / HashBlock_BaseRow.get), or -1
+XM_FN int pyr_find_after(const Pyr& P, int level, int p) {
+  int n = pyr_level_size(P, level);
+  const HB16* b = P.blk + (n > 0 ? P.level_off[level] : 0);
+  int lo = 0, hi = n;
   XM_NOUNROLL
-  for (int i = 0; i < r.cnt; i++) {
-    const HB& b = r.ring[(r.head + i) % ROW_W];
-    if (b.start > p) { out = b; return true; }
-  }
+  while (lo < hi) { int mid = (lo + hi) >> 1; if ((int)b[mid].start > p) hi = mid; else lo = mid + 1; }
+  return lo < n ? lo : -1;
+}
+XM_FN bool pyr_build(WS& w, MatePath& m) {
+  Pyr& P = m.pyr;
+  const int len = m.q.len;
+  if (len > P.cap_blocks || P.cap_levels < 2 || len > 32000) { w.fail(Q_NEED_MORE); return false; }
+#if defined(__CUDA_ARCH__)
+  const int lane = (int)(threadIdx.x & 31);
+  const unsigned lt_mask = (1u << lane) - 1u;
+  bool amb = false;
   XM_NOUNROLL
-  while (true) {  // HashBlock_ParentRow.getAfter :44-59
-    if (w.status != 0) return false;
-    if (r.mpc >= m.q.len) return false;
-    if (r.cnt > 0) {
-      const HB& last = r.ring[(r.head + r.cnt - 1) % ROW_W];
-      if (last.start > p) { out = last; return true; }
+  for (int k = lane; k < len; k += 32) {
+    uint8_t code = m.q.at(k);
+    amb |= bp_is_ambiguous(code);
+    P.blk[k] = base_block16(code, k); P.child[k] = -1; P.up[k] = -1;
+  }
+  amb = __any_sync(0xffffffffu, amb);
+#else
+  bool amb = false;
+  for (int k = 0; k < len; k++) {
+    uint8_t code = m.q.at(k);
+    amb |= bp_is_ambiguous(code);
+    P.blk[k] = base_block16(code, k); P.child[k] = -1; P.up[k] = -1;
+  }
+#endif
+  P.level_off[0] = 0; P.level_off[1] = len; P.n_levels = 1;
+  // IUPAC-ambiguous query bases need MultiHashBlocks (HashBlock_ParentRow.java:97-120), which the device does not build
+  if (amb) { w.fail(Q_AMBIGUOUS_QUERY); return false; }
+  int prev_off = 0, n_prev = len, level = 1;
+  XM_NOUNROLL
+  while (n_prev >= 2) {
+    if (level >= P.cap_levels) { w.fail(Q_NEED_MORE); return false; }
+    const int cur_off = prev_off + n_prev;
+    int n_new = 0;
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+    XM_NOUNROLL
+    for (int base = 0; base < n_prev - 1; base += 32) {
+      const int i = base + lane;
+      const bool valid = i < n_prev - 1;
+      bool keep = false;
+      HB16 L, R;
+      if (valid) {
+        L = P.blk[prev_off + i]; R = P.blk[prev_off + i + 1];
+        keep = ((int)L.start + (int)L.len >= (int)R.start) && ((L.flags & 2) || (R.flags & 1));  // shouldMergeBlocks :200-208
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, keep);
+      const int total = __popc(mask);
+      if (cur_off + n_new + total > P.cap_blocks) { w.fail(Q_NEED_MORE); return false; }
+      const int pos = n_new + __popc(mask & lt_mask);
+      if (keep) { P.blk[cur_off + pos] = merge_blocks16(L, R); P.child[cur_off + pos] = (int16_t)i; P.up[cur_off + pos] = -1; }
+      if (valid) P.up[prev_off + i] = keep ? (int16_t)pos : (int16_t)-1;
+      n_new += total;
     }
-    row_maybe_make(w, m, level);
+    __syncwarp();
+#else
+    for (int i = 0; i < n_prev - 1; i++) {
+      const HB16 L = P.blk[prev_off + i], R = P.blk[prev_off + i + 1];
+      bool keep = ((int)L.start + (int)L.len >= (int)R.start) && ((L.flags & 2) || (R.flags & 1));
+      if (keep) {
+        if (cur_off + n_new + 1 > P.cap_blocks) { w.fail(Q_NEED_MORE); return false; }
+        P.blk[cur_off + n_new] = merge_blocks16(L, R); P.child[cur_off + n_new] = (int16_t)i; P.up[cur_off + n_new] = -1;
+        P.up[prev_off + i] = (int16_t)n_new;
+        n_new++;
+      } else P.up[prev_off + i] = -1;
+    }
+#endif
+    if (n_new == 0) break;
+    P.level_off[level + 1] = cur_off + n_new; P.n_levels = level + 1;
+    prev_off = cur_off; n_prev = n_new; level++;
   }
-}
-XM_HD inline bool row_get(WS& w, MatePath& m, int level, int index, HB& out) {  // :21-26
-  if (!row_get_after(w, m, level, index - 1, out)) return false;
-  return out.start == index;
+  return true;
 }
 
 // ---------------- index reads (Readable_HashBlock_Database / PackedMap) ----------------
@@ -273,7 +399,7 @@ XM_HD inline int ix_max_num_matches_allowed(WS& w, const HB& b) {  // :82-90
 
 // ---------------- HashBlockPath ----------------
 XM_HD inline void path_init(WS& w, MatePath& m) {
-  m.batch_index = -1; m.cur_valid = 1;
+  m.batch_index = -1; m.cur_valid = 1; m.cur_idx = -1;
   HB d; d.start = 0; d.len = 0; d.used = 0; d.fwd = 0; d.rev = 0; d.gap_dir = 0; d.flags = 0; d.extra = 0; d.ident = -1;  // new HashBlock(0, 0)
   m.cur = d; m.have_gapmer = 0; m.have_prev = 0; m.have_prevprev = 0; m.prev_fwd = 0; m.prevprev_fwd = 0; m.gapmer_serial = 0;
 }
@@ -288,19 +414,34 @@ XM_HD inline bool path_with_gap(WS& w, MatePath& m, HB& out) {  // :197-203
   out = m.gapmer;
   return true;
 }
-XM_HD inline void path_move_right(WS& w, MatePath& m) {  // :125-128
-  HB n;
-  m.cur_valid = row_get_after(w, m, m.batch_index, m.cur.start, n) ? 1 : 0;
-  if (m.cur_valid) m.cur = n;
+XM_HD inline void path_set(MatePath& m, int level, int idx) { m.batch_index = level; m.cur_idx = idx; m.cur = pyr_block(m.pyr, level, idx); m.cur_valid = 1; }
+XM_HD inline void path_move_right(WS& w, MatePath& m) {  // :125-128  row.getAfter(cur.start)
+  int nxt = -1;
+  if (m.batch_index >= 0) {
+    if (m.cur_idx >= 0) { nxt = m.cur_idx + 1; if (nxt >= pyr_level_size(m.pyr, m.batch_index)) nxt = -1; }
+    else nxt = pyr_find_after(m.pyr, m.batch_index, m.cur.start);
+  }
+  if (nxt >= 0) path_set(m, m.batch_index, nxt); else m.cur_valid = 0;
   m.have_gapmer = 0;
 }
-XM_HD inline void path_move_down(WS& w, MatePath& m) {  // :99-108
-  m.batch_index--;
-  path_move_right(w, m);
+XM_HD inline void path_move_down(WS& w, MatePath& m) {  // :99-108  the row below, first block after cur.start
+  int level = m.batch_index - 1;
+  int nxt;
+  if (m.cur_idx >= 0) { nxt = (int)m.pyr.child[m.pyr.level_off[m.batch_index] + m.cur_idx] + 1; if (nxt >= pyr_level_size(m.pyr, level)) nxt = -1; }
+  else nxt = pyr_find_after(m.pyr, level, m.cur.start);
+  m.batch_index = level;
+  if (nxt >= 0) path_set(m, level, nxt); else { m.cur_valid = 0; m.cur_idx = -1; }
+  m.have_gapmer = 0;
 }
-XM_HD inline void path_move_up_or_right(WS& w, MatePath& m) {  // :111-122
-  HB up;
-  if (row_get(w, m, m.batch_index + 1, m.cur.start, up) && up.start <= m.cur.start) { m.batch_index++; m.cur = up; m.have_gapmer = 0; }
+XM_HD inline void path_move_up_or_right(WS& w, MatePath& m) {  // :111-122  the row above, block starting exactly at cur.start
+  int u = -1;
+  if (m.cur_idx >= 0) u = (int)m.pyr.up[m.pyr.level_off[m.batch_index] + m.cur_idx];
+  else {
+    int level = m.batch_index + 1;
+    int f = pyr_find_after(m.pyr, level, m.cur.start - 1);
+    if (f >= 0 && (int)m.pyr.blk[m.pyr.level_off[level] + f].start == m.cur.start) u = f;
+  }
+  if (u >= 0) { path_set(m, m.batch_index + 1, u); m.have_gapmer = 0; }
   else path_move_right(w, m);
 }
 XM_HD inline int path_max_allowed(WS& w, MatePath& m, const HB& b) {  // :205-219
@@ -450,6 +591,43 @@ XM_HD inline bool counting_next_block(WS& w, MatePath& m, HB& out) {  // getNext
     return true;
   }
 }
+// One index hit of seed qb at global position pos: decode, flank verification (Counting_HashBlockPath.step :98-153)
+// and the resulting SequenceMatch (:155-166).  mate < 0 = rejected.
+XM_FN SM verify_hit(const WS& w, const MatePath& m, const HB& qb, uint32_t pos, bool invert) {
+  SM full; full.mate = -1; full.rev = 0; full.contig = 0; full.offset = 0; full.from_hash = 1;
+  int seq_id, rstart;
+  w.ref->decode((int64_t)pos, seq_id, rstart);
+  if (invert) { seq_id ^= 1; rstart = w.ref->len[seq_id >> 1] - rstart - qb.len; }
+  const int contig = seq_id >> 1, on_rc = seq_id & 1;
+  const SeqView cms = w.ref->contig(contig, on_rc);
+  const int qlen = m.q.len;
+  int mism = 0, mat = 0;
+  XM_NOUNROLL
+  for (int d = 1; d < 20; d++) {
+    int qi = qb.start - d;
+    if (qi >= 0 && qi < qlen) {
+      int ri = rstart - d;
+      if (ri >= 0 && ri < cms.len) { if (!bp_can_match(m.q.at(qi), cms.at(ri))) mism++; else mat++; }
+    }
+    qi = qb.start + qb.len - 1 + d;
+    if (qi >= 0 && qi < qlen) {
+      int ri = rstart + qb.len - 1 + d;
+      if (ri >= 0 && ri < cms.len) { if (!bp_can_match(m.q.at(qi), cms.at(ri))) mism++; else mat++; }
+    }
+    if (mat < mism) break;
+    if (mat >= mism + qb.used) break;
+  }
+  XM_T("  hit seq=%d rstart=%d mism=%d mat=%d\n", seq_id, rstart, mism, mat);
+  if (mism > mat) return full;
+  full.mate = m.mate; full.contig = contig;
+  if (on_rc) {  // :155-166
+    int rq = qlen - qb.end();
+    int rr = cms.len - (rstart + qb.len);
+    full.rev = m.path_is_rc ? 0 : 1;  // a = reverseComplementQuery
+    full.offset = rr - rq;
+  } else { full.rev = m.path_is_rc ? 1 : 0; full.offset = rstart - qb.start; }
+  return full;
+}
 XM_FN bool counting_step(WS& w, MatePath& m) {  // step :40-179
   if (m.done || w.status != 0) return false;
   PhaseClock pc_(&w.st_cyc[0]);
@@ -481,42 +659,34 @@ XM_FN bool counting_step(WS& w, MatePath& m) {  // step :40-179
   w.st_seeds++; w.st_hits += (unsigned long long)count;
   bool invert = !qb.primary();
   const uint32_t* pos = (count > 0) ? t->positions + (word >> 24) : nullptr;
-  int qlen = m.q.len;
+  // Each hit is verified independently (flank comparison, :98-153); the bins are then updated in bucket order.
+  // On the device 32 lanes verify 32 hits at a time and lane results are replayed in order by the whole warp.
+#if defined(__CUDA_ARCH__)
+  const int lane = (int)(threadIdx.x & 31);
   XM_NOUNROLL
-  for (int k = 0; k < count; k++) {
-    int seq_id, rstart;
-    w.ref->decode((int64_t)pos[k], seq_id, rstart);
-    if (invert) { seq_id ^= 1; rstart = w.ref->len[seq_id >> 1] - rstart - qb.len; }
-    int contig = seq_id >> 1, on_rc = seq_id & 1;
-    SeqView cms = w.ref->contig(contig, on_rc);
-    int mism = 0, mat = 0;
+  for (int base = 0; base < count; base += 32) {
+    const int n = imin(32, count - base);
+    SM mine; mine.mate = -1; mine.rev = 0; mine.contig = 0; mine.offset = 0; mine.from_hash = 1;
+    if (lane < n) mine = verify_hit(w, m, qb, pos[base + lane], invert);
     XM_NOUNROLL
-    for (int d = 1; d < 20; d++) {  // :98-153
-      int qi = qb.start - d;
-      if (qi >= 0 && qi < qlen) {
-        int ri = rstart - d;
-        if (ri >= 0 && ri < cms.len) { if (!bp_can_match(m.q.at(qi), cms.at(ri))) mism++; else mat++; }
-      }
-      qi = qb.start + qb.len - 1 + d;
-      if (qi >= 0 && qi < qlen) {
-        int ri = rstart + qb.len - 1 + d;
-        if (ri >= 0 && ri < cms.len) { if (!bp_can_match(m.q.at(qi), cms.at(ri))) mism++; else mat++; }
-      }
-      if (mat < mism) break;
-      if (mat >= mism + qb.used) break;
+    for (int j = 0; j < n; j++) {
+      SM full;
+      full.mate = __shfl_sync(0xffffffffu, mine.mate, j);
+      if (full.mate < 0) continue;
+      full.rev = __shfl_sync(0xffffffffu, mine.rev, j); full.contig = __shfl_sync(0xffffffffu, mine.contig, j);
+      full.offset = __shfl_sync(0xffffffffu, mine.offset, j); full.from_hash = 1;
+      counting_update_matches(w, m, full, qb, count);
+      if (w.status != 0) return false;
     }
-    XM_T("  hit seq=%d rstart=%d mism=%d mat=%d\n", seq_id, rstart, mism, mat);
-    if (mism > mat) continue;
-    SM full; full.mate = m.mate; full.contig = contig; full.from_hash = 1;
-    if (on_rc) {  // :155-166
-      int rq = qlen - qb.end();
-      int rr = cms.len - (rstart + qb.len);
-      full.rev = m.path_is_rc ? 0 : 1;  // a = reverseComplementQuery
-      full.offset = rr - rq;
-    } else { full.rev = m.path_is_rc ? 1 : 0; full.offset = rstart - qb.start; }
+  }
+#else
+  for (int k = 0; k < count; k++) {
+    SM full = verify_hit(w, m, qb, pos[k], invert);
+    if (full.mate < 0) continue;
     counting_update_matches(w, m, full, qb, count);
     if (w.status != 0) return false;
   }
+#endif
   if (qb.start >= m.max_nonoverlap_visited) { m.max_nonoverlap_visited = qb.end(); m.n_nonoverlap_visited++; }
   m.n_blocks_anywhere++;
   m.min_num_distinct = -1;
