@@ -97,9 +97,12 @@ XM_FN MatcherD* matcher_new(WS& w, const ACtx& c, const Sec& rsec, int section_l
   m->ref_start = rsec.start; m->ref_len = rsec.length(); m->section_len = section_len;
   m->max_section_index = (c.b.len - 1 - m->ref_start) / section_len;
   m->loc_size = 0;
-  int words = (m->max_section_index + 1 + 31) / 32;
+  // lookups only ask for sections that intersect [ref_start, ref_start + ref_len] (matcher_lookup clamps to the
+  // window), so the "materialised" bitmap needs ref_len / section_len + 2 bits; an index beyond it asks for more workspace
+  int n_sec = imin(m->max_section_index + 1, (m->ref_len + 1) / section_len + 2);
+  int words = (n_sec + 31) / 32;
   if (words < 1) words = 1;
-  if (words > 4096) words = 4096;  // sections beyond this are never requested for windows that fit the workspace
+  if (words > 4096) words = 4096;
   m->mat_words = words;
   m->materialized = (uint32_t*)w.salloc((long long)words * 4);
   if (!m->materialized) return nullptr;
@@ -368,6 +371,123 @@ XM_INLINE bool pa_can_remove(const Blk& b) {  // canRemoveSection :358-366
   if ((b.a_start <= 0 && b.a_len <= 0) || (b.b_start <= 0 && b.b_len <= 0)) return true;
   return false;
 }
+// The best-first search loop of PathAligner.align :153-192 with explore :722-729, update :555-571, computeUpdated
+// :573-719, putNode :446-473 and estimateOverallPenalty :475-521 folded into ONE compact loop: every per-search
+// constant lives in a register, the three neighbours share one copy of the update code, and base pairs are
+// classified through the 256-entry tables.  This loop is where gapped reads spend their time, and on the device its
+// code size (not its arithmetic) is what limits it.  Returns 0 goal reached (last_x/last_y), 1 over budget (null), 2 failed.
+XM_FN int pa_search(WS& w, PathState& S, int& last_x, int& last_y) {
+  const int A = S.A, B = S.B, H = S.H, step = S.step, goal_x = S.goal_x, goal_y = S.goal_y, diag = S.diagonal;
+  const bool may_extend = S.may_extend != 0, confident = S.an->confident != 0;
+  const double ins_start = S.prm.ins_start, ins_ext = S.prm.ins_ext, del_start = S.prm.del_start, del_ext = S.prm.del_ext, unaligned = S.prm.unaligned;
+  const double max_ins = S.an->max_ins, max_del = S.an->max_del, budget = S.max_interesting + 0.000001;
+  const double min_indel = dmin(ins_start + ins_ext, del_start + del_ext);
+  const double* pen_tab = S.prm.pen_tab; const uint8_t* cls_tab = S.prm.cls_tab;
+  PNode* nodes = S.nodes; uint8_t* flags = S.flags; const uint8_t* qa = S.qa; const uint8_t* rb = S.rb;
+  PHeapEnt* heap = S.heap; const int heap_cap = S.heap_cap;
+  int heap_n = S.heap_n; uint32_t seq = S.seq; double active = S.active;
+  unsigned long long steps = 0;
+  int rc = 2;
+  XM_NOUNROLL
+  while (true) {
+    if (heap_n == 0) { w.fail(Q_INTERNAL); break; }  // priorities.poll() == null -> NullPointerException
+    PHeapEnt top = heap[0];
+    {  // pop
+      PHeapEnt e = heap[--heap_n];
+      int i = 0;
+      XM_NOUNROLL
+      while (true) {
+        int l = 2 * i + 1;
+        if (l >= heap_n) break;
+        int c = l;
+        PHeapEnt ce = heap[l];
+        if (l + 1 < heap_n) { PHeapEnt re = heap[l + 1]; if (pa_heap_less(re, ce)) { c = l + 1; ce = re; } }
+        if (pa_heap_less(ce, e)) { heap[i] = ce; i = c; } else break;
+      }
+      if (heap_n > 0) heap[i] = e;
+    }
+    active = top.pri;
+    steps++;
+    if (active > budget) { rc = 1; break; }
+    if (top.x == goal_x) { last_x = top.x; last_y = top.y; rc = 0; break; }
+    XM_NOUNROLL
+    for (int nb = 0; nb < 3; nb++) {  // (x+step, y), (x, y+step), (x+step, y+step)
+      const int x = top.x + (nb != 1 ? step : 0), y = top.y + (nb != 0 ? step : 0);
+      if (x <= 0 || x > A || y <= 0 || y > B) continue;
+      const int ie = x * H + y, il = ie - step * H, iu = ie - step, id = il - step;
+      const uint8_t fe = flags[ie], fl_ = flags[il], fu = flags[iu], fd = flags[id];
+      double ins_x = XM_DISALLOWED, ins_y = XM_DISALLOWED, overlay = XM_DISALLOWED;
+      if (fd & 1) overlay = nodes[id].pen + pen_tab[((int)qa[x - 1] << 4) | (int)rb[y - 1]];
+      if (fl_ & 1) {
+        const double lp = nodes[il].pen;
+        if (y == goal_y && may_extend) ins_x = lp + unaligned;
+        else {
+          bool allowed = true;
+          const int pa = x - 1 - step, pb = y - 1;
+          if (pa >= 0 && pa < A && pb >= 0 && pb < B) allowed = (cls_tab[((int)qa[pa] << 4) | (int)rb[pb]] & 1) != 0;
+          if (allowed) {
+            const int na = x - 1, nbb = y - 1 + step;
+            if (na >= 0 && na < A && nbb >= 0 && nbb < B) allowed = (cls_tab[((int)qa[na] << 4) | (int)rb[nbb]] & 6) == 0;
+          }
+          const double nw = allowed ? lp + ins_start + ins_ext : XM_DISALLOWED;
+          ins_x = dmin(nodes[il].ins_x + ins_ext, nw);
+        }
+      }
+      if (fu & 1) {
+        bool allowed = true;
+        const int pa = x - 1, pb = y - 1 - step;
+        if (pa >= 0 && pa < A && pb >= 0 && pb < B) allowed = (cls_tab[((int)qa[pa] << 4) | (int)rb[pb]] & 1) != 0;
+        if (allowed) {
+          const int na = x - 1 + step, nbb = y - 1;
+          if (na >= 0 && na < A && nbb >= 0 && nbb < B) allowed = (cls_tab[((int)qa[na] << 4) | (int)rb[nbb]] & 6) == 0;
+        }
+        const double nw = allowed ? nodes[iu].pen + del_start + del_ext : XM_DISALLOWED;
+        ins_y = dmin(nodes[iu].ins_y + del_ext, nw);
+      }
+      const double best = dmin(dmin(overlay, ins_x), ins_y);
+      if ((fe & 1) && !(best < nodes[ie].pen || ins_x < nodes[ie].ins_x || ins_y < nodes[ie].ins_y)) continue;
+      const int sd = x - y - diag;
+      int fl = 0;
+      if (best != XM_DISALLOWED) {
+        const int src = (best == overlay) ? fd : (best == ins_x) ? fl_ : fu;
+        fl = (src & 6) | (sd == 0 ? 2 : 4);
+      }
+      // estimateOverallPenalty :475-521
+      double est = best;
+      if (confident) {
+        const int sds = sd * step;
+        if (fl & 2) {
+          const bool over = (sds > 0) ? (fabs(sd * ins_ext) > max_ins) : (fabs(sd * del_ext) > max_del);
+          if (over) est = XM_DISALLOWED;
+          else if (!(fl & 4)) est = best + min_indel;
+        } else if (sds < 0) {
+          const double ie_ = fabs(sd * ins_ext);
+          if (ie_ > max_ins) est = XM_DISALLOWED;
+          else est = best + dmin(ins_start, ins_x - best) + ie_;
+        } else {
+          const double de = fabs(sd * del_ext);
+          if (de > max_del) est = XM_DISALLOWED;
+          else est = best + dmin(del_start, ins_y - best) + de;
+        }
+      }
+      if (est < active) est = active;
+      if (heap_n >= heap_cap) { w.fail(Q_NEED_MORE); break; }
+      {  // push
+        PHeapEnt e; e.pri = est; e.seq = seq++; e.x = (int16_t)x; e.y = (int16_t)y;
+        int i = heap_n++;
+        XM_NOUNROLL
+        while (i > 0) { int pr = (i - 1) >> 1; PHeapEnt pe = heap[pr]; if (pa_heap_less(e, pe)) { heap[i] = pe; i = pr; } else break; }
+        heap[i] = e;
+      }
+      PNode n; n.pen = best; n.ins_x = ins_x; n.ins_y = ins_y;
+      nodes[ie] = n; flags[ie] = (uint8_t)(1 | fl);
+    }
+    if (w.status != 0) break;
+  }
+  S.heap_n = heap_n; S.seq = seq; S.active = active;
+  w.st_path_steps += steps;
+  return rc;
+}
 XM_FN DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Params& p, Analysis& an) {  // PathAligner.align :55-293
   PhaseClock pc_(&w.st_cyc[3]);
   long long mark = w.scratch_top;
@@ -462,17 +582,9 @@ XM_FN DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Pa
     }
   }
   int last_x = -1, last_y = -1;
-  XM_NOUNROLL
-  while (w.status == 0) {
-    if (s.heap_n == 0) { w.fail(Q_INTERNAL); break; }  // priorities.poll() == null -> NullPointerException
-    PHeapEnt e = pa_heap_pop(s);
-    s.active = e.pri;
-    w.st_path_steps++;
-    if (s.active > s.max_interesting + 0.000001) { w.scratch_top = mark; return aln_null(); }
-    if (e.x == s.goal_x) { last_x = e.x; last_y = e.y; break; }
-    pa_update(w, s, e.x + s.step, e.y);       // explore :722-729
-    pa_update(w, s, e.x, e.y + s.step);
-    pa_update(w, s, e.x + s.step, e.y + s.step);
+  if (w.status == 0) {
+    int rc = pa_search(w, s, last_x, last_y);
+    if (rc == 1 && w.status == 0) { w.scratch_top = mark; return aln_null(); }
   }
   if (w.status != 0) { w.scratch_top = mark; return aln_null(); }
   // traceback :193-269. Blocks are collected in a temporary array placed after the heap.
@@ -1523,8 +1635,13 @@ XM_HD inline void align_query(WS& w, OutArena& out, OutQuery& oq) {
 
 // Carves the per-thread workspace out of a flat arena and resets all per-query state.
 // fills the 256-entry pair-penalty table (Params::pen_tab) with the reference's formula
-XM_HD inline void fill_pen_tab(const Params& prm, double* tab, int first, int step) {
-  for (int i = first; i < 256; i += step) tab[i] = prm.base_penalty_formula((uint8_t)(i >> 4), (uint8_t)(i & 15));
+XM_HD inline void fill_pen_tab(const Params& prm, double* tab, uint8_t* cls, int first, int step) {
+  for (int i = first; i < 256; i += step) {
+    uint8_t q = (uint8_t)(i >> 4), r = (uint8_t)(i & 15);
+    double v = prm.base_penalty_formula(q, r);
+    tab[i] = v;
+    cls[i] = (uint8_t)((bp_can_match(q, r) ? 1 : 0) | (v == 0 ? 2 : 0) | ((bp_is_fully_ambiguous(q) || bp_is_fully_ambiguous(r)) ? 4 : 0));
+  }
 }
 XM_HD inline bool ws_init(WS& w, char* arena, long long arena_bytes, const RefD* ref, const IndexD* ix, const DupD* dup, const Params& prm, const QueryIn& q) {
   w.ref = ref; w.ix = ix; w.dup = dup; w.prm = prm; w.query = q;

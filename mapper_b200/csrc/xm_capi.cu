@@ -17,6 +17,9 @@ using namespace xm;
 
 // ---------------------------------------------------------------- kernels
 #define XM_BLOCK 128
+#ifndef XM_MIN_BLOCKS
+#define XM_MIN_BLOCKS 8
+#endif
 struct BatchD {
   int n_queries;
   const uint16_t* packed; const int64_t* seq_word_off; const int32_t* seq_len; const int64_t* first_seq;  // first_seq: n_queries+1
@@ -38,14 +41,15 @@ struct LaunchD {
 // EASY = true: first pass over every query (small arenas, no cascade code in the image); false: the full aligner
 // over the queries the first pass handed on.
 template <bool EASY>
-__global__ void __launch_bounds__(XM_BLOCK, 4) xm_align_kernel(LaunchD L) {
+__global__ void __launch_bounds__(XM_BLOCK, XM_MIN_BLOCKS) xm_align_kernel(LaunchD L) {
   const int lane = threadIdx.x & 31;
   long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   char* arena = L.arenas + warp * L.arena_bytes;
   __shared__ double s_pen[256];
-  fill_pen_tab(L.prm, s_pen, threadIdx.x, blockDim.x);
+  __shared__ uint8_t s_cls[256];
+  fill_pen_tab(L.prm, s_pen, s_cls, threadIdx.x, blockDim.x);
   __syncthreads();
-  L.prm.pen_tab = s_pen;
+  L.prm.pen_tab = s_pen; L.prm.cls_tab = s_cls;
   unsigned long long st[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   while (true) {
     int t = 0;
@@ -269,7 +273,7 @@ int xm_create(const xm_params* p, int device, xm_handle** out) {
   q.mutation = p->mutation_penalty; q.ins_start = p->insertion_start_penalty; q.ins_ext = p->insertion_extension_penalty;
   q.del_start = p->deletion_start_penalty; q.del_ext = p->deletion_extension_penalty; q.max_error_rate = p->max_error_rate;
   q.unaligned = p->unaligned_penalty; q.ambiguity = p->ambiguity_penalty; q.span = p->max_penalty_span;
-  q.max_num_matches = p->max_num_matches; q.start_free = 0; q.pen_tab = nullptr;
+  q.max_num_matches = p->max_num_matches; q.start_free = 0; q.pen_tab = nullptr; q.cls_tab = nullptr;
   h->m.gapmers = p->enable_gapmers ? 1 : 0;
   *out = h;
   return XM_OK;

@@ -85,6 +85,7 @@ struct Params {
   int max_num_matches;
   int start_free;  // StartingInsertionStartFree
   const double* pen_tab;  // 256 entries [q << 4 | r] of the formula below, filled once per kernel launch (device: shared memory)
+  const uint8_t* cls_tab; // 256 entries [q << 4 | r]: bit 0 canMatch, bit 1 penalty == 0, bit 2 either base fully ambiguous
   XM_INLINE double starting_ins_start() const { return start_free ? 0.0 : ins_start; }
   XM_INLINE double min_possible_nonzero() const {
     double r = mutation;

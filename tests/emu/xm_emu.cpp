@@ -12,7 +12,7 @@ using namespace xm;
 
 namespace {
 struct CParams { double mutation, ins_start, ins_ext, del_start, del_ext, max_error_rate, unaligned, ambiguity, span; int32_t max_num_matches, enable_gapmers; };
-struct Emu { HostModel m; std::string err; double pen[256]; };
+struct Emu { HostModel m; std::string err; double pen[256]; uint8_t cls[256]; };
 }
 
 extern "C" {
@@ -23,8 +23,8 @@ void* xe_create(const CParams* p) {
   q.mutation = p->mutation; q.ins_start = p->ins_start; q.ins_ext = p->ins_ext; q.del_start = p->del_start; q.del_ext = p->del_ext;
   q.max_error_rate = p->max_error_rate; q.unaligned = p->unaligned; q.ambiguity = p->ambiguity; q.span = p->span;
   q.max_num_matches = p->max_num_matches; q.start_free = 0;
-  fill_pen_tab(q, e->pen, 0, 1);
-  q.pen_tab = e->pen;
+  fill_pen_tab(q, e->pen, e->cls, 0, 1);
+  q.pen_tab = e->pen; q.cls_tab = e->cls;
   e->m.gapmers = p->enable_gapmers;
   return e;
 }

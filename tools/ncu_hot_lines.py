@@ -37,7 +37,7 @@ kname = rows[0][1]
 hdr = rows[1]; col = {h: i for i, h in enumerate(hdr)}
 data = [r for r in rows[2:] if len(r) == len(hdr)]
 # find the matching section: mangled name contains "xm_align_kernelILb1" for <1>
-want = "ILb1" if "<1>" in kname else "ILb0" if "<0>" in kname else ""
+want = "ILb1" if ("<1>" in kname or "(bool)1" in kname) else "ILb0" if ("<0>" in kname or "(bool)0" in kname) else ""
 sec = [k for k in sections if want in k and "align" in k]
 sec = sections[sec[0]] if sec else max(sections.values(), key=len)
 base = min(int(r[col["Address"]], 16) if r[col["Address"]].startswith("0x") else int(r[col["Address"]]) for r in data)
