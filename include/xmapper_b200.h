@@ -140,7 +140,9 @@ enum xm_stat {
   XM_STAT_CYC_SEED = 18, XM_STAT_CYC_STRAIGHT = 19, XM_STAT_CYC_HBA = 20, XM_STAT_CYC_PATH = 21, XM_STAT_CYC_TABLES = 22, XM_STAT_CYC_SPARE = 23,
   XM_STAT_CYC_TOTAL = 24,       /* SM clock ticks summed over queries, per phase (TOTAL only when XM_QCYCLES=1) */
   XM_STAT_EASY_QUERIES = 25, XM_STAT_EASY_NS = 26, /* first-pass kernel: queries in, device time */
-  XM_STAT_COUNT = 28
+  XM_STAT_EASY_DONE = 27,       /* queries the first-pass kernel completed */
+  XM_STAT_EASY_PROBES = 28, XM_STAT_EASY_HITS = 29, XM_STAT_EASY_STRAIGHT = 30, /* counters of the queries completed by the first pass */
+  XM_STAT_COUNT = 32
 };
 int64_t xm_results_array(const xm_results* r, int which, const void** ptr);
 void xm_release_results(xm_results* r);

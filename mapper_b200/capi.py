@@ -22,7 +22,7 @@ RESULT_ARRAYS = [("q_comp_off", np.int64), ("comp_choice_off", np.int64), ("choi
                  ("blocks", np.int32), ("q_status", np.int32), ("sa_reversed", np.uint8), ("stats", np.int64), ("q_cycles", np.int64)]
 STAT = dict(kernel_ns=0, launches=1, tier0=2, tier1=3, tier2=4, probes=5, seeds=6, hits=7, straight=8, path_calls=9,
             path_steps=10, path_cells=11, h2d_bytes=12, d2h_bytes=13, align_kernel_ns=14, tier0_ns=15, tier1_ns=16, tier2_ns=17,
-            cyc_seed=18, cyc_straight=19, cyc_hba=20, cyc_path=21, cyc_tables=22, cyc_spare=23, cyc_total=24, easy=25, easy_ns=26)
+            cyc_seed=18, cyc_straight=19, cyc_hba=20, cyc_path=21, cyc_tables=22, cyc_spare=23, cyc_total=24, easy=25, easy_ns=26, easy_done=27, easy_probes=28, easy_hits=29, easy_straight=30)
 
 
 class XmParams(C.Structure):

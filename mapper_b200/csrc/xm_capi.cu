@@ -407,6 +407,7 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
   int n_ids = nq;
   int32_t* next_ids = (int32_t*)h->d_ids_a.p;
   float align_ms_tier0 = 0, easy_ms = 0, tier_ms[XM_NUM_TIERS] = {0};
+  unsigned long long easy_stats[7] = {0, 0, 0, 0, 0, 0, 0};
   for (int round = 0; round < 4; round++) {  // extra rounds only after growing the result arena
     for (int tier = (round == 0 ? -1 : 0); tier < XM_NUM_TIERS && n_ids > 0; tier++) {  // tier -1: the first-pass kernel
       long long resident = (long long)h->sm_count * h->blocks_per_sm * warps_per_block;
@@ -432,8 +433,10 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
       if (tier < 0) R->r.stats[XM_STAT_EASY_QUERIES] += n_ids; else R->r.stats[XM_STAT_TIER0_QUERIES + tier] += n_ids;
       int counts[3];
       CK(cudaMemcpyAsync(counts, d_ints, 12, cudaMemcpyDeviceToHost, st));
+      if (tier < 0) CK(cudaMemcpyAsync(easy_stats, d_stats, sizeof(easy_stats), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
       { float t = 0; cudaEventElapsedTime(&t, h->ev2, h->ev3); if (tier < 0) easy_ms += t; else tier_ms[tier] += t; if (time_it) align_ms_tier0 = t; }
+      if (tier < 0) R->r.stats[XM_STAT_EASY_DONE] += n_ids - counts[1];
       ids = next_ids; n_ids = counts[1];
       next_ids = (next_ids == (int32_t*)h->d_ids_a.p) ? (int32_t*)h->d_ids_b.p : (int32_t*)h->d_ids_a.p;
     }
@@ -491,6 +494,7 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
   R->r.stats[XM_STAT_LAUNCHES] = launches;
   for (int t = 0; t < XM_NUM_TIERS && t < 3; t++) R->r.stats[XM_STAT_TIER0_NS + t] = (int64_t)((double)tier_ms[t] * 1e6);
   R->r.stats[XM_STAT_EASY_NS] = (int64_t)((double)easy_ms * 1e6);
+  R->r.stats[XM_STAT_EASY_PROBES] = (int64_t)easy_stats[0]; R->r.stats[XM_STAT_EASY_HITS] = (int64_t)easy_stats[2]; R->r.stats[XM_STAT_EASY_STRAIGHT] = (int64_t)easy_stats[3];
   if (h->probe_cycles) { R->r.q_cycles.resize((size_t)nq); CK(cudaMemcpy(R->r.q_cycles.data(), h->d_qcycles.p, (size_t)nq * 8, cudaMemcpyDeviceToHost)); }
   R->r.stats[XM_STAT_PROBES] = (int64_t)misc[3]; R->r.stats[XM_STAT_SEEDS] = (int64_t)misc[4]; R->r.stats[XM_STAT_HITS] = (int64_t)misc[5];
   R->r.stats[XM_STAT_STRAIGHT] = (int64_t)misc[6]; R->r.stats[XM_STAT_PATH_CALLS] = (int64_t)misc[7]; R->r.stats[XM_STAT_PATH_STEPS] = (int64_t)misc[8];
