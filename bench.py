@@ -235,14 +235,13 @@ def main():
     if a.counts:
         ptr, n_int = g.counts_device_ptr()
         if world > 1:
-            # wrap the library's device buffer without copying (__cuda_array_interface__) and all-reduce it in place over NVLink
-            class _Planes:
-                __cuda_array_interface__ = dict(shape=(n_int,), typestr="<i4", data=(ptr, False), version=2)
-            planes = torch.as_tensor(_Planes(), device=torch.device("cuda", local_rank))
+            # wrap the library's device buffer without copying and all-reduce it in place over NVLink (int32 sum: exact, order-free)
+            from mapper_b200 import shard
+            planes = shard.wrap_device_planes(ptr, n_int, torch.device("cuda", local_rank))
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            dist.all_reduce(planes, op=dist.ReduceOp.SUM)
+            shard.allreduce_planes_(planes)
             e1.record()
             torch.cuda.synchronize()
             allreduce_ms = e0.elapsed_time(e1)

@@ -47,6 +47,10 @@ __global__ void __launch_bounds__(XM_BLOCK, XM_MIN_BLOCKS) xm_align_kernel(Launc
   char* arena = L.arenas + warp * L.arena_bytes;
   __shared__ double s_pen[256];
   __shared__ uint8_t s_cls[256];
+  // the per-query state lives in shared memory, one slot per warp: in local memory every lane would keep (and
+  // write through to L2/HBM) its own copy of the same bytes
+  __shared__ WS s_ws[XM_BLOCK / 32];
+  WS& w = s_ws[threadIdx.x >> 5];
   fill_pen_tab(L.prm, s_pen, s_cls, threadIdx.x, blockDim.x);
   __syncthreads();
   L.prm.pen_tab = s_pen; L.prm.cls_tab = s_cls;
@@ -65,7 +69,6 @@ __global__ void __launch_bounds__(XM_BLOCK, XM_MIN_BLOCKS) xm_align_kernel(Launc
     if (q.n_seqs < 2) { q.seq[1] = q.seq[0]; q.seq[1].len = 0; }
     q.expected_inner = q.n_seqs > 1 ? L.batch.expected_inner[qi] : 0.0;
     q.per_penalty = q.n_seqs > 1 ? L.batch.per_penalty[qi] : 1.0;
-    WS w;
     OutQuery rec; rec.status = 0; rec.n_comp = 1; rec.n_choice[0] = 0; rec.n_choice[1] = 0; rec.choice_first[0] = 0; rec.choice_first[1] = 0;
     if (!ws_init(w, arena, L.arena_bytes, &L.ref, &L.ix, &L.dup, L.prm, q)) w.status = Q_NEED_MORE;
     else align_query<EASY>(w, L.out, rec);
@@ -111,13 +114,15 @@ __global__ void xm_chunk_scan_kernel(const uint8_t* n_seqs, int n, int chunk, co
   if (hi == n) first_seq[n] = s;
 }
 
-// ---- per-position reference-base depth planes (QV/Alignments.java:89-150, DirectionalAlignments.java:20-28) ----
-// One thread per (choice, sequence alignment); walks its blocks and adds (int)(weight*100) for every aligned
-// reference position whose query base can match it, where weight = 1/numChoices/numMatesCoveringPosition.
+// ---- per-position reference-base depth planes (QV/MatchDatabase.java:34-59, QV/Alignments.java:89-156,
+// QV/WeightedAlignment.java:19-28, QV/QueryAlignment.java:97-120,203-214, QV/DirectionalAlignments.java:20-28) ----
+// One thread per query; walks every sequence alignment of every choice and adds (int)(weight * 100) for each
+// aligned reference position whose (unambiguous) query base equals the reference base.  All weights are Java
+// floats: weight = 1f / numChoices, times 1f / numAlignmentsCoveringIndexB.
 struct CountsD {
-  int32_t* planes;            // [contig_off[c]*4 + ((region*2+dir)*len + pos)]
+  int32_t* planes;            // [contig_off[c]*4 + ((region*2+dir)*len + pos)]   region: 0 middle, 1 near a query end; dir: 0 forward, 1 reverse
   const int64_t* contig_off;  // prefix of contig lengths
-  double end_fraction;
+  double end_fraction;        // MatchDatabase.queryEndFraction
 };
 __global__ void xm_counts_kernel(RefD ref, BatchD batch, OutArena out, CountsD C, int n_queries) {
   int qi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -128,35 +133,45 @@ __global__ void xm_counts_kernel(RefD ref, BatchD batch, OutArena out, CountsD C
   for (int comp = 0; comp < oq.n_comp; comp++) {
     int nch = oq.n_choice[comp];
     if (nch < 1) continue;
-    double weight = 1.0 / (double)nch;  // MatchDatabase.addAlignments :36-44
+    const float weight = 1.0f / (float)nch;  // MatchDatabase.groupByReference :40
     for (int k = 0; k < nch; k++) {
       const OutChoice& ch = out.choices[oq.choice_first[comp] + k];
+      // QueryAlignment.computeOverlap :203-214 (alignments found by the aligner are reference-contiguous)
+      int min_overlap = -1, max_overlap = -1;
+      for (int s = 0; s < ch.n_sa; s++) {
+        const OutSA& o = out.sas[ch.sa_first + s];
+        const int32_t* ob = out.blocks + 4 * o.block_first;
+        int mn = ob[1], mx = ob[4 * (o.n_blocks - 1) + 1] + ob[4 * (o.n_blocks - 1) + 3];
+        if (min_overlap < 0 || mn >= min_overlap) min_overlap = mn;
+        if (max_overlap < 0 || mx <= max_overlap) max_overlap = mx;
+      }
       for (int s = 0; s < ch.n_sa; s++) {
         const OutSA& sa = out.sas[ch.sa_first + s];
         int mate = (oq.n_comp == 2) ? comp : s;
         SeqView qv; qv.w = batch.packed + batch.seq_word_off[s0 + mate]; qv.len = batch.seq_len[s0 + mate]; qv.rc = sa.reversed; qv.bytes = nullptr;
         SeqView rv = ref.contig(sa.contig, 0);
-        int end_len = (int)(qv.len * C.end_fraction);
+        const int32_t* bl0 = out.blocks + 4 * sa.block_first;
+        const int first_start_a = bl0[0];
+        const int last_end_a = bl0[4 * (sa.n_blocks - 1)] + bl0[4 * (sa.n_blocks - 1) + 2];
+        const double end_limit = (double)qv.len * C.end_fraction;  // Alignments.isNearQueryEnd :153-156
         long long base = C.contig_off[sa.contig] * 4;
-        // the other mate's reference span (contiguous alignments): positions covered by both get weight / 2
-        int o_lo = 0, o_hi = 0;
-        if (ch.n_sa == 2) {
-          const OutSA& ot = out.sas[ch.sa_first + (1 - s)];
-          const int32_t* ob = out.blocks + 4 * ot.block_first;
-          o_lo = ob[1]; o_hi = ob[4 * (ot.n_blocks - 1) + 1] + ob[4 * (ot.n_blocks - 1) + 3];
-        }
+        const int dir = sa.reversed ? 1 : 0;
         for (int b = 0; b < sa.n_blocks; b++) {
-          const int32_t* bl = out.blocks + 4 * (sa.block_first + b);
+          const int32_t* bl = bl0 + 4 * b;
           int a0 = bl[0], b0 = bl[1], al = bl[2], blen = bl[3];
-          if (al != blen) continue;  // indels are variant records, not reference-base depth
+          if (al != blen) continue;  // insertions / deletions are variant records, not reference-base depth
           for (int i = 0; i < al; i++) {
             int qa = a0 + i, rb = b0 + i;
-            if (qv.at(qa) != rv.at(rb)) continue;
-            double wgt = weight;
-            if (ch.n_sa == 2 && rb >= o_lo && rb < o_hi) wgt = wgt / 2.0;
-            int region = (qa < end_len || qa >= qv.len - end_len) ? 1 : 0;
-            int dir = sa.reversed ? 1 : 0;
-            atomicAdd(&C.planes[base + (long long)(region * 2 + dir) * rv.len + rb], (int32_t)(wgt * 100));
+            uint8_t code = qv.at(qa);
+            if (bp_is_ambiguous(code)) continue;         // DirectionalAlignments.add :21-25
+            if (code != rv.at(rb)) continue;             // alternates are variant records
+            int num = ch.n_sa;
+            if (ch.n_sa >= 2 && (rb < min_overlap || rb >= max_overlap)) num = 1;  // QueryAlignment.getNumAlignmentsCoveringIndexB :97-111
+            float pos_w = (num != 0) ? 1.0f / (float)num : 0.0f;
+            float wgt = weight * pos_w;
+            int dist = min(qa - first_start_a, last_end_a - qa - 1);
+            int region = ((double)dist < end_limit) ? 1 : 0;
+            atomicAdd(&C.planes[base + (long long)(region * 2 + dir) * rv.len + rb], (int32_t)(wgt * 100.0f));
           }
         }
       }

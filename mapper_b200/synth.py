@@ -98,6 +98,21 @@ def pack_reads(reads):
     return packed, off, lens
 
 
+def unpack_reads(batch):
+    """Inverse of pack_reads for a packed batch: list (per query) of lists of uint8 code arrays (mates as sent)."""
+    off, lens, n_seqs = batch["seq_word_off"], batch["seq_len"], batch["n_seqs"]
+    seqs = []
+    for i in range(len(lens)):
+        w = batch["packed"][off[i]:off[i + 1]].astype(np.uint16)
+        codes = np.stack([w & 15, (w >> 4) & 15, (w >> 8) & 15, (w >> 12) & 15], axis=1).reshape(-1).astype(np.uint8)
+        seqs.append(codes[:int(lens[i])])
+    out, k = [], 0
+    for n in n_seqs:
+        out.append(seqs[k:k + int(n)])
+        k += int(n)
+    return out
+
+
 def pack_contig(codes):
     """uint8 codes -> QV-packed uint16 words."""
     n = len(codes)

