@@ -72,6 +72,18 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+class _ResultOwner:
+    """Keeps an xm_results alive while zero-copy views of its arrays are in use."""
+
+    def __init__(self, lib, r):
+        self.lib, self.r = lib, r
+
+    def __del__(self):
+        if self.r is not None:
+            self.lib.xm_release_results(self.r)
+            self.r = None
+
+
 class XMapper:
     """One xm_handle: the aligner stage of one GPU."""
 
@@ -157,34 +169,40 @@ class XMapper:
         return out[:n.value]
 
     # ---- alignment ----
-    def _take(self, r):
+    def _take(self, r, copy=True):
+        """copy=False: the arrays are views into the library's pinned result slab (what a JNI/FFM host maps as direct
+        buffers); they stay valid while the returned dict's "_owner" is alive."""
         out = {}
         for i, (name, dt) in enumerate(RESULT_ARRAYS):
             ptr = C.c_void_p()
             n = self.L.xm_results_array(r, i, C.byref(ptr))
             if n > 0:
-                out[name] = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n * np.dtype(dt).itemsize,)).view(dt).copy()
+                v = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n * np.dtype(dt).itemsize,)).view(dt)
+                out[name] = v.copy() if copy else v
             else:
                 out[name] = np.zeros(0, dtype=dt)
-        self.L.xm_release_results(r)
+        if copy:
+            self.L.xm_release_results(r)
+        else:
+            out["_owner"] = _ResultOwner(self.L, r)
         return out
 
-    def align_batch(self, batch, strict=False, **_):
+    def align_batch(self, batch, strict=False, copy=True, **_):
         """batch: dict(packed uint16, seq_word_off int64, seq_len int32, n_seqs uint8, expected_inner f64, per_penalty f64) in HOST memory."""
         nq = len(batch["n_seqs"])
         r = C.c_void_p()
         rc = self.L.xm_align_batch(self.h, nq, _ptr(batch["packed"]), _ptr(batch["seq_word_off"]), _ptr(batch["seq_len"]), _ptr(batch["n_seqs"]),
                                    _ptr(batch["expected_inner"]), _ptr(batch["per_penalty"]), C.byref(r))
         self._ok(rc, allow=() if strict else (-4,))
-        return self._take(r)
+        return self._take(r, copy)
 
-    def align_batch_device(self, nq, d_packed, n_words, d_seq_word_off, d_seq_len, d_n_seqs, d_expected, d_per, max_seq_len, strict=False):
+    def align_batch_device(self, nq, d_packed, n_words, d_seq_word_off, d_seq_len, d_n_seqs, d_expected, d_per, max_seq_len, strict=False, copy=True):
         """All arguments are device pointers (ints) on this handle's GPU."""
         r = C.c_void_p()
         rc = self.L.xm_align_batch_device(self.h, int(nq), C.c_void_p(d_packed), C.c_int64(n_words), C.c_void_p(d_seq_word_off), C.c_void_p(d_seq_len),
                                           C.c_void_p(d_n_seqs), C.c_void_p(d_expected), C.c_void_p(d_per), int(max_seq_len), C.byref(r))
         self._ok(rc, allow=() if strict else (-4,))
-        return self._take(r)
+        return self._take(r, copy)
 
     # ---- per-position counts ----
     def counts_enable(self, query_end_fraction=0.1):

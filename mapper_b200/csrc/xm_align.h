@@ -249,6 +249,7 @@ struct PathState {
   const uint8_t* qa; const uint8_t* rb;  // the two sections, one code per byte
   PHeapEnt* heap; int heap_n, heap_cap; uint32_t seq;
   double active, max_interesting;
+  int an_confident; double an_max_ins, an_max_del;  // copies of the AlignmentAnalysis fields the search reads (the search may run in another warp)
 };
 XM_INLINE uint8_t pa_qa(const PathState& s, int i) { return s.qa[i]; }
 XM_INLINE uint8_t pa_rb(const PathState& s, int j) { return s.rb[j]; }
@@ -372,122 +373,215 @@ XM_INLINE bool pa_can_remove(const Blk& b) {  // canRemoveSection :358-366
   return false;
 }
 // The best-first search loop of PathAligner.align :153-192 with explore :722-729, update :555-571, computeUpdated
-// :573-719, putNode :446-473 and estimateOverallPenalty :475-521 folded into ONE compact loop: every per-search
-// constant lives in a register, the three neighbours share one copy of the update code, and base pairs are
-// classified through the 256-entry tables.  This loop is where gapped reads spend their time, and on the device its
-// code size (not its arithmetic) is what limits it.  Returns 0 goal reached (last_x/last_y), 1 over budget (null), 2 failed.
-XM_FN int pa_search(WS& w, PathState& S, int& last_x, int& last_y) {
-  const int A = S.A, B = S.B, H = S.H, step = S.step, goal_x = S.goal_x, goal_y = S.goal_y, diag = S.diagonal;
-  const bool may_extend = S.may_extend != 0, confident = S.an->confident != 0;
-  const double ins_start = S.prm.ins_start, ins_ext = S.prm.ins_ext, del_start = S.prm.del_start, del_ext = S.prm.del_ext, unaligned = S.prm.unaligned;
-  const double max_ins = S.an->max_ins, max_del = S.an->max_del, budget = S.max_interesting + 0.000001;
-  const double min_indel = dmin(ins_start + ins_ext, del_start + del_ext);
-  const double* pen_tab = S.prm.pen_tab; const uint8_t* cls_tab = S.prm.cls_tab;
-  PNode* nodes = S.nodes; uint8_t* flags = S.flags; const uint8_t* qa = S.qa; const uint8_t* rb = S.rb;
-  PHeapEnt* heap = S.heap; const int heap_cap = S.heap_cap;
-  int heap_n = S.heap_n; uint32_t seq = S.seq; double active = S.active;
-  unsigned long long steps = 0;
-  int rc = 2;
-  XM_NOUNROLL
-  while (true) {
-    if (heap_n == 0) { w.fail(Q_INTERNAL); break; }  // priorities.poll() == null -> NullPointerException
-    PHeapEnt top = heap[0];
-    {  // pop
-      PHeapEnt e = heap[--heap_n];
-      int i = 0;
-      XM_NOUNROLL
-      while (true) {
-        int l = 2 * i + 1;
-        if (l >= heap_n) break;
-        int c = l;
-        PHeapEnt ce = heap[l];
-        if (l + 1 < heap_n) { PHeapEnt re = heap[l + 1]; if (pa_heap_less(re, ce)) { c = l + 1; ce = re; } }
-        if (pa_heap_less(ce, e)) { heap[i] = ce; i = c; } else break;
-      }
-      if (heap_n > 0) heap[i] = e;
-    }
-    active = top.pri;
-    steps++;
-    if (active > budget) { rc = 1; break; }
-    if (top.x == goal_x) { last_x = top.x; last_y = top.y; rc = 0; break; }
+// :573-719, putNode :446-473 and estimateOverallPenalty :475-521 folded into ONE compact step function: every per-search
+// constant lives in a register (PaRegs), the three neighbours share one copy of the update code, and base pairs are
+// classified through the 256-entry tables.  The step touches nothing but the search's own lattice/heap, so the same
+// code runs (a) warp-uniformly inside the calling warp (pa_search) and (b) one search per LANE inside the path-service
+// warp of a block (pa_service), where up to 31 searches of different queries advance in SIMT lockstep.
+struct PaRegs {
+  int A, B, H, step, goal_x, goal_y, diag, heap_cap, heap_n; uint32_t seq;
+  bool may_extend, confident;
+  double ins_start, ins_ext, del_start, del_ext, unaligned, max_ins, max_del, budget, min_indel, active;
+  const double* pen_tab; const uint8_t* cls_tab; PNode* nodes; uint8_t* flags; const uint8_t* qa; const uint8_t* rb; PHeapEnt* heap;
+  unsigned long long steps;
+};
+XM_INLINE void pa_regs_load(PaRegs& R, const PathState& S) {
+  R.A = S.A; R.B = S.B; R.H = S.H; R.step = S.step; R.goal_x = S.goal_x; R.goal_y = S.goal_y; R.diag = S.diagonal;
+  R.may_extend = S.may_extend != 0; R.confident = S.an_confident != 0;
+  R.ins_start = S.prm.ins_start; R.ins_ext = S.prm.ins_ext; R.del_start = S.prm.del_start; R.del_ext = S.prm.del_ext; R.unaligned = S.prm.unaligned;
+  R.max_ins = S.an_max_ins; R.max_del = S.an_max_del; R.budget = S.max_interesting + 0.000001;
+  R.min_indel = dmin(R.ins_start + R.ins_ext, R.del_start + R.del_ext);
+  R.pen_tab = S.prm.pen_tab; R.cls_tab = S.prm.cls_tab;
+  R.nodes = S.nodes; R.flags = S.flags; R.qa = S.qa; R.rb = S.rb; R.heap = S.heap; R.heap_cap = S.heap_cap;
+  R.heap_n = S.heap_n; R.seq = S.seq; R.active = S.active; R.steps = 0;
+}
+enum { PA_CONTINUE = -1, PA_GOAL = 0, PA_OVER_BUDGET = 1, PA_EMPTY = 2, PA_HEAP_FULL = 3 };
+// One iteration of the main loop :153-192 (pop the best node, explore its three neighbours).
+XM_INLINE int pa_step(PaRegs& R, int& last_x, int& last_y) {
+  PHeapEnt* heap = R.heap; PNode* nodes = R.nodes; uint8_t* flags = R.flags; const uint8_t* qa = R.qa; const uint8_t* rb = R.rb;
+  const int A = R.A, B = R.B, H = R.H, step = R.step;
+  if (R.heap_n == 0) return PA_EMPTY;  // priorities.poll() == null -> NullPointerException
+  PHeapEnt top = heap[0];
+  {  // pop
+    int heap_n = --R.heap_n;
+    PHeapEnt e = heap[heap_n];
+    int i = 0;
     XM_NOUNROLL
-    for (int nb = 0; nb < 3; nb++) {  // (x+step, y), (x, y+step), (x+step, y+step)
-      const int x = top.x + (nb != 1 ? step : 0), y = top.y + (nb != 0 ? step : 0);
-      if (x <= 0 || x > A || y <= 0 || y > B) continue;
-      const int ie = x * H + y, il = ie - step * H, iu = ie - step, id = il - step;
-      const uint8_t fe = flags[ie], fl_ = flags[il], fu = flags[iu], fd = flags[id];
-      double ins_x = XM_DISALLOWED, ins_y = XM_DISALLOWED, overlay = XM_DISALLOWED;
-      if (fd & 1) overlay = nodes[id].pen + pen_tab[((int)qa[x - 1] << 4) | (int)rb[y - 1]];
-      if (fl_ & 1) {
-        const double lp = nodes[il].pen;
-        if (y == goal_y && may_extend) ins_x = lp + unaligned;
-        else {
-          bool allowed = true;
-          const int pa = x - 1 - step, pb = y - 1;
-          if (pa >= 0 && pa < A && pb >= 0 && pb < B) allowed = (cls_tab[((int)qa[pa] << 4) | (int)rb[pb]] & 1) != 0;
-          if (allowed) {
-            const int na = x - 1, nbb = y - 1 + step;
-            if (na >= 0 && na < A && nbb >= 0 && nbb < B) allowed = (cls_tab[((int)qa[na] << 4) | (int)rb[nbb]] & 6) == 0;
-          }
-          const double nw = allowed ? lp + ins_start + ins_ext : XM_DISALLOWED;
-          ins_x = dmin(nodes[il].ins_x + ins_ext, nw);
-        }
-      }
-      if (fu & 1) {
-        bool allowed = true;
-        const int pa = x - 1, pb = y - 1 - step;
-        if (pa >= 0 && pa < A && pb >= 0 && pb < B) allowed = (cls_tab[((int)qa[pa] << 4) | (int)rb[pb]] & 1) != 0;
-        if (allowed) {
-          const int na = x - 1 + step, nbb = y - 1;
-          if (na >= 0 && na < A && nbb >= 0 && nbb < B) allowed = (cls_tab[((int)qa[na] << 4) | (int)rb[nbb]] & 6) == 0;
-        }
-        const double nw = allowed ? nodes[iu].pen + del_start + del_ext : XM_DISALLOWED;
-        ins_y = dmin(nodes[iu].ins_y + del_ext, nw);
-      }
-      const double best = dmin(dmin(overlay, ins_x), ins_y);
-      if ((fe & 1) && !(best < nodes[ie].pen || ins_x < nodes[ie].ins_x || ins_y < nodes[ie].ins_y)) continue;
-      const int sd = x - y - diag;
-      int fl = 0;
-      if (best != XM_DISALLOWED) {
-        const int src = (best == overlay) ? fd : (best == ins_x) ? fl_ : fu;
-        fl = (src & 6) | (sd == 0 ? 2 : 4);
-      }
-      // estimateOverallPenalty :475-521
-      double est = best;
-      if (confident) {
-        const int sds = sd * step;
-        if (fl & 2) {
-          const bool over = (sds > 0) ? (fabs(sd * ins_ext) > max_ins) : (fabs(sd * del_ext) > max_del);
-          if (over) est = XM_DISALLOWED;
-          else if (!(fl & 4)) est = best + min_indel;
-        } else if (sds < 0) {
-          const double ie_ = fabs(sd * ins_ext);
-          if (ie_ > max_ins) est = XM_DISALLOWED;
-          else est = best + dmin(ins_start, ins_x - best) + ie_;
-        } else {
-          const double de = fabs(sd * del_ext);
-          if (de > max_del) est = XM_DISALLOWED;
-          else est = best + dmin(del_start, ins_y - best) + de;
-        }
-      }
-      if (est < active) est = active;
-      if (heap_n >= heap_cap) { w.fail(Q_NEED_MORE); break; }
-      {  // push
-        PHeapEnt e; e.pri = est; e.seq = seq++; e.x = (int16_t)x; e.y = (int16_t)y;
-        int i = heap_n++;
-        XM_NOUNROLL
-        while (i > 0) { int pr = (i - 1) >> 1; PHeapEnt pe = heap[pr]; if (pa_heap_less(e, pe)) { heap[i] = pe; i = pr; } else break; }
-        heap[i] = e;
-      }
-      PNode n; n.pen = best; n.ins_x = ins_x; n.ins_y = ins_y;
-      nodes[ie] = n; flags[ie] = (uint8_t)(1 | fl);
+    while (true) {
+      int l = 2 * i + 1;
+      if (l >= heap_n) break;
+      int c = l;
+      PHeapEnt ce = heap[l];
+      if (l + 1 < heap_n) { PHeapEnt re = heap[l + 1]; if (pa_heap_less(re, ce)) { c = l + 1; ce = re; } }
+      if (pa_heap_less(ce, e)) { heap[i] = ce; i = c; } else break;
     }
-    if (w.status != 0) break;
+    if (heap_n > 0) heap[i] = e;
   }
-  S.heap_n = heap_n; S.seq = seq; S.active = active;
-  w.st_path_steps += steps;
+  const double active = top.pri;
+  R.active = active;
+  R.steps++;
+  if (active > R.budget) return PA_OVER_BUDGET;
+  if (top.x == R.goal_x) { last_x = top.x; last_y = top.y; return PA_GOAL; }
+  XM_NOUNROLL
+  for (int nb = 0; nb < 3; nb++) {  // (x+step, y), (x, y+step), (x+step, y+step)
+    const int x = top.x + (nb != 1 ? step : 0), y = top.y + (nb != 0 ? step : 0);
+    if (x <= 0 || x > A || y <= 0 || y > B) continue;
+    const int ie = x * H + y, il = ie - step * H, iu = ie - step, id = il - step;
+    const uint8_t fe = flags[ie], fl_ = flags[il], fu = flags[iu], fd = flags[id];
+    double ins_x = XM_DISALLOWED, ins_y = XM_DISALLOWED, overlay = XM_DISALLOWED;
+    if (fd & 1) overlay = nodes[id].pen + R.pen_tab[((int)qa[x - 1] << 4) | (int)rb[y - 1]];
+    if (fl_ & 1) {
+      const double lp = nodes[il].pen;
+      if (y == R.goal_y && R.may_extend) ins_x = lp + R.unaligned;
+      else {
+        bool allowed = true;
+        const int pa = x - 1 - step, pb = y - 1;
+        if (pa >= 0 && pa < A && pb >= 0 && pb < B) allowed = (R.cls_tab[((int)qa[pa] << 4) | (int)rb[pb]] & 1) != 0;
+        if (allowed) {
+          const int na = x - 1, nbb = y - 1 + step;
+          if (na >= 0 && na < A && nbb >= 0 && nbb < B) allowed = (R.cls_tab[((int)qa[na] << 4) | (int)rb[nbb]] & 6) == 0;
+        }
+        const double nw = allowed ? lp + R.ins_start + R.ins_ext : XM_DISALLOWED;
+        ins_x = dmin(nodes[il].ins_x + R.ins_ext, nw);
+      }
+    }
+    if (fu & 1) {
+      bool allowed = true;
+      const int pa = x - 1, pb = y - 1 - step;
+      if (pa >= 0 && pa < A && pb >= 0 && pb < B) allowed = (R.cls_tab[((int)qa[pa] << 4) | (int)rb[pb]] & 1) != 0;
+      if (allowed) {
+        const int na = x - 1 + step, nbb = y - 1;
+        if (na >= 0 && na < A && nbb >= 0 && nbb < B) allowed = (R.cls_tab[((int)qa[na] << 4) | (int)rb[nbb]] & 6) == 0;
+      }
+      const double nw = allowed ? nodes[iu].pen + R.del_start + R.del_ext : XM_DISALLOWED;
+      ins_y = dmin(nodes[iu].ins_y + R.del_ext, nw);
+    }
+    const double best = dmin(dmin(overlay, ins_x), ins_y);
+    if ((fe & 1) && !(best < nodes[ie].pen || ins_x < nodes[ie].ins_x || ins_y < nodes[ie].ins_y)) continue;
+    const int sd = x - y - R.diag;
+    int fl = 0;
+    if (best != XM_DISALLOWED) {
+      const int src = (best == overlay) ? fd : (best == ins_x) ? fl_ : fu;
+      fl = (src & 6) | (sd == 0 ? 2 : 4);
+    }
+    // estimateOverallPenalty :475-521
+    double est = best;
+    if (R.confident) {
+      const int sds = sd * step;
+      if (fl & 2) {
+        const bool over = (sds > 0) ? (fabs(sd * R.ins_ext) > R.max_ins) : (fabs(sd * R.del_ext) > R.max_del);
+        if (over) est = XM_DISALLOWED;
+        else if (!(fl & 4)) est = best + R.min_indel;
+      } else if (sds < 0) {
+        const double ie_ = fabs(sd * R.ins_ext);
+        if (ie_ > R.max_ins) est = XM_DISALLOWED;
+        else est = best + dmin(R.ins_start, ins_x - best) + ie_;
+      } else {
+        const double de = fabs(sd * R.del_ext);
+        if (de > R.max_del) est = XM_DISALLOWED;
+        else est = best + dmin(R.del_start, ins_y - best) + de;
+      }
+    }
+    if (est < active) est = active;
+    if (R.heap_n >= R.heap_cap) return PA_HEAP_FULL;
+    {  // push
+      PHeapEnt e; e.pri = est; e.seq = R.seq++; e.x = (int16_t)x; e.y = (int16_t)y;
+      int i = R.heap_n++;
+      XM_NOUNROLL
+      while (i > 0) { int pr = (i - 1) >> 1; PHeapEnt pe = heap[pr]; if (pa_heap_less(e, pe)) { heap[i] = pe; i = pr; } else break; }
+      heap[i] = e;
+    }
+    PNode n; n.pen = best; n.ins_x = ins_x; n.ins_y = ins_y;
+    nodes[ie] = n; flags[ie] = (uint8_t)(1 | fl);
+  }
+  return PA_CONTINUE;
+}
+// Runs the search inside the calling warp (all lanes on the same values).  Returns 0 goal reached (last_x/last_y),
+// 1 over budget (null), 2 failed (w.status set).
+XM_FN int pa_search(WS& w, PathState& S, int& last_x, int& last_y) {
+  PaRegs R;
+  pa_regs_load(R, S);
+  int rc;
+  XM_NOUNROLL
+  do { rc = pa_step(R, last_x, last_y); } while (rc == PA_CONTINUE);
+  S.heap_n = R.heap_n; S.seq = R.seq; S.active = R.active;
+  w.st_path_steps += R.steps;
+  if (rc == PA_EMPTY) { w.fail(Q_INTERNAL); return 2; }
+  if (rc == PA_HEAP_FULL) { w.fail(Q_NEED_MORE); return 2; }
   return rc;
 }
+#if defined(__CUDACC__)
+// ---- path service: one warp per block runs the searches of the block's other warps, one search per lane ----
+// The per-query code is scalar: a client warp executes it once on 32 identical lanes.  The best-first search is the
+// biggest scalar loop, so a client posts its PathState here instead and sleeps; lane l of the service warp serves
+// client warp l, picks a posted search up at the next step boundary and advances it together with the searches of
+// the other lanes.  Same step code, same order of operations per search => same bits.
+struct PathSvcSlot {
+  PathState* req;
+  volatile int state;  // 0 idle, 1 posted, 2 done
+  volatile int rc, last_x, last_y;
+  volatile unsigned long long steps;
+};
+__device__ __noinline__ void pa_service(PathSvcSlot* slots, int n_clients, int my_index, int n_services, volatile int* clients_done) {
+  const int lane = (int)(threadIdx.x & 31);
+  const int client = lane * n_services + my_index;  // clients are dealt round-robin to the block's service warps
+  const bool have_client = client < n_clients;
+  PathSvcSlot* sl = slots + (have_client ? client : 0);
+  bool busy = false;
+  PaRegs R;
+  int lx = -1, ly = -1;
+  PathState* cur = nullptr;
+  XM_NOUNROLL
+  while (true) {
+    __syncwarp();
+    if (!busy && have_client && sl->state == 1) {
+      __threadfence_block();
+      cur = sl->req;
+      pa_regs_load(R, *cur);
+      lx = -1; ly = -1;
+      busy = true;
+    }
+    if (!__any_sync(0xffffffffu, busy)) {
+      int d = (lane == 0) ? *clients_done : 0;
+      d = __shfl_sync(0xffffffffu, d, 0);
+      if (d >= n_clients) break;
+      __nanosleep(100);
+      continue;
+    }
+    if (busy) {
+      int rc = pa_step(R, lx, ly);
+      if (rc != PA_CONTINUE) {
+        cur->heap_n = R.heap_n; cur->seq = R.seq; cur->active = R.active;
+        sl->rc = rc; sl->last_x = lx; sl->last_y = ly; sl->steps = R.steps;
+        __threadfence_block();
+        sl->state = 2;
+        busy = false;
+      }
+    }
+  }
+}
+// client side: post the search, sleep until the service lane finished it
+__device__ __noinline__ int pa_search_remote(WS& w, PathState& S, int& last_x, int& last_y) {
+  PathSvcSlot* sl = (PathSvcSlot*)w.svc;
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    sl->req = &S;
+    __threadfence_block();
+    sl->state = 1;
+    XM_NOUNROLL
+    while (sl->state != 2) __nanosleep(2000);
+    __threadfence_block();
+  }
+  __syncwarp();
+  int rc = sl->rc; last_x = sl->last_x; last_y = sl->last_y;
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) { w.st_path_steps += sl->steps; sl->state = 0; }  // one lane: the lanes need not be converged here
+  __syncwarp();
+  if (rc == PA_EMPTY) { w.fail(Q_INTERNAL); return 2; }
+  if (rc == PA_HEAP_FULL) { w.fail(Q_NEED_MORE); return 2; }
+  return rc;
+}
+#endif
 XM_FN DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Params& p, Analysis& an) {  // PathAligner.align :55-293
   PhaseClock pc_(&w.st_cyc[3]);
   long long mark = w.scratch_top;
@@ -495,6 +589,7 @@ XM_FN DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Pa
   if (!sp) return aln_null();
   PathState& s = *sp;
   s.prm = p; s.ctx = c; s.an = &an;
+  s.an_confident = an.confident; s.an_max_ins = an.max_ins; s.an_max_del = an.max_del;
   s.max_interesting = q.length() * p.max_error_rate;
   s.start_a = q.start; s.end_a = q.end; s.start_b = r.start; s.end_b = r.end;
   s.A = q.length(); s.B = r.length(); s.W = s.A + 2; s.H = s.B + 2;
@@ -583,7 +678,11 @@ XM_FN DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Pa
   }
   int last_x = -1, last_y = -1;
   if (w.status == 0) {
-    int rc = pa_search(w, s, last_x, last_y);
+    int rc;
+#if defined(__CUDA_ARCH__)
+    if (w.svc != nullptr) rc = pa_search_remote(w, s, last_x, last_y); else
+#endif
+    rc = pa_search(w, s, last_x, last_y);
     if (rc == 1 && w.status == 0) { w.scratch_top = mark; return aln_null(); }
   }
   if (w.status != 0) { w.scratch_top = mark; return aln_null(); }

@@ -8,6 +8,9 @@
 #include "xm_host_model.h"
 #include "xm_results.h"
 #include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 #include <cstdio>
@@ -16,10 +19,13 @@
 using namespace xm;
 
 // ---------------------------------------------------------------- kernels
+// first pass: blocks of 4 warps, 8 per SM.  full kernel: ONE block per SM of up to 32 warps = 1 path-service warp
+// (pa_service, xm_align.h) + up to 31 client warps, each client owning one query at a time.
 #define XM_BLOCK 128
 #ifndef XM_MIN_BLOCKS
 #define XM_MIN_BLOCKS 8
 #endif
+#define XM_FULL_BLOCK 1024
 struct BatchD {
   int n_queries;
   const uint16_t* packed; const int64_t* seq_word_off; const int32_t* seq_len; const int64_t* first_seq;  // first_seq: n_queries+1
@@ -35,31 +41,51 @@ struct LaunchD {
   int32_t* out_full; int* n_out_full;     // queries to re-run after growing the result arena
   char* arenas; long long arena_bytes;
   int last_tier;
+  int exp_dup;                            // experiment (XM_EXP_DUP=n): every warp of a block aligns the same n queries, results discarded by overwrite
+  int path_service;                       // full kernel: the first `path_service` warps of every block are path-service warps
   long long* q_cycles;                    // optional per-query cost probe (XM_QCYCLES=1): clock64 ticks of the tier that finished it
 };
 
 // EASY = true: first pass over every query (small arenas, no cascade code in the image); false: the full aligner
 // over the queries the first pass handed on.
 template <bool EASY>
-__global__ void __launch_bounds__(XM_BLOCK, XM_MIN_BLOCKS) xm_align_kernel(LaunchD L) {
+__global__ void __launch_bounds__(EASY ? XM_BLOCK : XM_FULL_BLOCK, EASY ? XM_MIN_BLOCKS : 1) xm_align_kernel(LaunchD L) {
   const int lane = threadIdx.x & 31;
-  long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int warp_in_block = (int)(threadIdx.x >> 5), warps_per_block = (int)(blockDim.x >> 5);
+  const int n_services = EASY ? 0 : L.path_service;
+  const bool service = n_services > 0;
+  const int clients_per_block = warps_per_block - n_services;
+  const int client = warp_in_block - n_services;   // < 0: a service warp
+  long long warp = (long long)blockIdx.x * clients_per_block + client;
   char* arena = L.arenas + warp * L.arena_bytes;
   __shared__ double s_pen[256];
   __shared__ uint8_t s_cls[256];
   // the per-query state lives in shared memory, one slot per warp: in local memory every lane would keep (and
   // write through to L2/HBM) its own copy of the same bytes
-  __shared__ WS s_ws[XM_BLOCK / 32];
+  __shared__ WS s_ws[(EASY ? XM_BLOCK : XM_FULL_BLOCK) / 32];
+  __shared__ PathSvcSlot s_svc[EASY ? 1 : 32];
+  __shared__ int s_clients_done;
   WS& w = s_ws[threadIdx.x >> 5];
+  if (threadIdx.x < 32) { s_svc[EASY ? 0 : threadIdx.x].state = 0; s_svc[EASY ? 0 : threadIdx.x].req = nullptr; }
+  if (threadIdx.x == 0) s_clients_done = 0;
+  w.svc = (service && client >= 0) ? (void*)&s_svc[client] : nullptr;
   fill_pen_tab(L.prm, s_pen, s_cls, threadIdx.x, blockDim.x);
   __syncthreads();
   L.prm.pen_tab = s_pen; L.prm.cls_tab = s_cls;
+  if (!EASY && service && client < 0) { pa_service(s_svc, clients_per_block, warp_in_block, n_services, &s_clients_done); return; }
   unsigned long long st[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int dup_i = 0;
   while (true) {
     int t = 0;
-    if (lane == 0) t = atomicAdd(L.ticket, 1);
-    t = __shfl_sync(0xffffffffu, t, 0);
-    if (t >= L.n_ids) break;
+    if (L.exp_dup > 0) {
+      if (dup_i >= L.exp_dup) break;
+      t = (int)(((long long)blockIdx.x * L.exp_dup + dup_i) % L.n_ids);
+      dup_i++;
+    } else {
+      if (lane == 0) t = atomicAdd(L.ticket, 1);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= L.n_ids) break;
+    }
     int qi = L.ids ? L.ids[t] : t;
     QueryIn q;
     long long c0 = L.q_cycles ? clock64() : 0;
@@ -91,6 +117,7 @@ __global__ void __launch_bounds__(XM_BLOCK, XM_MIN_BLOCKS) xm_align_kernel(Launc
     }
   }
   if (lane == 0) for (int i = 0; i < 14; i++) if (st[i]) atomicAdd(&L.out.stats[i], st[i]);
+  if (service) { __syncwarp(); if (lane == 0) { __threadfence_block(); atomicAdd(&s_clients_done, 1); } }
 }
 
 // first_seq[q] = exclusive prefix sum of n_seqs_per_query (single block scan is enough off the hot path; uses a
@@ -112,6 +139,72 @@ __global__ void xm_chunk_scan_kernel(const uint8_t* n_seqs, int n, int chunk, co
   long long s = chunk_off[c];
   for (long long i = lo; i < hi; i++) { first_seq[i] = s; s += n_seqs[i]; }
   if (hi == n) first_seq[n] = s;
+}
+
+// ---- result CSR assembly on the device (include/xmapper_b200.h: xm_results_array) ----
+// The align kernels bump-allocate choices / sequence alignments / blocks in completion order.  These two kernels put
+// them into query order as the eleven CSR arrays of the C ABI, laid out back to back in one slab that goes to the
+// host in a single transfer (the host used to walk 1 M records with push_back: 160 ms per 1 M reads).
+struct CsrD {
+  int64_t* q_comp_off; int64_t* comp_choice_off; int64_t* choice_sa_off; int64_t* sa_block_off;
+  double* choice_f64; double* sa_f64; int32_t* choice_inner; int32_t* sa_contig; int32_t* blocks; int32_t* q_status; uint8_t* sa_reversed;
+};
+// cnt: 4 arrays of nq + 1 int64 (components, choices, sequence alignments, blocks per query; the extra element is 0)
+__global__ void xm_csr_count_kernel(OutArena out, int nq, long long* cnt) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q > nq) return;
+  long long n_comp = 0, n_ch = 0, n_sa = 0, n_blk = 0;
+  if (q < nq) {
+    const OutQuery oq = out.q[q];
+    n_comp = oq.status == 0 ? oq.n_comp : 1;
+    if (oq.status == 0) {
+      for (int c = 0; c < oq.n_comp; c++) {
+        n_ch += oq.n_choice[c];
+        for (int k = 0; k < oq.n_choice[c]; k++) {
+          const OutChoice& ch = out.choices[oq.choice_first[c] + k];
+          n_sa += ch.n_sa;
+          for (int s = 0; s < ch.n_sa; s++) n_blk += out.sas[ch.sa_first + s].n_blocks;
+        }
+      }
+    }
+  }
+  const long long stride = (long long)nq + 1;
+  cnt[q] = n_comp; cnt[stride + q] = n_ch; cnt[2 * stride + q] = n_sa; cnt[3 * stride + q] = n_blk;
+}
+// base: exclusive sums of cnt (same layout); base[k * stride + nq] is the total of array k
+__global__ void xm_csr_fill_kernel(OutArena out, int nq, const long long* base, CsrD c) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const long long stride = (long long)nq + 1;
+  long long i_comp = base[q], i_ch = base[stride + q], i_sa = base[2 * stride + q], i_blk = base[3 * stride + q];
+  if (q == 0) { c.q_comp_off[0] = 0; c.comp_choice_off[0] = 0; c.choice_sa_off[0] = 0; c.sa_block_off[0] = 0; }
+  const OutQuery oq = out.q[q];
+  c.q_status[q] = oq.status;
+  const int n_comp = oq.status == 0 ? oq.n_comp : 1;
+  for (int cc = 0; cc < n_comp; cc++) {
+    const int n_ch = oq.status == 0 ? oq.n_choice[cc] : 0;
+    for (int k = 0; k < n_ch; k++) {
+      const OutChoice ch = out.choices[oq.choice_first[cc] + k];
+      c.choice_f64[4 * i_ch] = ch.spacing; c.choice_f64[4 * i_ch + 1] = ch.multiplier; c.choice_f64[4 * i_ch + 2] = ch.bonus; c.choice_f64[4 * i_ch + 3] = ch.total;
+      c.choice_inner[i_ch] = ch.inner;
+      for (int s = 0; s < ch.n_sa; s++) {
+        const OutSA sa = out.sas[ch.sa_first + s];
+        c.sa_contig[i_sa] = sa.contig; c.sa_reversed[i_sa] = (uint8_t)sa.reversed;
+        c.sa_f64[2 * i_sa] = sa.penalty; c.sa_f64[2 * i_sa + 1] = sa.aligned;
+        const int4* src = (const int4*)out.blocks + sa.block_first;
+        int4* dst = (int4*)c.blocks + i_blk;
+        for (int b = 0; b < sa.n_blocks; b++) dst[b] = src[b];
+        i_blk += sa.n_blocks;
+        i_sa++;
+        c.sa_block_off[i_sa] = i_blk;
+      }
+      i_ch++;
+      c.choice_sa_off[i_ch] = i_sa;
+    }
+    i_comp++;
+    c.comp_choice_off[i_comp] = i_ch;
+  }
+  c.q_comp_off[q + 1] = i_comp;
 }
 
 // ---- per-position reference-base depth planes (QV/MatchDatabase.java:34-59, QV/Alignments.java:89-156,
@@ -194,11 +287,40 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-struct xm_results { ResultsHost r; };
+// pinned host slabs for results, recycled between batches (cudaHostAlloc of 100 MB costs tens of ms)
+struct PinnedPool {
+  std::mutex mu;
+  std::vector<std::pair<void*, size_t>> free_list;
+  void* take(size_t bytes, size_t& cap) {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      for (size_t i = 0; i < free_list.size(); i++) if (free_list[i].second >= bytes) { void* p = free_list[i].first; cap = free_list[i].second; free_list.erase(free_list.begin() + (long)i); return p; }
+    }
+    void* p = nullptr;
+    size_t want = bytes + bytes / 4 + 4096;
+    if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    cap = want;
+    return p;
+  }
+  void give(void* p, size_t cap) {
+    std::lock_guard<std::mutex> g(mu);
+    if (free_list.size() >= 4) { size_t smallest = 0; for (size_t i = 1; i < free_list.size(); i++) if (free_list[i].second < free_list[smallest].second) smallest = i;
+      if (free_list[smallest].second < cap) { cudaFreeHost(free_list[smallest].first); free_list[smallest] = {p, cap}; } else cudaFreeHost(p);
+      return; }
+    free_list.push_back({p, cap});
+  }
+  ~PinnedPool() { for (auto& f : free_list) cudaFreeHost(f.first); }
+};
+struct xm_results {
+  ResultsHost r;
+  std::shared_ptr<PinnedPool> pool; void* slab = nullptr; size_t slab_cap = 0;
+  ~xm_results() { if (slab && pool) pool->give(slab, slab_cap); }
+};
 
 struct xm_handle {
   HostModel m;
   int device = 0, sm_count = 148, blocks_per_sm = 4;
+  int path_service = 0, full_warps = XM_FULL_BLOCK / 32;  // full kernel: warps per block (service + clients)
   std::string err;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
@@ -210,6 +332,8 @@ struct xm_handle {
   // batch staging + results + workspace
   DevBuf d_packed, d_seq_word_off, d_seq_len, d_n_seqs, d_expected, d_per, d_first_seq, d_chunk;
   DevBuf d_q, d_choices, d_sas, d_blocks, d_misc, d_ids_a, d_ids_b, d_ids_full, d_ws, d_qcycles;
+  DevBuf d_csr_cnt, d_csr_base, d_csr_tmp, d_csr_slab;
+  std::shared_ptr<PinnedPool> pinned = std::make_shared<PinnedPool>();
   bool probe_cycles = false;
   long long cap_choices = 0, cap_sas = 0, cap_blocks = 0;
   size_t ws_budget = (size_t)24 << 30;
@@ -273,8 +397,11 @@ int xm_create(const xm_params* p, int device, xm_handle** out) {
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   h->sm_count = prop.multiProcessorCount;
-  { int nb = 0; if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, xm_align_kernel<false>, XM_BLOCK, 0) == cudaSuccess && nb > 0) h->blocks_per_sm = nb; }
+  { int nb = 0; if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, xm_align_kernel<true>, XM_BLOCK, 0) == cudaSuccess && nb > 0) h->blocks_per_sm = nb; }
   if (const char* e = getenv("XM_BLOCKS_PER_SM")) { int v = atoi(e); if (v > 0) h->blocks_per_sm = v; }
+  if (const char* e = getenv("XM_PATH_SERVICE")) { int v = atoi(e); if (v >= 0 && v <= 8) h->path_service = v; }
+  if (const char* e = getenv("XM_FULL_WARPS")) { int v = atoi(e); if (v >= 2 && v <= XM_FULL_BLOCK / 32) h->full_warps = v; }
+  if (h->path_service >= h->full_warps) h->path_service = h->full_warps - 1;
   cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3);
   size_t stack = 32 * 1024;
@@ -299,7 +426,7 @@ void xm_destroy(xm_handle* h) {
   cudaSetDevice(h->device);
   DevBuf* bufs[] = {&h->d_words, &h->d_word_off, &h->d_len, &h->d_gstart, &h->d_tables, &h->d_dup_off, &h->d_dup_starts, &h->d_packed, &h->d_seq_word_off,
                     &h->d_seq_len, &h->d_n_seqs, &h->d_expected, &h->d_per, &h->d_first_seq, &h->d_chunk, &h->d_q, &h->d_choices, &h->d_sas, &h->d_blocks,
-                    &h->d_misc, &h->d_ids_a, &h->d_ids_b, &h->d_ids_full, &h->d_ws, &h->d_qcycles, &h->d_planes, &h->d_contig_off};
+                    &h->d_misc, &h->d_ids_a, &h->d_ids_b, &h->d_ids_full, &h->d_ws, &h->d_qcycles, &h->d_csr_cnt, &h->d_csr_base, &h->d_csr_tmp, &h->d_csr_slab, &h->d_planes, &h->d_contig_off};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : h->d_buckets) b.release();
   for (auto& b : h->d_positions) b.release();
@@ -425,23 +552,44 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
   unsigned long long easy_stats[7] = {0, 0, 0, 0, 0, 0, 0};
   for (int round = 0; round < 4; round++) {  // extra rounds only after growing the result arena
     for (int tier = (round == 0 ? -1 : 0); tier < XM_NUM_TIERS && n_ids > 0; tier++) {  // tier -1: the first-pass kernel
-      long long resident = (long long)h->sm_count * h->blocks_per_sm * warps_per_block;
-      long long arena = tier < 0 ? easy_arena_bytes(max_seq_len, 2) : tier_arena_bytes(tier, max_seq_len, 2, (long long)h->ws_budget, resident);
-      long long max_warps = (long long)(h->ws_budget / (size_t)arena);
-      long long warps = (long long)h->sm_count * h->blocks_per_sm * warps_per_block;  // one resident wave: the kernel is persistent (ticket loop)
-      if (warps > max_warps) warps = max_warps;
-      if (warps > n_ids) warps = n_ids;
-      int blocks = (int)((warps + warps_per_block - 1) / warps_per_block);
-      if (blocks < 1) blocks = 1;
-      if ((long long)blocks * warps_per_block * arena > (long long)h->ws_budget && blocks > 1) blocks = (int)(h->ws_budget / (size_t)(arena * warps_per_block));
+      // tier < 0: first pass, blocks of 4 warps.  tier >= 0: one block per SM of `cpb` client warps (+ 1 path-service warp)
+      int cpb = warps_per_block, extra = 0, blocks = 1;
+      long long arena = 0;
+      if (tier < 0) {
+        arena = easy_arena_bytes(max_seq_len, 2);
+        long long max_warps = (long long)(h->ws_budget / (size_t)arena);
+        long long warps = (long long)h->sm_count * h->blocks_per_sm * warps_per_block;  // one resident wave: the kernel is persistent (ticket loop)
+        if (warps > max_warps) warps = max_warps;
+        if (warps > n_ids) warps = n_ids;
+        blocks = (int)((warps + warps_per_block - 1) / warps_per_block);
+        if (blocks < 1) blocks = 1;
+        if ((long long)blocks * warps_per_block * arena > (long long)h->ws_budget && blocks > 1) blocks = (int)(h->ws_budget / (size_t)(arena * warps_per_block));
+      } else {
+        extra = h->path_service;
+        cpb = h->full_warps - extra;
+        long long resident = (long long)h->sm_count * cpb;
+        arena = tier_arena_bytes(tier, max_seq_len, 2, (long long)h->ws_budget, resident);
+        long long clients = resident, max_warps = (long long)(h->ws_budget / (size_t)arena);
+        if (clients > max_warps) clients = max_warps;
+        if (clients > n_ids) clients = n_ids;
+        if (clients < 1) { h->err = "workspace budget too small for one query"; return XM_ERR_CUDA; }
+        if (clients < (long long)h->sm_count * cpb) cpb = (int)(clients / h->sm_count);
+        if (cpb < 1) cpb = 1;
+        if (extra > cpb) extra = cpb;
+        blocks = (int)(clients / cpb);
+        if (blocks > h->sm_count) blocks = h->sm_count;
+      }
       if (blocks < 1) { h->err = "workspace budget too small for one block"; return XM_ERR_CUDA; }
-      if (!h->d_ws.ensure((size_t)blocks * warps_per_block * (size_t)arena)) { h->err = "out of device memory (workspace)"; return XM_ERR_CUDA; }
+      if (!h->d_ws.ensure((size_t)blocks * cpb * (size_t)arena)) { h->err = "out of device memory (workspace)"; return XM_ERR_CUDA; }
       CK(cudaMemsetAsync(d_ints, 0, 8, st));  // ticket, n_need_more
       L.ids = ids; L.n_ids = n_ids; L.need_more = next_ids; L.arenas = (char*)h->d_ws.p; L.arena_bytes = arena; L.last_tier = (tier == XM_NUM_TIERS - 1);
+      L.path_service = extra;
+      L.exp_dup = 0;
+      if (tier >= 0) { if (const char* e = getenv("XM_EXP_DUP")) L.exp_dup = atoi(e); }
       bool time_it = (round == 0 && tier == -1);
       CK(cudaEventRecord(h->ev2, st));
       if (tier < 0) xm_align_kernel<true><<<blocks, block, 0, st>>>(L);
-      else xm_align_kernel<false><<<blocks, block, 0, st>>>(L);
+      else xm_align_kernel<false><<<blocks, 32 * (cpb + extra), 0, st>>>(L);
       CK(cudaEventRecord(h->ev3, st));
       launches++;
       CK(cudaGetLastError());
@@ -486,24 +634,48 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
     xm_counts_kernel<<<(nq + 127) / 128, 128, 0, st>>>(h->ref, L.batch, L.out, C, nq);
     launches++;
   }
-  CK(cudaEventRecord(h->ev1, st));
   // D2H
   unsigned long long misc[20];
   CK(cudaMemcpyAsync(misc, h->d_misc.p, sizeof(misc), cudaMemcpyDeviceToHost, st));
+  // CSR assembly on the device, then one transfer into a pinned slab
+  const long long stride = (long long)nq + 1;
+  size_t scan_tmp = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (const long long*)nullptr, (long long*)nullptr, (int)stride, st);
+  if (!h->d_csr_cnt.ensure((size_t)stride * 32) || !h->d_csr_base.ensure((size_t)stride * 32) || !h->d_csr_tmp.ensure(scan_tmp + 16)) { h->err = "out of device memory (csr)"; return XM_ERR_CUDA; }
+  long long* d_cnt = (long long*)h->d_csr_cnt.p; long long* d_base = (long long*)h->d_csr_base.p;
+  xm_csr_count_kernel<<<(int)((stride + 255) / 256), 256, 0, st>>>(L.out, nq, d_cnt);
+  for (int k = 0; k < 4; k++) { size_t tb = scan_tmp; CK(cub::DeviceScan::ExclusiveSum(h->d_csr_tmp.p, tb, d_cnt + k * stride, d_base + k * stride, (int)stride, st)); }
+  long long totals[4];
+  for (int k = 0; k < 4; k++) CK(cudaMemcpyAsync(&totals[k], d_base + k * stride + nq, 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  const long long n_comp = totals[0], n_ch = totals[1], n_sa = totals[2], n_blk = totals[3];
+  {
+    int64_t n[11] = {(int64_t)nq + 1, n_comp + 1, n_ch + 1, n_sa + 1, 4 * n_ch, 2 * n_sa, n_ch, n_sa, 4 * n_blk, (int64_t)nq, n_sa};
+    const int elem[11] = {8, 8, 8, 8, 8, 8, 4, 4, 4, 4, 1};
+    int64_t off = 0;
+    for (int i = 0; i < 11; i++) { R->r.slab_off[i] = off; R->r.slab_n[i] = n[i]; off += (n[i] * elem[i] + 15) & ~(int64_t)15; }
+    size_t slab_bytes = (size_t)off + 16;
+    if (!h->d_csr_slab.ensure(slab_bytes)) { h->err = "out of device memory (csr slab)"; return XM_ERR_CUDA; }
+    R->pool = h->pinned;
+    R->slab = h->pinned->take(slab_bytes, R->slab_cap);
+    if (!R->slab) { h->err = "out of pinned host memory (results)"; return XM_ERR_CUDA; }
+    char* d = (char*)h->d_csr_slab.p;
+    CsrD c;
+    c.q_comp_off = (int64_t*)(d + R->r.slab_off[0]); c.comp_choice_off = (int64_t*)(d + R->r.slab_off[1]); c.choice_sa_off = (int64_t*)(d + R->r.slab_off[2]);
+    c.sa_block_off = (int64_t*)(d + R->r.slab_off[3]); c.choice_f64 = (double*)(d + R->r.slab_off[4]); c.sa_f64 = (double*)(d + R->r.slab_off[5]);
+    c.choice_inner = (int32_t*)(d + R->r.slab_off[6]); c.sa_contig = (int32_t*)(d + R->r.slab_off[7]); c.blocks = (int32_t*)(d + R->r.slab_off[8]);
+    c.q_status = (int32_t*)(d + R->r.slab_off[9]); c.sa_reversed = (uint8_t*)(d + R->r.slab_off[10]);
+    xm_csr_fill_kernel<<<(nq + 255) / 256, 256, 0, st>>>(L.out, nq, d_base, c);
+    launches += 6;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, st));  // device time of a step = every kernel from the scan of n_seqs to the CSR fill
+    CK(cudaMemcpyAsync(R->slab, d, slab_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    R->r.slab = (const char*)R->slab;
+    R->r.stats[XM_STAT_D2H_BYTES] = (int64_t)(slab_bytes + sizeof(misc) + 32);
+  }
   float ms = 0;
   cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-  std::vector<OutQuery> oq((size_t)nq);
-  unsigned long long uc = misc[0] < (unsigned long long)h->cap_choices ? misc[0] : (unsigned long long)h->cap_choices;
-  unsigned long long us = misc[1] < (unsigned long long)h->cap_sas ? misc[1] : (unsigned long long)h->cap_sas;
-  unsigned long long ub = misc[2] < (unsigned long long)h->cap_blocks ? misc[2] : (unsigned long long)h->cap_blocks;
-  std::vector<OutChoice> choices((size_t)uc + 1); std::vector<OutSA> sas((size_t)us + 1); std::vector<int32_t> blocks(((size_t)ub + 1) * 4);
-  CK(cudaMemcpyAsync(oq.data(), h->d_q.p, (size_t)nq * sizeof(OutQuery), cudaMemcpyDeviceToHost, st));
-  if (uc) CK(cudaMemcpyAsync(choices.data(), h->d_choices.p, (size_t)uc * sizeof(OutChoice), cudaMemcpyDeviceToHost, st));
-  if (us) CK(cudaMemcpyAsync(sas.data(), h->d_sas.p, (size_t)us * sizeof(OutSA), cudaMemcpyDeviceToHost, st));
-  if (ub) CK(cudaMemcpyAsync(blocks.data(), h->d_blocks.p, (size_t)ub * 16, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  R->r.assemble(nq, oq.data(), choices.data(), sas.data(), blocks.data());
   R->r.stats[XM_STAT_KERNEL_NS] = (int64_t)((double)ms * 1e6);
   R->r.stats[XM_STAT_ALIGN_KERNEL_NS] = (int64_t)((double)align_ms_tier0 * 1e6);
   R->r.stats[XM_STAT_LAUNCHES] = launches;
@@ -515,9 +687,9 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
   R->r.stats[XM_STAT_STRAIGHT] = (int64_t)misc[6]; R->r.stats[XM_STAT_PATH_CALLS] = (int64_t)misc[7]; R->r.stats[XM_STAT_PATH_STEPS] = (int64_t)misc[8];
   R->r.stats[XM_STAT_PATH_CELLS] = (int64_t)misc[9];
   for (int i = 0; i < 7; i++) R->r.stats[XM_STAT_CYC_SEED + i] = (int64_t)misc[10 + i];
-  R->r.stats[XM_STAT_D2H_BYTES] = (int64_t)((size_t)nq * sizeof(OutQuery) + uc * sizeof(OutChoice) + us * sizeof(OutSA) + ub * 16 + sizeof(misc));
   *out = R;
-  for (int i = 0; i < nq; i++) if (oq[(size_t)i].status != 0) { h->err = "at least one query could not be aligned on the device (see q_status)"; return XM_ERR_QUERY; }
+  const int32_t* q_status = (const int32_t*)(R->r.slab + R->r.slab_off[9]);
+  for (int i = 0; i < nq; i++) if (q_status[i] != 0) { h->err = "at least one query could not be aligned on the device (see q_status)"; return XM_ERR_QUERY; }
   return XM_OK;
 }
 

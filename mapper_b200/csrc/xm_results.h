@@ -13,6 +13,10 @@ struct ResultsHost {
   std::vector<uint8_t> sa_reversed;
   std::vector<int64_t> stats;
   std::vector<int64_t> q_cycles;  // debug probe (XM_QCYCLES=1)
+  // slab mode (the CUDA library): the CSR arrays were assembled on the device and copied in ONE transfer into a
+  // pinned host slab; the eleven arrays are views into it.  The vectors above stay empty.
+  const char* slab = nullptr;
+  int64_t slab_off[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, slab_n[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
   // q: n_queries records; choices/sas/blocks: host copies of the arena
   void assemble(int n_queries, const OutQuery* q, const OutChoice* choices, const OutSA* sas, const int32_t* blk) {
@@ -44,6 +48,7 @@ struct ResultsHost {
     }
   }
   int64_t array(int which, const void** ptr) const {
+    if (slab != nullptr && which >= 0 && which < 11) { *ptr = slab + slab_off[which]; return slab_n[which]; }
     switch (which) {
       case 0: *ptr = q_comp_off.data(); return (int64_t)q_comp_off.size();
       case 1: *ptr = comp_choice_off.data(); return (int64_t)comp_choice_off.size();
