@@ -45,8 +45,23 @@ XM_INLINE DAln aln_null() { DAln a; a.valid = 0; a.n = 0; a.b = nullptr; a.penal
 XM_FN double block_penalty(const Params& p, const ACtx& c, const Blk& k) {  // AlignmentParameters.getPenalty(AlignedBlock) :106-126
   double pen = 0;
   if (k.a_len == k.b_len) {
+#if defined(__CUDA_ARCH__)
+    // lanes classify 32 base pairs at a time; the non-zero penalties are then added in base order (x + 0.0 == x, so
+    // skipping the zero terms keeps the reference's left-to-right double sum bit for bit)
+    const int lane = (int)(threadIdx.x & 31);
+    XM_NOUNROLL
+    for (int base = 0; base < k.a_len; base += 32) {
+      const int i = base + lane;
+      double v = 0;
+      if (i < k.a_len) v = p.base_penalty(c.a.at(k.a_start + i), c.b.at(k.b_start + i));
+      unsigned m = __ballot_sync(0xffffffffu, v != 0);
+      XM_NOUNROLL
+      while (m) { const int src = __ffs(m) - 1; m &= m - 1; pen += __shfl_sync(0xffffffffu, v, src); }
+    }
+#else
     XM_NOUNROLL
     for (int i = 0; i < k.a_len; i++) pen += p.base_penalty(c.a.at(k.a_start + i), c.b.at(k.b_start + i));
+#endif
   } else if (k.a_len > 0) { pen += p.ins_start; pen += p.ins_ext * k.a_len; }
   else { pen += p.del_start; pen += p.del_ext * k.b_len; }
   return pen;
@@ -54,8 +69,21 @@ XM_FN double block_penalty(const Params& p, const ACtx& c, const Blk& k) {  // A
 XM_FN double block_penalty_range(const Params& p, const SeqView& a, const SeqView& b, const Blk& k, int start_b, int end_b) {  // :128-154
   double pen = 0;
   if (k.a_len == k.b_len) {
+#if defined(__CUDA_ARCH__)
+    const int lane = (int)(threadIdx.x & 31);
+    XM_NOUNROLL
+    for (int base = 0; base < k.a_len; base += 32) {
+      const int i = base + lane, bi = k.b_start + i;
+      double v = 0;
+      if (i < k.a_len && bi >= start_b && bi < end_b) v = p.base_penalty(a.at(k.a_start + i), b.at(bi));
+      unsigned m = __ballot_sync(0xffffffffu, v != 0);
+      XM_NOUNROLL
+      while (m) { const int src = __ffs(m) - 1; m &= m - 1; pen += __shfl_sync(0xffffffffu, v, src); }
+    }
+#else
     XM_NOUNROLL
     for (int i = 0; i < k.a_len; i++) { int bi = k.b_start + i; if (bi >= start_b && bi < end_b) pen += p.base_penalty(a.at(k.a_start + i), b.at(bi)); }
+#endif
   } else if (k.b_start < end_b && k.b_start + k.b_len > start_b) {
     if (k.a_len > 0) { pen += p.ins_start; pen += p.ins_ext * k.a_len; } else { pen += p.del_start; pen += p.del_ext * k.b_len; }
   }
@@ -613,6 +641,17 @@ XM_FN DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Pa
     int sum_mis = 0, num_mis = 0, sum_mat = 0, num_mat = 0;
     int si = imax(s.start_a, s.start_b - an.predicted), ei = imin(s.end_a, s.end_b - an.predicted);
     int length = ei - si;
+#if defined(__CUDA_ARCH__)
+    XM_NOUNROLL
+    for (int i = (int)(threadIdx.x & 31); i < length; i += 32) {  // integer sums: any order
+      int j = i - s.diagonal;
+      if (j >= 0 && j < s.B) {
+        if (!bp_can_match(pa_qa(s, i), pa_rb(s, j))) { sum_mis += i; num_mis++; } else { sum_mat += i; num_mat++; }
+      }
+    }
+    sum_mis = __reduce_add_sync(0xffffffffu, sum_mis); num_mis = __reduce_add_sync(0xffffffffu, num_mis);
+    sum_mat = __reduce_add_sync(0xffffffffu, sum_mat); num_mat = __reduce_add_sync(0xffffffffu, num_mat);
+#else
     XM_NOUNROLL
     for (int i = 0; i < length; i++) {
       int j = i - s.diagonal;
@@ -620,6 +659,7 @@ XM_FN DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Pa
         if (!bp_can_match(pa_qa(s, i), pa_rb(s, j))) { sum_mis += i; num_mis++; } else { sum_mat += i; num_mat++; }
       }
     }
+#endif
     s.reverse = (num_mis > 1 && num_mat > 1) ? ((sum_mis / num_mis) > (sum_mat / num_mat) ? 1 : 0) : 1;
   }
   if (s.reverse) { s.step = -1; s.may_extend = (s.start_b == 0); } else { s.step = 1; s.may_extend = (s.end_b == c.b.len); }
@@ -935,12 +975,33 @@ XM_FN PenaltyAnalysisD hba_analyze(WS& w, const ACtx& c, const Sec& q, const Sec
       int other = position;
       int reverse_count = imin(bs - max_nonmatch_end, other);
       bool found = false;
+#if defined(__CUDA_ARCH__)
+      const int lane = (int)(threadIdx.x & 31);
+      XM_NOUNROLL
+      for (int base = 1; base <= reverse_count && !found; base += 32) {  // any mismatch among the bases left of the block
+        const int i = base + lane;
+        const bool bad = (i <= reverse_count) && !bp_can_match(c.a.at(bs - i), c.b.at(other - i));
+        if (__ballot_sync(0xffffffffu, bad) != 0) found = true;
+      }
+      if (found) { num_mis++; max_nonmatch_end = bs + bl; }
+#else
       XM_NOUNROLL
       for (int i = 1; i <= reverse_count; i++) {
         if (!bp_can_match(c.a.at(bs - i), c.b.at(other - i))) { num_mis++; found = true; max_nonmatch_end = bs + bl; break; }
       }
+#endif
       if (!found) {
         int fwd = q.end - bs;
+#if defined(__CUDA_ARCH__)
+        XM_NOUNROLL
+        for (int base = bl; base < fwd && !found; base += 32) {  // first mismatch right of the block
+          const int i = base + lane, ia = bs + i, ib = other + i;
+          bool bad = false;
+          if (i < fwd) { uint8_t ca = c.a.at(ia); uint8_t cb = (ib < r.end) ? c.b.at(ib) : (uint8_t)0; bad = !bp_can_match(ca, cb); }
+          const unsigned m = __ballot_sync(0xffffffffu, bad);
+          if (m != 0) { num_mis++; found = true; max_nonmatch_end = bs + base + (__ffs(m) - 1) + 1; }
+        }
+#else
         XM_NOUNROLL
         for (int i = bl; i < fwd; i++) {
           int ia = bs + i, ib = other + i;
@@ -948,6 +1009,7 @@ XM_FN PenaltyAnalysisD hba_analyze(WS& w, const ACtx& c, const Sec& q, const Sec
           uint8_t cb = (ib < r.end) ? c.b.at(ib) : (uint8_t)0;
           if (!bp_can_match(ca, cb)) { num_mis++; found = true; max_nonmatch_end = ia + 1; break; }
         }
+#endif
         if (!found) max_nonmatch_end = q.end;
         int num_other = 0;
         int fwd2 = max_nonmatch_end - bs - bl;
@@ -1124,8 +1186,16 @@ XM_HD inline DAln cascade(WS& w, int stage, const ACtx& c, const Sec& q, const S
     case ST_STRAIGHT1: case ST_STRAIGHT2: case ST_STRAIGHT3: return straight_align(w, stage, c, q, r, p, an);
     case ST_SKIP: {  // SkipHighAmbiguity_Aligner.align :13-28
       int amb = 0;
+#if defined(__CUDA_ARCH__)
+      XM_NOUNROLL
+      for (int base = r.start; base < r.end; base += 32) {
+        const int i = base + (int)(threadIdx.x & 31);
+        amb += __popc(__ballot_sync(0xffffffffu, i < r.end && bp_is_ambiguous(c.b.at(i))));
+      }
+#else
       XM_NOUNROLL
       for (int i = r.start; i < r.end; i++) if (bp_is_ambiguous(c.b.at(i))) amb++;
+#endif
       if (amb >= r.length() / 4) return aln_null();
       return cascade(w, stage + 1, c, q, r, p, an);
     }
@@ -1180,6 +1250,20 @@ XM_FN DAln qma_align_match(WS& w, const ACtx& c, const SM& sm, const Params& p, 
   an.max_ins = max_interesting - p.ins_start; an.max_del = max_interesting - p.del_start;
   an.predicted = best_offset; an.confident = sm.from_hash ? 1 : 0;
   if (EASY) return straight_align_t<true>(w, ST_STRAIGHT1, c, q, r, p, an);
+#if defined(__CUDA_ARCH__)
+  {  // every stage of the cascade reads the reference through this window: unpack it once (lanes split the bases)
+    const int wn = r.end - r.start;
+    if (wn > 0 && w.scratch_top + wn + 64 <= w.scratch_size) {
+      uint8_t* wb = (uint8_t*)w.salloc(wn);
+      XM_NOUNROLL
+      for (int k = (int)(threadIdx.x & 31); k < wn; k += 32) wb[k] = c.b.at(r.start + k);
+      __syncwarp();
+      ACtx cw = c;
+      cw.b.bytes = wb; cw.b.b0 = r.start; cw.b.bn = wn;
+      return cascade(w, ST_STRAIGHT1, cw, q, r, p, an);
+    }
+  }
+#endif
   return cascade(w, ST_STRAIGHT1, c, q, r, p, an);
 }
 XM_HD inline bool sa_store_from(WS& w, SAStore& out, const DAln& a, int contig, int a_mate, int a_rev) {

@@ -230,7 +230,7 @@ struct WS {
   }
   uint8_t* qbytes[2][2];  // [mate][reverse-complemented]: one code per byte
   void* svc;  // PathSvcSlot of this warp when the block runs a path-service warp (device, full kernel), else nullptr
-  XM_INLINE SeqView query_view(int mate, int rev) const { SeqView v = query.seq[mate]; v.rc = rev; v.bytes = qbytes[mate][rev]; return v; }
+  XM_INLINE SeqView query_view(int mate, int rev) const { SeqView v = query.seq[mate]; v.rc = rev; v.bytes = qbytes[mate][rev]; v.b0 = 0; v.bn = v.len; return v; }
 };
 
 XM_INLINE int sm_start_b(const WS& w, const SM& m) { return imax(0, m.offset); }

@@ -105,9 +105,10 @@ struct SeqView {
   const uint16_t* w;
   int len;
   int rc;
-  const uint8_t* bytes;  // optional: the same view unpacked to one code per byte (queries; filled by ws_init)
+  const uint8_t* bytes;  // optional: positions [b0, b0 + bn) of the same view unpacked to one code per byte (whole queries: ws_init; reference windows: qma_align_match)
+  int b0, bn;
   XM_INLINE uint8_t at(int i) const {
-    if (bytes) return bytes[i];
+    if (bytes) { unsigned k = (unsigned)(i - b0); if (k < (unsigned)bn) return bytes[k]; }
     int j = rc ? len - 1 - i : i;
     uint8_t c = (uint8_t)((w[j >> 2] >> ((j & 3) << 2)) & 15);
     return rc ? bp_complement(c) : c;
