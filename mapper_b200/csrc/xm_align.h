@@ -820,7 +820,11 @@ XM_FN DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Pa
 // ---------------- cascade ----------------
 // stage ids follow QueryMatch_Aligner.buildAligner :18-29 from the outside in
 enum { ST_STRAIGHT1 = 0, ST_SKIP = 1, ST_HBA1 = 2, ST_BLOCK = 3, ST_STRAIGHT2 = 4, ST_HBA2 = 5, ST_STRAIGHT3 = 6, ST_PATH = 7 };
-XM_HD DAln cascade(WS& w, int stage, const ACtx& c, const Sec& q, const Sec& r, const Params& p, Analysis& an);
+// The cascade is a template over the stage so that the call graph has no cycle: with a (bounded) recursion in it ptxas
+// falls back to a conservative ABI for EVERY function of the kernel (memory descriptors re-materialised with two R2UR
+// before each load/store, callee-saved registers spilled at every call).
+template <int STAGE>
+XM_HD DAln cascade_t(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Params& p, Analysis& an);
 
 XM_HD inline DAln straight_alignment(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Params& p, const Analysis& an) {  // :73-94
   int qs = q.start, qe = q.end, rs = r.start, re = r.end, off = an.predicted;
@@ -833,8 +837,8 @@ XM_HD inline DAln straight_alignment(WS& w, const ACtx& c, const Sec& q, const S
 }
 // EASY = the first-pass kernel: it completes a query only when every alignMatch is settled by the outermost
 // StraightAligner; the first time the cascade would go deeper the query is handed to the full kernel (Q_HARD).
-template <bool EASY>
-XM_FN DAln straight_align_t(WS& w, int stage, const ACtx& c, const Sec& q, const Sec& r, const Params& p, Analysis& an) {  // StraightAligner.align :13-71
+template <bool EASY, int STAGE>
+XM_FN DAln straight_align_t(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Params& p, Analysis& an) {  // StraightAligner.align :13-71
   an.last_checked = an.predicted;
   w.st_straight++;
   DAln simple;
@@ -851,13 +855,14 @@ XM_FN DAln straight_align_t(WS& w, int stage, const ACtx& c, const Sec& q, const
   double rate = simple.aligned / q.length();
   Params sub = p;
   sub.max_error_rate = dmin(rate, p.max_error_rate);
-  if (EASY) { w.fail(Q_HARD); return aln_null(); }
-  DAln a = cascade(w, stage + 1, c, q, r, sub, an);
-  if (w.status != 0) return aln_null();
-  if (!a.valid || a.aligned >= sp) { if (sp <= max_interesting) return simple; }
-  return a;
+  if constexpr (EASY) { w.hard_hint = (int)(sp * 16.0); w.fail(Q_HARD); return aln_null(); }
+  else {
+    DAln a = cascade_t<STAGE + 1>(w, c, q, r, sub, an);
+    if (w.status != 0) return aln_null();
+    if (!a.valid || a.aligned >= sp) { if (sp <= max_interesting) return simple; }
+    return a;
+  }
 }
-XM_INLINE DAln straight_align(WS& w, int stage, const ACtx& c, const Sec& q, const Sec& r, const Params& p, Analysis& an) { return straight_align_t<false>(w, stage, c, q, r, p, an); }
 
 struct CountMapD {  // M/CountMap.java with a small open list instead of HashMap
   int most_key, most_count, have;
@@ -1042,14 +1047,15 @@ XM_FN PenaltyAnalysisD hba_analyze(WS& w, const ACtx& c, const Sec& q, const Sec
   return res;
 }
 
-XM_FN DAln hba_align(WS& w, int stage, const ACtx& c, const Sec& q, const Sec& r_in, const Params& p, Analysis& an_in) {  // HashBlock_Aligner.align :21-81 (tail recursion as a loop)
+template <int STAGE>
+XM_FN DAln hba_align(WS& w, const ACtx& c, const Sec& q, const Sec& r_in, const Params& p, Analysis& an_in) {  // HashBlock_Aligner.align :21-81 (tail recursion as a loop)
   Sec r = r_in;
   Analysis cur = an_in;       // the analysis object of the current recursion level
   Analysis* anp = &an_in;     // first level mutates the caller's object (hashBlock_matcher assignment)
   XM_NOUNROLL
   while (true) {
     double max_interesting = p.max_error_rate * q.length();
-    if (q.length() > r.length()) return cascade(w, stage + 1, c, q, r, p, *anp);
+    if (q.length() > r.length()) return cascade_t<STAGE + 1>(w, c, q, r, p, *anp);
     PenaltyAnalysisD pa = hba_analyze(w, c, q, r, p, *anp);
     if (w.status != 0) return aln_null();
     if (pa.min_possible > max_interesting) return aln_null();
@@ -1068,7 +1074,7 @@ XM_FN DAln hba_align(WS& w, int stage, const ACtx& c, const Sec& q, const Sec& r
       rsub.end = imin(r.end, wadd(wadd(q.end, sub.predicted), max_indel));
     }
     if (rsub.length() < r.length()) { cur = sub; anp = &cur; r = rsub; continue; }
-    return cascade(w, stage + 1, c, q, rsub, p, sub);
+    return cascade_t<STAGE + 1>(w, c, q, rsub, p, sub);
   }
 }
 
@@ -1088,7 +1094,7 @@ XM_FN DAln block_align_piece(WS& w, const ACtx& c, const Sec& q, const Sec& r, d
   sub.max_error_rate = max_penalty / q.length();
   Analysis child = parent;
   child.confident = 0;
-  return cascade(w, ST_BLOCK + 1, c, q, rsub, sub, child);
+  return cascade_t<ST_BLOCK + 1>(w, c, q, rsub, sub, child);
 }
 XM_FN DAln block_try_merge(WS& w, const ACtx& c, const DAln& left, const DAln& right, const Params& p) {  // doTryMerge :158-212
   if (aln_end_b(left) != aln_start_b(right)) return aln_null();
@@ -1180,29 +1186,28 @@ XM_FN DAln block_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const P
   return cur[0];
 }
 
-XM_HD inline DAln cascade(WS& w, int stage, const ACtx& c, const Sec& q, const Sec& r, const Params& p, Analysis& an) {
+template <int STAGE>
+XM_HD inline DAln cascade_t(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Params& p, Analysis& an) {
   if (w.status != 0) return aln_null();
-  switch (stage) {
-    case ST_STRAIGHT1: case ST_STRAIGHT2: case ST_STRAIGHT3: return straight_align(w, stage, c, q, r, p, an);
-    case ST_SKIP: {  // SkipHighAmbiguity_Aligner.align :13-28
-      int amb = 0;
+  if constexpr (STAGE == ST_STRAIGHT1 || STAGE == ST_STRAIGHT2 || STAGE == ST_STRAIGHT3) return straight_align_t<false, STAGE>(w, c, q, r, p, an);
+  else if constexpr (STAGE == ST_SKIP) {  // SkipHighAmbiguity_Aligner.align :13-28
+    int amb = 0;
 #if defined(__CUDA_ARCH__)
-      XM_NOUNROLL
-      for (int base = r.start; base < r.end; base += 32) {
-        const int i = base + (int)(threadIdx.x & 31);
-        amb += __popc(__ballot_sync(0xffffffffu, i < r.end && bp_is_ambiguous(c.b.at(i))));
-      }
-#else
-      XM_NOUNROLL
-      for (int i = r.start; i < r.end; i++) if (bp_is_ambiguous(c.b.at(i))) amb++;
-#endif
-      if (amb >= r.length() / 4) return aln_null();
-      return cascade(w, stage + 1, c, q, r, p, an);
+    XM_NOUNROLL
+    for (int base = r.start; base < r.end; base += 32) {
+      const int i = base + (int)(threadIdx.x & 31);
+      amb += __popc(__ballot_sync(0xffffffffu, i < r.end && bp_is_ambiguous(c.b.at(i))));
     }
-    case ST_HBA1: case ST_HBA2: return hba_align(w, stage, c, q, r, p, an);
-    case ST_BLOCK: return block_align(w, c, q, r, p, an);
-    default: return path_align(w, c, q, r, p, an);
+#else
+    XM_NOUNROLL
+    for (int i = r.start; i < r.end; i++) if (bp_is_ambiguous(c.b.at(i))) amb++;
+#endif
+    if (amb >= r.length() / 4) return aln_null();
+    return cascade_t<STAGE + 1>(w, c, q, r, p, an);
   }
+  else if constexpr (STAGE == ST_HBA1 || STAGE == ST_HBA2) return hba_align<STAGE>(w, c, q, r, p, an);
+  else if constexpr (STAGE == ST_BLOCK) return block_align(w, c, q, r, p, an);
+  else return path_align(w, c, q, r, p, an);
 }
 
 // ---------------- QueryMatch_Aligner ----------------
@@ -1249,7 +1254,7 @@ XM_FN DAln qma_align_match(WS& w, const ACtx& c, const SM& sm, const Params& p, 
   Analysis an; an.matcher = nullptr; an.last_checked = 0;
   an.max_ins = max_interesting - p.ins_start; an.max_del = max_interesting - p.del_start;
   an.predicted = best_offset; an.confident = sm.from_hash ? 1 : 0;
-  if (EASY) return straight_align_t<true>(w, ST_STRAIGHT1, c, q, r, p, an);
+  if (EASY) return straight_align_t<true, ST_STRAIGHT1>(w, c, q, r, p, an);
 #if defined(__CUDA_ARCH__)
   {  // every stage of the cascade reads the reference through this window: unpack it once (lanes split the bases)
     const int wn = r.end - r.start;
@@ -1260,11 +1265,11 @@ XM_FN DAln qma_align_match(WS& w, const ACtx& c, const SM& sm, const Params& p, 
       __syncwarp();
       ACtx cw = c;
       cw.b.bytes = wb; cw.b.b0 = r.start; cw.b.bn = wn;
-      return cascade(w, ST_STRAIGHT1, cw, q, r, p, an);
+      return cascade_t<ST_STRAIGHT1>(w, cw, q, r, p, an);
     }
   }
 #endif
-  return cascade(w, ST_STRAIGHT1, c, q, r, p, an);
+  return cascade_t<ST_STRAIGHT1>(w, c, q, r, p, an);
 }
 XM_HD inline bool sa_store_from(WS& w, SAStore& out, const DAln& a, int contig, int a_mate, int a_rev) {
   out.contig = contig; out.ref_reversed = a.ref_reversed; out.a_mate = a_mate; out.a_rev = a_rev; out.n_blk = a.n; out.pad = 0;

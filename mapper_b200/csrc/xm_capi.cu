@@ -9,6 +9,7 @@
 #include "xm_results.h"
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -38,6 +39,7 @@ struct LaunchD {
   const int32_t* ids; int n_ids;          // queries of this tier (nullptr = identity)
   int* ticket;                            // dynamic work counter
   int32_t* need_more; int* n_need_more;   // queries to re-run in the next tier
+  int32_t* need_more_key;                 // first pass: cost estimate per entry of need_more (nullptr otherwise)
   int32_t* out_full; int* n_out_full;     // queries to re-run after growing the result arena
   char* arenas; long long arena_bytes;
   int last_tier;
@@ -96,6 +98,7 @@ __global__ void __launch_bounds__(EASY ? XM_BLOCK : XM_FULL_BLOCK, EASY ? XM_MIN
     q.expected_inner = q.n_seqs > 1 ? L.batch.expected_inner[qi] : 0.0;
     q.per_penalty = q.n_seqs > 1 ? L.batch.per_penalty[qi] : 1.0;
     OutQuery rec; rec.status = 0; rec.n_comp = 1; rec.n_choice[0] = 0; rec.n_choice[1] = 0; rec.choice_first[0] = 0; rec.choice_first[1] = 0;
+    w.hard_hint = 1 << 20;  // anything but Q_HARD (workspace exhausted in the first pass): assume long
     if (!ws_init(w, arena, L.arena_bytes, &L.ref, &L.ix, &L.dup, L.prm, q)) w.status = Q_NEED_MORE;
     else align_query<EASY>(w, L.out, rec);
     __syncwarp();
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(EASY ? XM_BLOCK : XM_FULL_BLOCK, EASY ? XM_MIN
     if (status == Q_HARD) status = Q_NEED_MORE;
     if (status == Q_NEED_MORE) {
       if (L.last_tier) status = Q_WORKSPACE;
-      else if (lane == 0) { int k = atomicAdd(L.n_need_more, 1); L.need_more[k] = qi; }
+      else if (lane == 0) { int k = atomicAdd(L.n_need_more, 1); L.need_more[k] = qi; if (L.need_more_key) L.need_more_key[k] = w.hard_hint; }
     } else if (status == Q_OUT_FULL) { if (lane == 0) { int k = atomicAdd(L.n_out_full, 1); L.out_full[k] = qi; } }
     rec.status = status;
     if (lane == 0) {
@@ -332,9 +335,9 @@ struct xm_handle {
   // batch staging + results + workspace
   DevBuf d_packed, d_seq_word_off, d_seq_len, d_n_seqs, d_expected, d_per, d_first_seq, d_chunk;
   DevBuf d_q, d_choices, d_sas, d_blocks, d_misc, d_ids_a, d_ids_b, d_ids_full, d_ws, d_qcycles;
-  DevBuf d_csr_cnt, d_csr_base, d_csr_tmp, d_csr_slab;
+  DevBuf d_csr_cnt, d_csr_base, d_csr_tmp, d_csr_slab, d_keys_a, d_keys_b, d_sort_tmp;
   std::shared_ptr<PinnedPool> pinned = std::make_shared<PinnedPool>();
-  bool probe_cycles = false;
+  bool probe_cycles = false, sort_hard = true;
   long long cap_choices = 0, cap_sas = 0, cap_blocks = 0;
   size_t ws_budget = (size_t)24 << 30;
   // counts
@@ -399,6 +402,7 @@ int xm_create(const xm_params* p, int device, xm_handle** out) {
   h->sm_count = prop.multiProcessorCount;
   { int nb = 0; if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, xm_align_kernel<true>, XM_BLOCK, 0) == cudaSuccess && nb > 0) h->blocks_per_sm = nb; }
   if (const char* e = getenv("XM_BLOCKS_PER_SM")) { int v = atoi(e); if (v > 0) h->blocks_per_sm = v; }
+  if (const char* e = getenv("XM_SORT_HARD")) h->sort_hard = atoi(e) != 0;
   if (const char* e = getenv("XM_PATH_SERVICE")) { int v = atoi(e); if (v >= 0 && v <= 8) h->path_service = v; }
   if (const char* e = getenv("XM_FULL_WARPS")) { int v = atoi(e); if (v >= 2 && v <= XM_FULL_BLOCK / 32) h->full_warps = v; }
   if (h->path_service >= h->full_warps) h->path_service = h->full_warps - 1;
@@ -426,7 +430,7 @@ void xm_destroy(xm_handle* h) {
   cudaSetDevice(h->device);
   DevBuf* bufs[] = {&h->d_words, &h->d_word_off, &h->d_len, &h->d_gstart, &h->d_tables, &h->d_dup_off, &h->d_dup_starts, &h->d_packed, &h->d_seq_word_off,
                     &h->d_seq_len, &h->d_n_seqs, &h->d_expected, &h->d_per, &h->d_first_seq, &h->d_chunk, &h->d_q, &h->d_choices, &h->d_sas, &h->d_blocks,
-                    &h->d_misc, &h->d_ids_a, &h->d_ids_b, &h->d_ids_full, &h->d_ws, &h->d_qcycles, &h->d_csr_cnt, &h->d_csr_base, &h->d_csr_tmp, &h->d_csr_slab, &h->d_planes, &h->d_contig_off};
+                    &h->d_misc, &h->d_ids_a, &h->d_ids_b, &h->d_ids_full, &h->d_ws, &h->d_qcycles, &h->d_csr_cnt, &h->d_csr_base, &h->d_csr_tmp, &h->d_csr_slab, &h->d_keys_a, &h->d_keys_b, &h->d_sort_tmp, &h->d_planes, &h->d_contig_off};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : h->d_buckets) b.release();
   for (auto& b : h->d_positions) b.release();
@@ -584,6 +588,8 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
       CK(cudaMemsetAsync(d_ints, 0, 8, st));  // ticket, n_need_more
       L.ids = ids; L.n_ids = n_ids; L.need_more = next_ids; L.arenas = (char*)h->d_ws.p; L.arena_bytes = arena; L.last_tier = (tier == XM_NUM_TIERS - 1);
       L.path_service = extra;
+      L.need_more_key = nullptr;
+      if (tier < 0 && h->sort_hard) { if (!h->d_keys_a.ensure((size_t)n_ids * 4) || !h->d_keys_b.ensure((size_t)n_ids * 4)) { h->err = "out of device memory"; return XM_ERR_CUDA; } L.need_more_key = (int32_t*)h->d_keys_a.p; }
       L.exp_dup = 0;
       if (tier >= 0) { if (const char* e = getenv("XM_EXP_DUP")) L.exp_dup = atoi(e); }
       bool time_it = (round == 0 && tier == -1);
@@ -600,8 +606,19 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
       CK(cudaStreamSynchronize(st));
       { float t = 0; cudaEventElapsedTime(&t, h->ev2, h->ev3); if (tier < 0) easy_ms += t; else tier_ms[tier] += t; if (time_it) align_ms_tier0 = t; }
       if (tier < 0) R->r.stats[XM_STAT_EASY_DONE] += n_ids - counts[1];
+      int32_t* other = (next_ids == (int32_t*)h->d_ids_a.p) ? (int32_t*)h->d_ids_b.p : (int32_t*)h->d_ids_a.p;
+      if (tier < 0 && L.need_more_key && counts[1] > 1) {
+        // longest first: the persistent full kernel ends when its slowest query does, so the queries the first pass
+        // scored worst (most likely gapped) start first and the cheap ones fill the tail
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, (const int32_t*)h->d_keys_a.p, (int32_t*)h->d_keys_b.p, (const int32_t*)next_ids, other, counts[1], 0, 32, st);
+        if (!h->d_sort_tmp.ensure(tb + 16)) { h->err = "out of device memory"; return XM_ERR_CUDA; }
+        CK(cub::DeviceRadixSort::SortPairsDescending(h->d_sort_tmp.p, tb, (const int32_t*)h->d_keys_a.p, (int32_t*)h->d_keys_b.p, (const int32_t*)next_ids, other, counts[1], 0, 32, st));
+        launches += 3;
+        int32_t* t = next_ids; next_ids = other; other = t;
+      }
       ids = next_ids; n_ids = counts[1];
-      next_ids = (next_ids == (int32_t*)h->d_ids_a.p) ? (int32_t*)h->d_ids_b.p : (int32_t*)h->d_ids_a.p;
+      next_ids = other;
     }
     int counts[3];
     CK(cudaMemcpy(counts, d_ints, 12, cudaMemcpyDeviceToHost));
