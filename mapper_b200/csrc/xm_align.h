@@ -267,7 +267,8 @@ XM_FN int matcher_lookup(WS& w, MatcherD& m, const ACtx& c, int query_index, int
 
 // ---------------- PathAligner ----------------
 struct PNode { double pen, ins_x, ins_y; };
-struct PHeapEnt { double pri; uint32_t seq; int16_t x, y; };
+// One queued node: packed (x, y) and the next entry of the same priority (-1 = last).
+struct PEnt { uint32_t xy; int32_t next; };
 struct PathState {
   Params prm; ACtx ctx; Analysis* an;
   int start_a, end_a, start_b, end_b, A, B, W, H;
@@ -275,36 +276,166 @@ struct PathState {
   int start_x, start_y, goal_x, goal_y;
   PNode* nodes; uint8_t* flags;  // flags: 1 present, 2 reachedMain, 4 reachedOther
   const uint8_t* qa; const uint8_t* rb;  // the two sections, one code per byte
-  PHeapEnt* heap; int heap_n, heap_cap; uint32_t seq;
-  double active, max_interesting;
-  int an_confident; double an_max_ins, an_max_del;  // copies of the AlignmentAnalysis fields the search reads (the search may run in another warp)
+  PEnt* ent; int ent_cap;
+  double max_interesting;
 };
 XM_INLINE uint8_t pa_qa(const PathState& s, int i) { return s.qa[i]; }
 XM_INLINE uint8_t pa_rb(const PathState& s, int j) { return s.rb[j]; }
-XM_INLINE bool pa_heap_less(const PHeapEnt& a, const PHeapEnt& b) { return a.pri < b.pri || (a.pri == b.pri && a.seq < b.seq); }
-XM_FN void pa_heap_push(WS& w, PathState& s, double pri, int x, int y) {
-  if (s.heap_n >= s.heap_cap) { w.fail(Q_NEED_MORE); return; }
-  PHeapEnt e; e.pri = pri; e.seq = s.seq++; e.x = (int16_t)x; e.y = (int16_t)y;
-  int i = s.heap_n++;
-  XM_NOUNROLL
-  while (i > 0) { int p = (i - 1) >> 1; if (pa_heap_less(e, s.heap[p])) { s.heap[i] = s.heap[p]; i = p; } else break; }
-  s.heap[i] = e;
+XM_INLINE bool pa_can_remove(const Blk& b) {  // canRemoveSection :358-366
+  if (b.a_len <= 0 && b.b_len <= 0) return true;
+  if ((b.a_start <= 0 && b.a_len <= 0) || (b.b_start <= 0 && b.b_len <= 0)) return true;
+  return false;
 }
-XM_FN PHeapEnt pa_heap_pop(PathState& s) {
-  PHeapEnt top = s.heap[0];
-  PHeapEnt e = s.heap[--s.heap_n];
-  int i = 0;
-  XM_NOUNROLL
-  while (true) {
-    int l = 2 * i + 1, r = l + 1;
-    if (l >= s.heap_n) break;
-    int c = (r < s.heap_n && pa_heap_less(s.heap[r], s.heap[l])) ? r : l;
-    if (pa_heap_less(s.heap[c], e)) { s.heap[i] = s.heap[c]; i = c; } else break;
+XM_INLINE uint32_t pa_pack_xy(int x, int y) { return ((uint32_t)(uint16_t)(int16_t)x << 16) | (uint32_t)(uint16_t)(int16_t)y; }
+
+// The reference's queue is a TreeMap<priority, List<node>> (PathAligner.java:446-473,153-192): nodes of the lowest
+// priority are processed in insertion order, including the ones appended while that list is being walked.  PaQueue
+// keeps exactly that structure: one FIFO (linked through PEnt::next) per distinct priority.  On the device the
+// buckets live in REGISTERS, one bucket per lane: finding the bucket of a priority is one compare + ballot, and the
+// bucket being drained (the minimum) is held warp-uniformly - so a pop is two loads and a push two stores, where a
+// binary heap cost a dependent chain of ~8 loads per operation.  Buckets beyond 32 go to a spill array kept SORTED by
+// priority (binary search to find, lane-parallel shift to insert, the front is the minimum): long reads with large
+// budgets keep hundreds of distinct priorities alive.
+struct PaOverflow { double key; int head, tail; };
+struct PaQueue {
+  PEnt* ent; int n_ent, cap, free_head;   // popped entries are chained for reuse once the fresh ones run out
+  double cur_key; int cur_head, cur_tail;  // the bucket being drained; cur_key == activePenalty
+  PaOverflow* ovf; int ovf_lo, ovf_hi, cap_ovf;  // live spill buckets are ovf[ovf_lo, ovf_hi), ascending keys
+#if defined(__CUDA_ARCH__)
+  double bkey; int bhead, btail;           // this lane's bucket (bhead < 0: free)
+#else
+  double bkey[32]; int bhead[32], btail[32];
+#endif
+  XM_INLINE void init(PEnt* e, int capacity, PaOverflow* o, int cap_o) {
+    ent = e; n_ent = 0; cap = capacity; free_head = -1; cur_key = 0; cur_head = -1; cur_tail = -1; ovf = o; ovf_lo = 0; ovf_hi = 0; cap_ovf = cap_o;
+#if defined(__CUDA_ARCH__)
+    bkey = 0; bhead = -1; btail = -1;
+#else
+    for (int i = 0; i < 32; i++) { bkey[i] = 0; bhead[i] = -1; btail[i] = -1; }
+#endif
   }
-  if (s.heap_n > 0) s.heap[i] = e;
-  return top;
-}
+  // 0 ok, 1 out of entry space, 2 out of overflow space.  pri >= cur_key always (estimates are clamped to activePenalty).
+  XM_INLINE int push(double pri, int x, int y) {
+    int id;
+    if (n_ent < cap) id = n_ent++;
+    else { if (free_head < 0) return 1; id = free_head; free_head = ent[id].next; }
+    PEnt e; e.xy = pa_pack_xy(x, y); e.next = -1;
+    ent[id] = e;
+    if (pri == cur_key) {
+      if (cur_tail >= 0) ent[cur_tail].next = id; else cur_head = id;
+      cur_tail = id;
+      return 0;
+    }
+#if defined(__CUDA_ARCH__)
+    const int lane = (int)(threadIdx.x & 31);
+    const unsigned hit = __ballot_sync(0xffffffffu, bhead >= 0 && bkey == pri);
+    if (hit != 0) {
+      const int b = __ffs(hit) - 1;
+      const int t = __shfl_sync(0xffffffffu, btail, b);
+      ent[t].next = id;
+      if (lane == b) btail = id;
+      return 0;
+    }
+#else
+    for (int b = 0; b < 32; b++) if (bhead[b] >= 0 && bkey[b] == pri) { ent[btail[b]].next = id; btail[b] = id; return 0; }
+#endif
+    // spill array: first position with key >= pri
+    int lo = ovf_lo, hi = ovf_hi;
+    XM_NOUNROLL
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ovf[mid].key < pri) lo = mid + 1; else hi = mid; }
+    if (lo < ovf_hi && ovf[lo].key == pri) { ent[ovf[lo].tail].next = id; ovf[lo].tail = id; return 0; }
+#if defined(__CUDA_ARCH__)
+    const unsigned fre = __ballot_sync(0xffffffffu, bhead < 0);
+    if (fre != 0) { const int b = __ffs(fre) - 1; if (lane == b) { bkey = pri; bhead = id; btail = id; } return 0; }
+#else
+    for (int b = 0; b < 32; b++) if (bhead[b] < 0) { bkey[b] = pri; bhead[b] = id; btail[b] = id; return 0; }
+#endif
+    if (ovf_hi >= cap_ovf) {
+      if (ovf_lo == 0) return 2;
+      const int n = ovf_hi - ovf_lo;  // slide the live range back to the start of the array
+#if defined(__CUDA_ARCH__)
+      XM_NOUNROLL
+      for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        PaOverflow t; if (i < n) t = ovf[ovf_lo + i];
+        __syncwarp();
+        if (i < n) ovf[i] = t;
+        __syncwarp();
+      }
+#else
+      for (int i = 0; i < n; i++) ovf[i] = ovf[ovf_lo + i];
+#endif
+      lo -= ovf_lo; ovf_lo = 0; ovf_hi = n;
+    }
+    {  // insert at lo: shift [lo, ovf_hi) up by one, highest elements first
+#if defined(__CUDA_ARCH__)
+      XM_NOUNROLL
+      for (int top = ovf_hi; top > lo; top -= 32) {
+        const int i = top - 1 - lane;
+        PaOverflow t; if (i >= lo) t = ovf[i];
+        __syncwarp();
+        if (i >= lo) ovf[i + 1] = t;
+        __syncwarp();
+      }
+#else
+      for (int i = ovf_hi - 1; i >= lo; i--) ovf[i + 1] = ovf[i];
+#endif
+      PaOverflow t; t.key = pri; t.head = id; t.tail = id;
+      ovf[lo] = t;
+      ovf_hi++;
+    }
+    return 0;
+  }
+  // false: queue empty.  Otherwise (x, y) of the next node in the reference's order; cur_key is its priority.
+  XM_INLINE bool pop(int& x, int& y) {
+    if (cur_head < 0) {  // next bucket = the smallest remaining priority (all are > cur_key)
+      bool have = false; double best = 0; int where = -1;  // where: 0..31 lane bucket, 32+i overflow entry i
+#if defined(__CUDA_ARCH__)
+      const int lane = (int)(threadIdx.x & 31);
+      const unsigned live = __ballot_sync(0xffffffffu, bhead >= 0);
+      if (live != 0) {
+        // non-negative doubles order like their bit patterns: min of the high words, then of the low words among ties
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(bkey);
+        const unsigned hi = bhead >= 0 ? (unsigned)(bits >> 32) : 0xffffffffu;
+        const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+        const unsigned lo = (bhead >= 0 && hi == mhi) ? (unsigned)bits : 0xffffffffu;
+        const unsigned mlo = __reduce_min_sync(0xffffffffu, lo);
+        const unsigned who = __ballot_sync(0xffffffffu, bhead >= 0 && hi == mhi && (unsigned)bits == mlo);
+        where = __ffs(who) - 1;
+        best = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+        have = true;
+      }
+#else
+      for (int b = 0; b < 32; b++) if (bhead[b] >= 0 && (!have || bkey[b] < best)) { have = true; best = bkey[b]; where = b; }
+#endif
+      if (ovf_lo < ovf_hi && (!have || ovf[ovf_lo].key < best)) { have = true; best = ovf[ovf_lo].key; where = 32; }
+      if (!have) return false;
+      cur_key = best;
+      if (where >= 32) { cur_head = ovf[ovf_lo].head; cur_tail = ovf[ovf_lo].tail; ovf_lo++; if (ovf_lo == ovf_hi) { ovf_lo = 0; ovf_hi = 0; } }
+      else {
+#if defined(__CUDA_ARCH__)
+        cur_head = __shfl_sync(0xffffffffu, bhead, where); cur_tail = __shfl_sync(0xffffffffu, btail, where);
+        if (lane == where) bhead = -1;
+#else
+        cur_head = bhead[where]; cur_tail = btail[where]; bhead[where] = -1;
+#endif
+      }
+    }
+    const PEnt e = ent[cur_head];
+    ent[cur_head].next = free_head; free_head = cur_head;
+    cur_head = e.next;
+    if (cur_head < 0) cur_tail = -1;
+    x = (int)(int16_t)(e.xy >> 16); y = (int)(int16_t)(e.xy & 0xffffu);
+    return true;
+  }
+};
+
 XM_INLINE int pa_signed_dist(const PathState& s, int x, int y) { return x - y - s.diagonal; }
+XM_INLINE bool pa_get(const PathState& s, int x, int y, int& idx) {
+  if (x < 0 || x >= s.W || y < 0 || y >= s.H) return false;
+  idx = x * s.H + y;
+  return (s.flags[idx] & 1) != 0;
+}
 XM_HD inline double pa_estimate(const PathState& s, int x, int y, const PNode& n, int fl) {  // estimateOverallPenalty :475-521
   if (!s.an->confident) return n.pen;
   int sd = pa_signed_dist(s, x, y);
@@ -327,289 +458,141 @@ XM_HD inline double pa_estimate(const PathState& s, int x, int y, const PNode& n
     return n.pen + ds + de;
   }
 }
-XM_HD inline void pa_put(WS& w, PathState& s, int x, int y, const PNode& n, int fl) {  // putNode :446-473 + saveNode
-  double est = pa_estimate(s, x, y, n, fl);
-  if (est < s.active) est = s.active;
-  pa_heap_push(w, s, est, x, y);
-  int idx = x * s.H + y;
-  s.nodes[idx] = n; s.flags[idx] = (uint8_t)(1 | fl);
-}
-XM_INLINE bool pa_get(const PathState& s, int x, int y, int& idx) {
-  if (x < 0 || x >= s.W || y < 0 || y >= s.H) return false;
-  idx = x * s.H + y;
-  return (s.flags[idx] & 1) != 0;
-}
-XM_FN void pa_update(WS& w, PathState& s, int x, int y) {  // update :555-571 + computeUpdated :573-719
-  if (x <= 0 || x > s.A) return;
-  if (y <= 0 || y > s.B) return;
-  const Params& p = s.prm;
-  int ie = 0, il = 0, iu = 0, id = 0;
-  bool he = pa_get(s, x, y, ie), hl = pa_get(s, x - s.step, y, il), hu = pa_get(s, x, y - s.step, iu), hd = pa_get(s, x - s.step, y - s.step, id);
-  double ins_x = XM_DISALLOWED, ins_y = XM_DISALLOWED, overlay = XM_DISALLOWED;
-  if (hd) overlay = s.nodes[id].pen + p.base_penalty(pa_qa(s, x - 1), pa_rb(s, y - 1));
-  if (hl) {
-    if (y == s.goal_y && s.may_extend) ins_x = s.nodes[il].pen + p.unaligned;
-    else {
-      bool allowed = true;
-      int pa = x - 1 - s.step, pb = y - 1;
-      if (pa >= 0 && pa < s.A && pb >= 0 && pb < s.B) { if (!bp_can_match(pa_qa(s, pa), pa_rb(s, pb))) allowed = false; }
-      if (allowed) {
-        int na = x - 1, nb = y - 1 + s.step;
-        if (na >= 0 && na < s.A && nb >= 0 && nb < s.B) {
-          uint8_t a = pa_qa(s, na), b = pa_rb(s, nb);
-          if (p.base_penalty(a, b) == 0) allowed = false;
-          else if (bp_is_fully_ambiguous(a) || bp_is_fully_ambiguous(b)) allowed = false;
-        }
-      }
-      double nw = allowed ? s.nodes[il].pen + p.ins_start + p.ins_ext : XM_DISALLOWED;
-      double ex = s.nodes[il].ins_x + p.ins_ext;
-      ins_x = dmin(ex, nw);
-    }
-  }
-  if (hu) {
-    bool allowed = true;
-    int pa = x - 1, pb = y - 1 - s.step;
-    if (pa >= 0 && pa < s.A && pb >= 0 && pb < s.B) { if (!bp_can_match(pa_qa(s, pa), pa_rb(s, pb))) allowed = false; }
-    if (allowed) {
-      int na = x - 1 + s.step, nb = y - 1;
-      if (na >= 0 && na < s.A && nb >= 0 && nb < s.B) {
-        uint8_t a = pa_qa(s, na), b = pa_rb(s, nb);
-        if (p.base_penalty(a, b) == 0) allowed = false;
-        else if (bp_is_fully_ambiguous(a) || bp_is_fully_ambiguous(b)) allowed = false;
-      }
-    }
-    double nw = allowed ? s.nodes[iu].pen + p.del_start + p.del_ext : XM_DISALLOWED;
-    double ex = s.nodes[iu].ins_y + p.del_ext;
-    ins_y = dmin(ex, nw);
-  }
-  double best = dmin(dmin(overlay, ins_x), ins_y);
-  if (!he || best < s.nodes[ie].pen || ins_x < s.nodes[ie].ins_x || ins_y < s.nodes[ie].ins_y) {
-    int fl = 0;
-    if (best != XM_DISALLOWED) {
-      int src;
-      if (best == overlay) src = s.flags[id]; else if (best == ins_x) src = s.flags[il]; else src = s.flags[iu];
-      fl = src & 6;
-      if (iabs(pa_signed_dist(s, x, y)) == 0) fl |= 2; else fl |= 4;
-    }
-    PNode n; n.pen = best; n.ins_x = ins_x; n.ins_y = ins_y;
-    pa_put(w, s, x, y, n, fl);
-  }
-}
-XM_INLINE bool pa_can_remove(const Blk& b) {  // canRemoveSection :358-366
-  if (b.a_len <= 0 && b.b_len <= 0) return true;
-  if ((b.a_start <= 0 && b.a_len <= 0) || (b.b_start <= 0 && b.b_len <= 0)) return true;
-  return false;
-}
-// The best-first search loop of PathAligner.align :153-192 with explore :722-729, update :555-571, computeUpdated
-// :573-719, putNode :446-473 and estimateOverallPenalty :475-521 folded into ONE compact step function: every per-search
-// constant lives in a register (PaRegs), the three neighbours share one copy of the update code, and base pairs are
-// classified through the 256-entry tables.  The step touches nothing but the search's own lattice/heap, so the same
-// code runs (a) warp-uniformly inside the calling warp (pa_search) and (b) one search per LANE inside the path-service
-// warp of a block (pa_service), where up to 31 searches of different queries advance in SIMT lockstep.
-struct PaRegs {
-  int A, B, H, step, goal_x, goal_y, diag, heap_cap, heap_n; uint32_t seq;
-  bool may_extend, confident;
-  double ins_start, ins_ext, del_start, del_ext, unaligned, max_ins, max_del, budget, min_indel, active;
-  const double* pen_tab; const uint8_t* cls_tab; PNode* nodes; uint8_t* flags; const uint8_t* qa; const uint8_t* rb; PHeapEnt* heap;
-  unsigned long long steps;
-};
-XM_INLINE void pa_regs_load(PaRegs& R, const PathState& S) {
-  R.A = S.A; R.B = S.B; R.H = S.H; R.step = S.step; R.goal_x = S.goal_x; R.goal_y = S.goal_y; R.diag = S.diagonal;
-  R.may_extend = S.may_extend != 0; R.confident = S.an_confident != 0;
-  R.ins_start = S.prm.ins_start; R.ins_ext = S.prm.ins_ext; R.del_start = S.prm.del_start; R.del_ext = S.prm.del_ext; R.unaligned = S.prm.unaligned;
-  R.max_ins = S.an_max_ins; R.max_del = S.an_max_del; R.budget = S.max_interesting + 0.000001;
-  R.min_indel = dmin(R.ins_start + R.ins_ext, R.del_start + R.del_ext);
-  R.pen_tab = S.prm.pen_tab; R.cls_tab = S.prm.cls_tab;
-  R.nodes = S.nodes; R.flags = S.flags; R.qa = S.qa; R.rb = S.rb; R.heap = S.heap; R.heap_cap = S.heap_cap;
-  R.heap_n = S.heap_n; R.seq = S.seq; R.active = S.active; R.steps = 0;
-}
-enum { PA_CONTINUE = -1, PA_GOAL = 0, PA_OVER_BUDGET = 1, PA_EMPTY = 2, PA_HEAP_FULL = 3 };
-// One iteration of the main loop :153-192 (pop the best node, explore its three neighbours).
-XM_INLINE int pa_step(PaRegs& R, int& last_x, int& last_y) {
-  PHeapEnt* heap = R.heap; PNode* nodes = R.nodes; uint8_t* flags = R.flags; const uint8_t* qa = R.qa; const uint8_t* rb = R.rb;
-  const int A = R.A, B = R.B, H = R.H, step = R.step;
-  if (R.heap_n == 0) return PA_EMPTY;  // priorities.poll() == null -> NullPointerException
-  PHeapEnt top = heap[0];
-  {  // pop
-    int heap_n = --R.heap_n;
-    PHeapEnt e = heap[heap_n];
-    int i = 0;
-    XM_NOUNROLL
-    while (true) {
-      int l = 2 * i + 1;
-      if (l >= heap_n) break;
-      int c = l;
-      PHeapEnt ce = heap[l];
-      if (l + 1 < heap_n) { PHeapEnt re = heap[l + 1]; if (pa_heap_less(re, ce)) { c = l + 1; ce = re; } }
-      if (pa_heap_less(ce, e)) { heap[i] = ce; i = c; } else break;
-    }
-    if (heap_n > 0) heap[i] = e;
-  }
-  const double active = top.pri;
-  R.active = active;
-  R.steps++;
-  if (active > R.budget) return PA_OVER_BUDGET;
-  if (top.x == R.goal_x) { last_x = top.x; last_y = top.y; return PA_GOAL; }
-  XM_NOUNROLL
-  for (int nb = 0; nb < 3; nb++) {  // (x+step, y), (x, y+step), (x+step, y+step)
-    const int x = top.x + (nb != 1 ? step : 0), y = top.y + (nb != 0 ? step : 0);
-    if (x <= 0 || x > A || y <= 0 || y > B) continue;
-    const int ie = x * H + y, il = ie - step * H, iu = ie - step, id = il - step;
-    const uint8_t fe = flags[ie], fl_ = flags[il], fu = flags[iu], fd = flags[id];
-    double ins_x = XM_DISALLOWED, ins_y = XM_DISALLOWED, overlay = XM_DISALLOWED;
-    if (fd & 1) overlay = nodes[id].pen + R.pen_tab[((int)qa[x - 1] << 4) | (int)rb[y - 1]];
-    if (fl_ & 1) {
-      const double lp = nodes[il].pen;
-      if (y == R.goal_y && R.may_extend) ins_x = lp + R.unaligned;
-      else {
-        bool allowed = true;
-        const int pa = x - 1 - step, pb = y - 1;
-        if (pa >= 0 && pa < A && pb >= 0 && pb < B) allowed = (R.cls_tab[((int)qa[pa] << 4) | (int)rb[pb]] & 1) != 0;
-        if (allowed) {
-          const int na = x - 1, nbb = y - 1 + step;
-          if (na >= 0 && na < A && nbb >= 0 && nbb < B) allowed = (R.cls_tab[((int)qa[na] << 4) | (int)rb[nbb]] & 6) == 0;
-        }
-        const double nw = allowed ? lp + R.ins_start + R.ins_ext : XM_DISALLOWED;
-        ins_x = dmin(nodes[il].ins_x + R.ins_ext, nw);
-      }
-    }
-    if (fu & 1) {
-      bool allowed = true;
-      const int pa = x - 1, pb = y - 1 - step;
-      if (pa >= 0 && pa < A && pb >= 0 && pb < B) allowed = (R.cls_tab[((int)qa[pa] << 4) | (int)rb[pb]] & 1) != 0;
-      if (allowed) {
-        const int na = x - 1 + step, nbb = y - 1;
-        if (na >= 0 && na < A && nbb >= 0 && nbb < B) allowed = (R.cls_tab[((int)qa[na] << 4) | (int)rb[nbb]] & 6) == 0;
-      }
-      const double nw = allowed ? nodes[iu].pen + R.del_start + R.del_ext : XM_DISALLOWED;
-      ins_y = dmin(nodes[iu].ins_y + R.del_ext, nw);
-    }
-    const double best = dmin(dmin(overlay, ins_x), ins_y);
-    if ((fe & 1) && !(best < nodes[ie].pen || ins_x < nodes[ie].ins_x || ins_y < nodes[ie].ins_y)) continue;
-    const int sd = x - y - R.diag;
-    int fl = 0;
-    if (best != XM_DISALLOWED) {
-      const int src = (best == overlay) ? fd : (best == ins_x) ? fl_ : fu;
-      fl = (src & 6) | (sd == 0 ? 2 : 4);
-    }
-    // estimateOverallPenalty :475-521
-    double est = best;
-    if (R.confident) {
-      const int sds = sd * step;
-      if (fl & 2) {
-        const bool over = (sds > 0) ? (fabs(sd * R.ins_ext) > R.max_ins) : (fabs(sd * R.del_ext) > R.max_del);
-        if (over) est = XM_DISALLOWED;
-        else if (!(fl & 4)) est = best + R.min_indel;
-      } else if (sds < 0) {
-        const double ie_ = fabs(sd * R.ins_ext);
-        if (ie_ > R.max_ins) est = XM_DISALLOWED;
-        else est = best + dmin(R.ins_start, ins_x - best) + ie_;
-      } else {
-        const double de = fabs(sd * R.del_ext);
-        if (de > R.max_del) est = XM_DISALLOWED;
-        else est = best + dmin(R.del_start, ins_y - best) + de;
-      }
-    }
-    if (est < active) est = active;
-    if (R.heap_n >= R.heap_cap) return PA_HEAP_FULL;
-    {  // push
-      PHeapEnt e; e.pri = est; e.seq = R.seq++; e.x = (int16_t)x; e.y = (int16_t)y;
-      int i = R.heap_n++;
+// PathAligner.align :120-192: seeds the queue (:120-150) and runs the best-first search (:153-192) with explore
+// :722-729, update :555-571, computeUpdated :573-719, putNode :446-473 and estimateOverallPenalty :475-521 folded
+// into ONE compact loop: every per-search constant lives in a register, the three neighbours share one copy of the
+// update code, and base pairs are classified through the 256-entry tables.  This loop is where gapped reads spend
+// their time.  Returns 0 goal reached (last_x/last_y), 1 over budget (null), 2 failed (w.status set).
+XM_FN int pa_search(WS& w, PathState& S, PaOverflow* ovf, int cap_ovf, int& last_x, int& last_y) {
+  const int A = S.A, B = S.B, H = S.H, step = S.step, goal_x = S.goal_x, goal_y = S.goal_y, diag = S.diagonal;
+  const bool may_extend = S.may_extend != 0, confident = S.an->confident != 0;
+  const double ins_start = S.prm.ins_start, ins_ext = S.prm.ins_ext, del_start = S.prm.del_start, del_ext = S.prm.del_ext, unaligned = S.prm.unaligned;
+  const double max_ins = S.an->max_ins, max_del = S.an->max_del, budget = S.max_interesting + 0.000001;
+  const double min_indel = dmin(ins_start + ins_ext, del_start + del_ext);
+  const double* pen_tab = S.prm.pen_tab; const uint8_t* cls_tab = S.prm.cls_tab;
+  PNode* nodes = S.nodes; uint8_t* flags = S.flags; const uint8_t* qa = S.qa; const uint8_t* rb = S.rb;
+  PaQueue Q;
+  Q.init(S.ent, S.ent_cap, ovf, cap_ovf);
+  int qrc = 0;
+  // seeding :120-150.  activePenalty is 0 here, estimates are never negative: no clamping needed.
+  {
+    const int start_x = S.start_x, start_y = S.start_y;
+    if (B >= A) {
+      double sisp = S.prm.starting_ins_start();
+      if (!may_extend) sisp = XM_DISALLOWED;
+      const int cnt = imax(0, B - A) + 1;
       XM_NOUNROLL
-      while (i > 0) { int pr = (i - 1) >> 1; PHeapEnt pe = heap[pr]; if (pa_heap_less(e, pe)) { heap[i] = pe; i = pr; } else break; }
-      heap[i] = e;
+      for (int i = 0; i < cnt && qrc == 0; i++) {
+        PNode n; n.pen = 0; n.ins_x = sisp; n.ins_y = XM_DISALLOWED;
+        const int x = start_x, y = start_y + i * step;
+        qrc = Q.push(pa_estimate(S, x, y, n, 0), x, y);
+        const int idx = x * H + y; nodes[idx] = n; flags[idx] = 1;
+      }
+    } else {
+      const int cnt = imax(0, A - B) + 1;
+      XM_NOUNROLL
+      for (int i = 0; i < cnt && qrc == 0; i++) {
+        PNode n; n.pen = 0; n.ins_x = XM_DISALLOWED; n.ins_y = XM_DISALLOWED;
+        const int x = start_x + i * step, y = start_y;
+        qrc = Q.push(pa_estimate(S, x, y, n, 0), x, y);
+        const int idx = x * H + y; nodes[idx] = n; flags[idx] = 1;
+      }
     }
-    PNode n; n.pen = best; n.ins_x = ins_x; n.ins_y = ins_y;
-    nodes[ie] = n; flags[ie] = (uint8_t)(1 | fl);
-  }
-  return PA_CONTINUE;
-}
-// Runs the search inside the calling warp (all lanes on the same values).  Returns 0 goal reached (last_x/last_y),
-// 1 over budget (null), 2 failed (w.status set).
-XM_FN int pa_search(WS& w, PathState& S, int& last_x, int& last_y) {
-  PaRegs R;
-  pa_regs_load(R, S);
-  int rc;
-  XM_NOUNROLL
-  do { rc = pa_step(R, last_x, last_y); } while (rc == PA_CONTINUE);
-  S.heap_n = R.heap_n; S.seq = R.seq; S.active = R.active;
-  w.st_path_steps += R.steps;
-  if (rc == PA_EMPTY) { w.fail(Q_INTERNAL); return 2; }
-  if (rc == PA_HEAP_FULL) { w.fail(Q_NEED_MORE); return 2; }
-  return rc;
-}
-#if defined(__CUDACC__)
-// ---- path service: one warp per block runs the searches of the block's other warps, one search per lane ----
-// The per-query code is scalar: a client warp executes it once on 32 identical lanes.  The best-first search is the
-// biggest scalar loop, so a client posts its PathState here instead and sleeps; lane l of the service warp serves
-// client warp l, picks a posted search up at the next step boundary and advances it together with the searches of
-// the other lanes.  Same step code, same order of operations per search => same bits.
-struct PathSvcSlot {
-  PathState* req;
-  volatile int state;  // 0 idle, 1 posted, 2 done
-  volatile int rc, last_x, last_y;
-  volatile unsigned long long steps;
-};
-__device__ __noinline__ void pa_service(PathSvcSlot* slots, int n_clients, int my_index, int n_services, volatile int* clients_done) {
-  const int lane = (int)(threadIdx.x & 31);
-  const int client = lane * n_services + my_index;  // clients are dealt round-robin to the block's service warps
-  const bool have_client = client < n_clients;
-  PathSvcSlot* sl = slots + (have_client ? client : 0);
-  bool busy = false;
-  PaRegs R;
-  int lx = -1, ly = -1;
-  PathState* cur = nullptr;
-  XM_NOUNROLL
-  while (true) {
-    __syncwarp();
-    if (!busy && have_client && sl->state == 1) {
-      __threadfence_block();
-      cur = sl->req;
-      pa_regs_load(R, *cur);
-      lx = -1; ly = -1;
-      busy = true;
-    }
-    if (!__any_sync(0xffffffffu, busy)) {
-      int d = (lane == 0) ? *clients_done : 0;
-      d = __shfl_sync(0xffffffffu, d, 0);
-      if (d >= n_clients) break;
-      __nanosleep(100);
-      continue;
-    }
-    if (busy) {
-      int rc = pa_step(R, lx, ly);
-      if (rc != PA_CONTINUE) {
-        cur->heap_n = R.heap_n; cur->seq = R.seq; cur->active = R.active;
-        sl->rc = rc; sl->last_x = lx; sl->last_y = ly; sl->steps = R.steps;
-        __threadfence_block();
-        sl->state = 2;
-        busy = false;
+    if (may_extend) {
+      const int cnt = j2i(S.an->max_ins / del_ext);
+      XM_NOUNROLL
+      for (int i = 1; i < cnt && qrc == 0; i++) {
+        const int xa = start_x + i * step;
+        PNode n; n.pen = i * unaligned; n.ins_x = XM_DISALLOWED; n.ins_y = XM_DISALLOWED;
+        // outside the lattice the reference still queues the node (saveNode ignores x < 0; x > width is stored but
+        // never read), and popping it can end the search when its priority exceeds the budget
+        if (xa < -32000 || xa > 32000) { qrc = 1; break; }
+        qrc = Q.push(pa_estimate(S, xa, start_y, n, 0), xa, start_y);
+        if (xa >= 0 && xa < S.W) { const int idx = xa * H + start_y; nodes[idx] = n; flags[idx] = 1; }
       }
     }
   }
-}
-// client side: post the search, sleep until the service lane finished it
-__device__ __noinline__ int pa_search_remote(WS& w, PathState& S, int& last_x, int& last_y) {
-  PathSvcSlot* sl = (PathSvcSlot*)w.svc;
-  __syncwarp();
-  if ((threadIdx.x & 31) == 0) {
-    sl->req = &S;
-    __threadfence_block();
-    sl->state = 1;
+  unsigned long long steps = 0;
+  int rc = 2;
+  XM_NOUNROLL
+  while (qrc == 0) {
+    int tx, ty;
+    if (!Q.pop(tx, ty)) { w.fail(Q_INTERNAL); break; }  // priorities.poll() == null -> NullPointerException
+    const double active = Q.cur_key;
+    steps++;
+    if (active > budget) { rc = 1; break; }
+    if (tx == goal_x) { last_x = tx; last_y = ty; rc = 0; break; }
     XM_NOUNROLL
-    while (sl->state != 2) __nanosleep(2000);
-    __threadfence_block();
+    for (int nb = 0; nb < 3; nb++) {  // (x+step, y), (x, y+step), (x+step, y+step)
+      const int x = tx + (nb != 1 ? step : 0), y = ty + (nb != 0 ? step : 0);
+      if (x <= 0 || x > A || y <= 0 || y > B) continue;
+      const int ie = x * H + y, il = ie - step * H, iu = ie - step, id = il - step;
+      const uint8_t fe = flags[ie], fl_ = flags[il], fu = flags[iu], fd = flags[id];
+      double ins_x = XM_DISALLOWED, ins_y = XM_DISALLOWED, overlay = XM_DISALLOWED;
+      if (fd & 1) overlay = nodes[id].pen + pen_tab[((int)qa[x - 1] << 4) | (int)rb[y - 1]];
+      if (fl_ & 1) {
+        const double lp = nodes[il].pen;
+        if (y == goal_y && may_extend) ins_x = lp + unaligned;
+        else {
+          bool allowed = true;
+          const int pa = x - 1 - step, pb = y - 1;
+          if (pa >= 0 && pa < A && pb >= 0 && pb < B) allowed = (cls_tab[((int)qa[pa] << 4) | (int)rb[pb]] & 1) != 0;
+          if (allowed) {
+            const int na = x - 1, nbb = y - 1 + step;
+            if (na >= 0 && na < A && nbb >= 0 && nbb < B) allowed = (cls_tab[((int)qa[na] << 4) | (int)rb[nbb]] & 6) == 0;
+          }
+          const double nw = allowed ? lp + ins_start + ins_ext : XM_DISALLOWED;
+          ins_x = dmin(nodes[il].ins_x + ins_ext, nw);
+        }
+      }
+      if (fu & 1) {
+        bool allowed = true;
+        const int pa = x - 1, pb = y - 1 - step;
+        if (pa >= 0 && pa < A && pb >= 0 && pb < B) allowed = (cls_tab[((int)qa[pa] << 4) | (int)rb[pb]] & 1) != 0;
+        if (allowed) {
+          const int na = x - 1 + step, nbb = y - 1;
+          if (na >= 0 && na < A && nbb >= 0 && nbb < B) allowed = (cls_tab[((int)qa[na] << 4) | (int)rb[nbb]] & 6) == 0;
+        }
+        const double nw = allowed ? nodes[iu].pen + del_start + del_ext : XM_DISALLOWED;
+        ins_y = dmin(nodes[iu].ins_y + del_ext, nw);
+      }
+      const double best = dmin(dmin(overlay, ins_x), ins_y);
+      if ((fe & 1) && !(best < nodes[ie].pen || ins_x < nodes[ie].ins_x || ins_y < nodes[ie].ins_y)) continue;
+      const int sd = x - y - diag;
+      int fl = 0;
+      if (best != XM_DISALLOWED) {
+        const int src = (best == overlay) ? fd : (best == ins_x) ? fl_ : fu;
+        fl = (src & 6) | (sd == 0 ? 2 : 4);
+      }
+      // estimateOverallPenalty :475-521
+      double est = best;
+      if (confident) {
+        const int sds = sd * step;
+        if (fl & 2) {
+          const bool over = (sds > 0) ? (fabs(sd * ins_ext) > max_ins) : (fabs(sd * del_ext) > max_del);
+          if (over) est = XM_DISALLOWED;
+          else if (!(fl & 4)) est = best + min_indel;
+        } else if (sds < 0) {
+          const double ie_ = fabs(sd * ins_ext);
+          if (ie_ > max_ins) est = XM_DISALLOWED;
+          else est = best + dmin(ins_start, ins_x - best) + ie_;
+        } else {
+          const double de = fabs(sd * del_ext);
+          if (de > max_del) est = XM_DISALLOWED;
+          else est = best + dmin(del_start, ins_y - best) + de;
+        }
+      }
+      if (est < active) est = active;
+      qrc = Q.push(est, x, y);
+      if (qrc != 0) break;
+      PNode n; n.pen = best; n.ins_x = ins_x; n.ins_y = ins_y;
+      nodes[ie] = n; flags[ie] = (uint8_t)(1 | fl);
+    }
   }
-  __syncwarp();
-  int rc = sl->rc; last_x = sl->last_x; last_y = sl->last_y;
-  __syncwarp();
-  if ((threadIdx.x & 31) == 0) { w.st_path_steps += sl->steps; sl->state = 0; }  // one lane: the lanes need not be converged here
-  __syncwarp();
-  if (rc == PA_EMPTY) { w.fail(Q_INTERNAL); return 2; }
-  if (rc == PA_HEAP_FULL) { w.fail(Q_NEED_MORE); return 2; }
+  if (qrc != 0) { w.fail(Q_NEED_MORE); rc = 2; }
+  w.st_path_steps += steps;
   return rc;
 }
-#endif
 XM_FN DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Params& p, Analysis& an) {  // PathAligner.align :55-293
   PhaseClock pc_(&w.st_cyc[3]);
   long long mark = w.scratch_top;
@@ -617,12 +600,10 @@ XM_FN DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Pa
   if (!sp) return aln_null();
   PathState& s = *sp;
   s.prm = p; s.ctx = c; s.an = &an;
-  s.an_confident = an.confident; s.an_max_ins = an.max_ins; s.an_max_del = an.max_del;
   s.max_interesting = q.length() * p.max_error_rate;
   s.start_a = q.start; s.end_a = q.end; s.start_b = r.start; s.end_b = r.end;
   s.A = q.length(); s.B = r.length(); s.W = s.A + 2; s.H = s.B + 2;
   s.diagonal = s.start_b - (s.start_a + an.predicted);
-  s.active = 0; s.seq = 0; s.heap_n = 0;
   {  // unpack both sections once (lanes split the bases on the device)
     uint8_t* qa = (uint8_t*)w.salloc(s.A + 1); uint8_t* rb = (uint8_t*)w.salloc(s.B + 1);
     if (w.status != 0) { w.scratch_top = mark; return aln_null(); }
@@ -671,10 +652,15 @@ XM_FN DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Pa
   s.nodes = (PNode*)w.salloc(cells * (long long)sizeof(PNode));
   if (w.status != 0) { w.scratch_top = mark; return aln_null(); }
   long long remaining = w.scratch_size - w.scratch_top;
-  s.heap_cap = (int)((remaining / 2) / (long long)sizeof(PHeapEnt));
-  if (s.heap_cap > 3 * cells + 16) s.heap_cap = (int)(3 * cells + 16);
-  s.heap = (PHeapEnt*)w.salloc((long long)s.heap_cap * (long long)sizeof(PHeapEnt));
-  if (w.status != 0 || s.heap_cap < 8) { w.fail(Q_NEED_MORE); w.scratch_top = mark; return aln_null(); }
+  // one spill bucket per distinct live priority: a budget of P has at most ~P / 0.1 of them per rounding variant
+  int cap_ovf = (int)(s.max_interesting * 64.0) + 256;
+  if ((long long)cap_ovf * (long long)sizeof(PaOverflow) > remaining / 8) cap_ovf = (int)((remaining / 8) / (long long)sizeof(PaOverflow));
+  PaOverflow* ovf = (PaOverflow*)w.salloc((long long)cap_ovf * (long long)sizeof(PaOverflow));
+  long long ent_cap = (remaining / 2) / (long long)sizeof(PEnt);
+  if (ent_cap > 3 * cells + 64) ent_cap = 3 * cells + 64;
+  s.ent_cap = (int)ent_cap;
+  s.ent = (PEnt*)w.salloc(ent_cap * (long long)sizeof(PEnt));
+  if (w.status != 0 || s.ent_cap < 8) { w.fail(Q_NEED_MORE); w.scratch_top = mark; return aln_null(); }
 #if defined(__CUDA_ARCH__)
   {  // lanes clear the lattice flags together; salloc keeps s.flags 8-byte aligned
     unsigned long long* f8 = (unsigned long long*)s.flags;
@@ -687,42 +673,9 @@ XM_FN DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Pa
   XM_NOUNROLL
   for (long long i = 0; i < cells; i++) s.flags[i] = 0;
 #endif
-
-  if (s.B >= s.A) {
-    double sisp = p.starting_ins_start();
-    if (!s.may_extend) sisp = XM_DISALLOWED;
-    int cnt = imax(0, s.B - s.A) + 1;
-    XM_NOUNROLL
-    for (int i = 0; i < cnt; i++) { PNode n; n.pen = 0; n.ins_x = sisp; n.ins_y = XM_DISALLOWED; pa_put(w, s, s.start_x, s.start_y + i * s.step, n, 0); }
-  } else {
-    int cnt = imax(0, s.A - s.B) + 1;
-    XM_NOUNROLL
-    for (int i = 0; i < cnt; i++) { PNode n; n.pen = 0; n.ins_x = XM_DISALLOWED; n.ins_y = XM_DISALLOWED; pa_put(w, s, s.start_x + i * s.step, s.start_y, n, 0); }
-  }
-  if (s.may_extend) {
-    int cnt = j2i(an.max_ins / p.del_ext);
-    XM_NOUNROLL
-    for (int i = 1; i < cnt; i++) {
-      int xa = s.start_x + i * s.step;
-      PNode n; n.pen = i * p.unaligned; n.ins_x = XM_DISALLOWED; n.ins_y = XM_DISALLOWED;
-      if (xa >= 0 && xa < s.W) pa_put(w, s, xa, s.start_y, n, 0);
-      else {
-        // outside the lattice: the reference still queues the node (saveNode ignores x < 0; x > width is stored but
-        // never read), and popping it can end the search when its priority exceeds the budget
-        if (xa < -32000 || xa > 32000) { w.fail(Q_NEED_MORE); break; }
-        double est = pa_estimate(s, xa, s.start_y, n, 0);
-        if (est < s.active) est = s.active;
-        pa_heap_push(w, s, est, xa, s.start_y);
-      }
-    }
-  }
   int last_x = -1, last_y = -1;
-  if (w.status == 0) {
-    int rc;
-#if defined(__CUDA_ARCH__)
-    if (w.svc != nullptr) rc = pa_search_remote(w, s, last_x, last_y); else
-#endif
-    rc = pa_search(w, s, last_x, last_y);
+  {
+    int rc = pa_search(w, s, ovf, cap_ovf, last_x, last_y);
     if (rc == 1 && w.status == 0) { w.scratch_top = mark; return aln_null(); }
   }
   if (w.status != 0) { w.scratch_top = mark; return aln_null(); }

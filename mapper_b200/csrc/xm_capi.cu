@@ -20,8 +20,8 @@
 using namespace xm;
 
 // ---------------------------------------------------------------- kernels
-// first pass: blocks of 4 warps, 8 per SM.  full kernel: ONE block per SM of up to 32 warps = 1 path-service warp
-// (pa_service, xm_align.h) + up to 31 client warps, each client owning one query at a time.
+// first pass: blocks of 4 warps, 8 per SM.  full kernel: ONE block per SM of up to 32 warps, each warp owning one
+// query at a time.
 #define XM_BLOCK 128
 #ifndef XM_MIN_BLOCKS
 #define XM_MIN_BLOCKS 8
@@ -44,7 +44,6 @@ struct LaunchD {
   char* arenas; long long arena_bytes;
   int last_tier;
   int exp_dup;                            // experiment (XM_EXP_DUP=n): every warp of a block aligns the same n queries, results discarded by overwrite
-  int path_service;                       // full kernel: the first `path_service` warps of every block are path-service warps
   long long* q_cycles;                    // optional per-query cost probe (XM_QCYCLES=1): clock64 ticks of the tier that finished it
 };
 
@@ -54,27 +53,17 @@ template <bool EASY>
 __global__ void __launch_bounds__(EASY ? XM_BLOCK : XM_FULL_BLOCK, EASY ? XM_MIN_BLOCKS : 1) xm_align_kernel(LaunchD L) {
   const int lane = threadIdx.x & 31;
   const int warp_in_block = (int)(threadIdx.x >> 5), warps_per_block = (int)(blockDim.x >> 5);
-  const int n_services = EASY ? 0 : L.path_service;
-  const bool service = n_services > 0;
-  const int clients_per_block = warps_per_block - n_services;
-  const int client = warp_in_block - n_services;   // < 0: a service warp
-  long long warp = (long long)blockIdx.x * clients_per_block + client;
+  long long warp = (long long)blockIdx.x * warps_per_block + warp_in_block;
   char* arena = L.arenas + warp * L.arena_bytes;
   __shared__ double s_pen[256];
   __shared__ uint8_t s_cls[256];
   // the per-query state lives in shared memory, one slot per warp: in local memory every lane would keep (and
   // write through to L2/HBM) its own copy of the same bytes
   __shared__ WS s_ws[(EASY ? XM_BLOCK : XM_FULL_BLOCK) / 32];
-  __shared__ PathSvcSlot s_svc[EASY ? 1 : 32];
-  __shared__ int s_clients_done;
   WS& w = s_ws[threadIdx.x >> 5];
-  if (threadIdx.x < 32) { s_svc[EASY ? 0 : threadIdx.x].state = 0; s_svc[EASY ? 0 : threadIdx.x].req = nullptr; }
-  if (threadIdx.x == 0) s_clients_done = 0;
-  w.svc = (service && client >= 0) ? (void*)&s_svc[client] : nullptr;
   fill_pen_tab(L.prm, s_pen, s_cls, threadIdx.x, blockDim.x);
   __syncthreads();
   L.prm.pen_tab = s_pen; L.prm.cls_tab = s_cls;
-  if (!EASY && service && client < 0) { pa_service(s_svc, clients_per_block, warp_in_block, n_services, &s_clients_done); return; }
   unsigned long long st[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   int dup_i = 0;
   while (true) {
@@ -120,7 +109,6 @@ __global__ void __launch_bounds__(EASY ? XM_BLOCK : XM_FULL_BLOCK, EASY ? XM_MIN
     }
   }
   if (lane == 0) for (int i = 0; i < 14; i++) if (st[i]) atomicAdd(&L.out.stats[i], st[i]);
-  if (service) { __syncwarp(); if (lane == 0) { __threadfence_block(); atomicAdd(&s_clients_done, 1); } }
 }
 
 // first_seq[q] = exclusive prefix sum of n_seqs_per_query (single block scan is enough off the hot path; uses a
@@ -323,7 +311,7 @@ struct xm_results {
 struct xm_handle {
   HostModel m;
   int device = 0, sm_count = 148, blocks_per_sm = 4;
-  int path_service = 0, full_warps = XM_FULL_BLOCK / 32;  // full kernel: warps per block (service + clients)
+  int full_warps = XM_FULL_BLOCK / 32;  // full kernel: warps per block
   std::string err;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
@@ -403,9 +391,7 @@ int xm_create(const xm_params* p, int device, xm_handle** out) {
   { int nb = 0; if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, xm_align_kernel<true>, XM_BLOCK, 0) == cudaSuccess && nb > 0) h->blocks_per_sm = nb; }
   if (const char* e = getenv("XM_BLOCKS_PER_SM")) { int v = atoi(e); if (v > 0) h->blocks_per_sm = v; }
   if (const char* e = getenv("XM_SORT_HARD")) h->sort_hard = atoi(e) != 0;
-  if (const char* e = getenv("XM_PATH_SERVICE")) { int v = atoi(e); if (v >= 0 && v <= 8) h->path_service = v; }
-  if (const char* e = getenv("XM_FULL_WARPS")) { int v = atoi(e); if (v >= 2 && v <= XM_FULL_BLOCK / 32) h->full_warps = v; }
-  if (h->path_service >= h->full_warps) h->path_service = h->full_warps - 1;
+  if (const char* e = getenv("XM_FULL_WARPS")) { int v = atoi(e); if (v >= 1 && v <= XM_FULL_BLOCK / 32) h->full_warps = v; }
   cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3);
   size_t stack = 32 * 1024;
@@ -556,8 +542,8 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
   unsigned long long easy_stats[7] = {0, 0, 0, 0, 0, 0, 0};
   for (int round = 0; round < 4; round++) {  // extra rounds only after growing the result arena
     for (int tier = (round == 0 ? -1 : 0); tier < XM_NUM_TIERS && n_ids > 0; tier++) {  // tier -1: the first-pass kernel
-      // tier < 0: first pass, blocks of 4 warps.  tier >= 0: one block per SM of `cpb` client warps (+ 1 path-service warp)
-      int cpb = warps_per_block, extra = 0, blocks = 1;
+      // tier < 0: first pass, blocks of 4 warps.  tier >= 0: one block per SM of `cpb` warps
+      int cpb = warps_per_block, blocks = 1;
       long long arena = 0;
       if (tier < 0) {
         arena = easy_arena_bytes(max_seq_len, 2);
@@ -569,8 +555,7 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
         if (blocks < 1) blocks = 1;
         if ((long long)blocks * warps_per_block * arena > (long long)h->ws_budget && blocks > 1) blocks = (int)(h->ws_budget / (size_t)(arena * warps_per_block));
       } else {
-        extra = h->path_service;
-        cpb = h->full_warps - extra;
+        cpb = h->full_warps;
         long long resident = (long long)h->sm_count * cpb;
         arena = tier_arena_bytes(tier, max_seq_len, 2, (long long)h->ws_budget, resident);
         long long clients = resident, max_warps = (long long)(h->ws_budget / (size_t)arena);
@@ -579,7 +564,6 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
         if (clients < 1) { h->err = "workspace budget too small for one query"; return XM_ERR_CUDA; }
         if (clients < (long long)h->sm_count * cpb) cpb = (int)(clients / h->sm_count);
         if (cpb < 1) cpb = 1;
-        if (extra > cpb) extra = cpb;
         blocks = (int)(clients / cpb);
         if (blocks > h->sm_count) blocks = h->sm_count;
       }
@@ -587,7 +571,6 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
       if (!h->d_ws.ensure((size_t)blocks * cpb * (size_t)arena)) { h->err = "out of device memory (workspace)"; return XM_ERR_CUDA; }
       CK(cudaMemsetAsync(d_ints, 0, 8, st));  // ticket, n_need_more
       L.ids = ids; L.n_ids = n_ids; L.need_more = next_ids; L.arenas = (char*)h->d_ws.p; L.arena_bytes = arena; L.last_tier = (tier == XM_NUM_TIERS - 1);
-      L.path_service = extra;
       L.need_more_key = nullptr;
       if (tier < 0 && h->sort_hard) { if (!h->d_keys_a.ensure((size_t)n_ids * 4) || !h->d_keys_b.ensure((size_t)n_ids * 4)) { h->err = "out of device memory"; return XM_ERR_CUDA; } L.need_more_key = (int32_t*)h->d_keys_a.p; }
       L.exp_dup = 0;
@@ -595,7 +578,7 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
       bool time_it = (round == 0 && tier == -1);
       CK(cudaEventRecord(h->ev2, st));
       if (tier < 0) xm_align_kernel<true><<<blocks, block, 0, st>>>(L);
-      else xm_align_kernel<false><<<blocks, 32 * (cpb + extra), 0, st>>>(L);
+      else xm_align_kernel<false><<<blocks, 32 * cpb, 0, st>>>(L);
       CK(cudaEventRecord(h->ev3, st));
       launches++;
       CK(cudaGetLastError());

@@ -230,7 +230,6 @@ struct WS {
   }
   uint8_t* qbytes[2][2];  // [mate][reverse-complemented]: one code per byte
   int hard_hint;  // first pass: cost estimate of a query handed to the full kernel (its ungapped penalty), used to start long queries first
-  void* svc;  // PathSvcSlot of this warp when the block runs a path-service warp (device, full kernel), else nullptr
   XM_INLINE SeqView query_view(int mate, int rev) const { SeqView v = query.seq[mate]; v.rc = rev; v.bytes = qbytes[mate][rev]; v.b0 = 0; v.bn = v.len; return v; }
 };
 

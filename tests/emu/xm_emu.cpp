@@ -96,7 +96,7 @@ void* xe_align_batch(void* h, int nq, const uint16_t* packed, const int64_t* seq
       {  // first pass: the EASY instantiation in its small arena, exactly as the library's first kernel runs it
         long long bytes = easy_arena_bytes(max_len, 2);
         if ((long long)easy_arena.size() < bytes) easy_arena.resize((size_t)bytes);
-        WS w; w.svc = nullptr;
+        WS w;
         OutArena out; out.q = oq.data(); out.choices = choices.data(); out.cap_choices = capc; out.sas = sas.data(); out.cap_sas = caps;
         out.blocks = blocks.data(); out.cap_blocks = capb; out.stats = nullptr;
         OutQuery rec; rec.status = 0; rec.n_comp = 1; rec.n_choice[0] = rec.n_choice[1] = 0; rec.choice_first[0] = rec.choice_first[1] = 0;
@@ -113,7 +113,7 @@ void* xe_align_batch(void* h, int nq, const uint16_t* packed, const int64_t* seq
       for (int tier = 0; tier < XM_NUM_TIERS && tier <= max_tier && status == Q_NEED_MORE; tier++) {
         long long bytes = tier_arena_bytes(tier, max_len, 2);
         if ((long long)arenas[(size_t)tier].size() < bytes) arenas[(size_t)tier].resize((size_t)bytes);
-        WS w; w.svc = nullptr;
+        WS w;
         OutArena out; out.q = oq.data(); out.choices = choices.data(); out.cap_choices = capc; out.sas = sas.data(); out.cap_sas = caps;
         out.blocks = blocks.data(); out.cap_blocks = capb; out.stats = nullptr;
         OutQuery rec; rec.status = 0; rec.n_comp = 1; rec.n_choice[0] = rec.n_choice[1] = 0; rec.choice_first[0] = rec.choice_first[1] = 0;
