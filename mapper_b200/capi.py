@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libxmapper_b200.so")
+LIB_PATH = os.environ.get("XM_LIB_PATH") or os.path.join(HERE, "libxmapper_b200.so")  # XM_LIB_PATH: build-variant experiments
 
 EXPORTS = ["xm_create", "xm_destroy", "xm_last_error", "xm_set_reference", "xm_set_index_length", "xm_finish_index",
            "xm_build_index", "xm_get_index_length", "xm_index_info", "xm_set_duplications", "xm_build_duplications",

@@ -26,7 +26,9 @@ using namespace xm;
 #ifndef XM_MIN_BLOCKS
 #define XM_MIN_BLOCKS 8
 #endif
+#ifndef XM_FULL_BLOCK
 #define XM_FULL_BLOCK 1024
+#endif
 struct BatchD {
   int n_queries;
   const uint16_t* packed; const int64_t* seq_word_off; const int32_t* seq_len; const int64_t* first_seq;  // first_seq: n_queries+1
