@@ -34,7 +34,7 @@ enum xm_status {
 /* per-query status in xm_results (q_status) */
 enum xm_query_status {
   XM_Q_OK = 0,
-  XM_Q_AMBIGUOUS_QUERY = -2,  /* query contains IUPAC-ambiguous bases next to a seed (MultiHashBlock path, HashBlock_ParentRow.java:97-120): not implemented on device */
+  XM_Q_AMBIGUOUS_QUERY = -2,  /* query with more than 64 IUPAC-ambiguous bases (MultiHashBlock conditions, HashBlock_ParentRow.java:97-120, are kept as 64-bit sets) */
   XM_Q_INDEX_TOO_SHORT = -3,  /* a seed needs a table longer than the index was built for (Readable_HashBlock_Database.java:108-113) */
   XM_Q_WORKSPACE = -5,        /* largest workspace tier exhausted */
   XM_Q_INTERNAL = -6          /* the reference would have thrown (e.g. PathAligner.java:159 on an empty queue) */

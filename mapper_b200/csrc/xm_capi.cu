@@ -599,7 +599,6 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
         cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, (const int32_t*)h->d_keys_a.p, (int32_t*)h->d_keys_b.p, (const int32_t*)next_ids, other, counts[1], 0, 32, st);
         if (!h->d_sort_tmp.ensure(tb + 16)) { h->err = "out of device memory"; return XM_ERR_CUDA; }
         CK(cub::DeviceRadixSort::SortPairsDescending(h->d_sort_tmp.p, tb, (const int32_t*)h->d_keys_a.p, (int32_t*)h->d_keys_b.p, (const int32_t*)next_ids, other, counts[1], 0, 32, st));
-        launches += 3;
         int32_t* t = next_ids; next_ids = other; other = t;
       }
       ids = next_ids; n_ids = counts[1];
@@ -668,7 +667,7 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
     c.choice_inner = (int32_t*)(d + R->r.slab_off[6]); c.sa_contig = (int32_t*)(d + R->r.slab_off[7]); c.blocks = (int32_t*)(d + R->r.slab_off[8]);
     c.q_status = (int32_t*)(d + R->r.slab_off[9]); c.sa_reversed = (uint8_t*)(d + R->r.slab_off[10]);
     xm_csr_fill_kernel<<<(nq + 255) / 256, 256, 0, st>>>(L.out, nq, d_base, c);
-    launches += 6;
+    launches += 2;  // xm_csr_count + xm_csr_fill (the cub scans in between are library kernels)
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, st));  // device time of a step = every kernel from the scan of n_seqs to the CSR fill
     CK(cudaMemcpyAsync(R->slab, d, slab_bytes, cudaMemcpyDeviceToHost, st));

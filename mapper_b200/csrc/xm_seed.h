@@ -156,7 +156,13 @@ XM_FN bool with_gap_and_extension(const HB& b, const SeqView& seq, HB& out) {
 // compact the survivors with a ballot.  child/up are the links the seed walk follows instead of searching.
 XM_INLINE long long pyr_arena_bytes(int len) { return (((long long)(len + 3) * 4 + 15) & ~15LL) + 64 + 20LL * (8LL * len + 64); }
 struct HB16 { int16_t start, len; int32_t fwd, rev; uint8_t flags; int8_t gap_dir; int16_t extra; };
+// One possibility of a MultiHashBlock (M/ConditionalHashBlock.java): the block (valid iff has) that exists when the
+// IUPAC-ambiguous query bases in `mask` (by ordinal among the query's ambiguous positions) take the bases in v0/v1
+// (2 bits per ordinal: A0 C1 G2 T3) - the bit-set form of M/SequenceCondition.java.
+struct POpt { HB16 hb; unsigned long long mask, v0, v1; int has, pad; };
+static const uint8_t HB_MULTI = 0x80;  // HB16::flags / HB::flags: the entry is a MultiHashBlock; fwd = first POpt, rev = number of POpts
 struct Pyr {
+  POpt* opt; int n_opt, cap_opt;   // possibilities of the multi-blocks (only queries with ambiguous bases)
   HB16* blk;          // all levels back to back, each level ascending by start
   int16_t* child;     // per block: index within the level below of its left parent (level 0: -1)
   int16_t* up;        // per block: index within the level above of the block it is the left parent of, or -1
@@ -298,6 +304,144 @@ XM_FN int pyr_find_after(const Pyr& P, int level, int p) {
   while (lo < hi) { int mid = (lo + hi) >> 1; if ((int)b[mid].start > p) hi = mid; else lo = mid + 1; }
   return lo < n ? lo : -1;
 }
+// ---- queries with IUPAC-ambiguous bases: MultiHashBlocks (M/MultiHashBlock.java, M/ConditionalHashBlock.java,
+// M/SequenceCondition.java, HashBlock_BaseRow.java:27-59, HashBlock_ParentRow.java:69-191) ----
+// Rare, so built by a scalar pass.  A multi-block occupies one entry of its level like any block (same start, child and
+// up links); the walk only ever asks for its start and steps past it (HashBlockPath.skipMultiblocks :130-140), but its
+// possibilities decide which blocks exist above it, so they are kept in full.
+XM_INLINE bool popt_intersect(const POpt& a, const POpt& b, POpt& out) {  // SequenceCondition.intersect :27-106; false = conflict
+  const unsigned long long common = a.mask & b.mask;
+  unsigned long long c = common;
+  XM_NOUNROLL
+  while (c) {
+    int k = 0;
+    { unsigned long long t = c; while (!(t & 1ull)) { t >>= 1; k++; } }
+    c &= c - 1;
+    const unsigned long long av = (k < 32) ? (a.v0 >> (2 * k)) & 3ull : (a.v1 >> (2 * (k - 32))) & 3ull;
+    const unsigned long long bv = (k < 32) ? (b.v0 >> (2 * k)) & 3ull : (b.v1 >> (2 * (k - 32))) & 3ull;
+    if (av != bv) return false;
+  }
+  out.mask = a.mask | b.mask; out.v0 = a.v0 | b.v0; out.v1 = a.v1 | b.v1;
+  return true;
+}
+XM_INLINE bool hb16_should_merge(const HB16& L, const HB16& R) {  // shouldMergeBlocks :200-208
+  return ((int)L.start + (int)L.len >= (int)R.start) && ((L.flags & 2) || (R.flags & 1));
+}
+// possibilities of entry e of a level: a single block counts as one unconditional possibility
+XM_INLINE int pyr_num_opts(const HB16& e) { return (e.flags & HB_MULTI) ? (int)e.rev : 1; }
+XM_INLINE POpt pyr_opt(const Pyr& P, const HB16& e, int k) {
+  if (e.flags & HB_MULTI) return P.opt[e.fwd + k];
+  POpt o; o.hb = e; o.mask = 0; o.v0 = 0; o.v1 = 0; o.has = 1; o.pad = 0; return o;
+}
+struct PExpandFrame { int j, k, found, pad; POpt cond; };
+// HashBlock_ParentRow.expand :137-191 with its recursion unrolled onto `stack`: appends to res[0..n_res)
+XM_FN bool pyr_expand(WS& w, const Pyr& P, const HB16* prev, int n_prev, const HB16& left, const POpt& start_cond, int j_from,
+                      POpt* res, int& n_res, int cap_res, PExpandFrame* stack, int cap_stack) {
+  const int max_combos = 64;  // maxNumCombinationsToExpand :10
+  int sp = 0;
+  stack[0].j = j_from + 1; stack[0].k = 0; stack[0].found = 0; stack[0].cond = start_cond; sp = 1;
+  XM_NOUNROLL
+  while (sp > 0) {
+    PExpandFrame& f = stack[sp - 1];
+    if (f.j >= n_prev) { sp--; continue; }           // getAfter(...) == null
+    const HB16 nxt = prev[f.j];
+    if (f.k >= pyr_num_opts(nxt)) { sp--; continue; }
+    const POpt ro = pyr_opt(P, nxt, f.k);
+    f.k++;
+    POpt inter;
+    if (!popt_intersect(f.cond, ro, inter)) { if (f.found) sp--; continue; }  // :163-167 (break once an intersection was seen)
+    f.found = 1;
+    if (n_res > max_combos) { sp--; continue; }      // :170 return
+    if (!ro.has) {                                   // :171-174 look further right under the narrowed condition
+      if (sp >= cap_stack) { w.fail(Q_NEED_MORE); return false; }
+      const int nj = f.j + 1;
+      PExpandFrame& g = stack[sp++];
+      g.j = nj; g.k = 0; g.found = 0; g.cond = inter; g.cond.has = 0;
+      continue;
+    }
+    if (n_res >= cap_res) { w.fail(Q_NEED_MORE); return false; }
+    POpt c = inter; c.pad = 0;
+    if (hb16_should_merge(left, ro.hb)) { c.has = 1; c.hb = merge_blocks16(left, ro.hb); } else { c.has = 0; c.hb = left; }
+    res[n_res++] = c;
+  }
+  return true;
+}
+XM_FN bool pyr_build_ambiguous(WS& w, MatePath& m) {
+  Pyr& P = m.pyr;
+  const int len = m.q.len;
+  // possibilities live at the bottom of the scratch stack for the whole query (ws_init calls this before anything marks it)
+  long long room = (w.scratch_size - w.scratch_top) / 4;
+  P.cap_opt = (int)(room / (long long)sizeof(POpt)); P.n_opt = 0;
+  if (P.cap_opt < 256) { w.fail(Q_NEED_MORE); return false; }
+  P.opt = (POpt*)w.salloc((long long)P.cap_opt * (long long)sizeof(POpt));
+  const int cap_res = 160, cap_stack = 96;
+  POpt* res = (POpt*)w.salloc((long long)cap_res * (long long)sizeof(POpt));
+  PExpandFrame* stack = (PExpandFrame*)w.salloc((long long)cap_stack * (long long)sizeof(PExpandFrame));
+  if (w.status != 0) return false;
+  int n_amb = 0;
+  XM_NOUNROLL
+  for (int k = 0; k < len; k++) {  // HashBlock_BaseRow.get :27-59
+    const uint8_t code = m.q.at(k);
+    P.child[k] = -1; P.up[k] = -1;
+    if (!bp_is_ambiguous(code)) { P.blk[k] = base_block16(code, k); continue; }
+    if (n_amb >= 64) { w.fail(Q_AMBIGUOUS_QUERY); return false; }  // more than 64 ambiguous bases in one query
+    HB16 e; e.start = (int16_t)k; e.len = 1; e.fwd = P.n_opt; e.rev = 0; e.flags = HB_MULTI; e.gap_dir = 0; e.extra = 0;
+    XM_NOUNROLL
+    for (int o = 0; o < 4; o++) {
+      const uint8_t base = (uint8_t)(1 << o);
+      if (!bp_can_match(code, base)) continue;
+      if (P.n_opt >= P.cap_opt) { w.fail(Q_NEED_MORE); return false; }
+      POpt c; c.hb = base_block16(base, k); c.has = 1; c.pad = 0; c.mask = 1ull << n_amb; c.v0 = 0; c.v1 = 0;
+      if (n_amb < 32) c.v0 = (unsigned long long)o << (2 * n_amb); else c.v1 = (unsigned long long)o << (2 * (n_amb - 32));
+      P.opt[P.n_opt++] = c; e.rev++;
+    }
+    P.blk[k] = e;
+    n_amb++;
+  }
+  P.level_off[0] = 0; P.level_off[1] = len; P.n_levels = 1;
+  int prev_off = 0, n_prev = len, level = 1;
+  XM_NOUNROLL
+  while (n_prev >= 2) {  // HashBlock_ParentRow.maybeMakeBlock :69-127 for every block of the row below
+    if (level >= P.cap_levels) { w.fail(Q_NEED_MORE); return false; }
+    const int cur_off = prev_off + n_prev;
+    const HB16* prev = P.blk + prev_off;
+    int n_new = 0;
+    XM_NOUNROLL
+    for (int i = 0; i < n_prev - 1; i++) {
+      const HB16 L = prev[i], R = prev[i + 1];
+      HB16 made; bool keep = false;
+      if (!((L.flags | R.flags) & HB_MULTI)) { keep = hb16_should_merge(L, R); if (keep) made = merge_blocks16(L, R); }
+      else {
+        int n_res = 0;
+        const int n_left = pyr_num_opts(L);
+        XM_NOUNROLL
+        for (int a = 0; a < n_left; a++) {
+          const POpt lo = pyr_opt(P, L, a);
+          if (lo.has) { if (!pyr_expand(w, P, prev, n_prev, lo.hb, lo, i, res, n_res, cap_res, stack, cap_stack)) return false; }
+          else { if (n_res >= cap_res) { w.fail(Q_NEED_MORE); return false; } res[n_res] = lo; res[n_res].has = 0; n_res++; }
+        }
+        bool any = false;
+        for (int a = 0; a < n_res; a++) any |= res[a].has != 0;
+        if (n_res > 0 && n_res <= 64 && any) {
+          if (P.n_opt + n_res > P.cap_opt) { w.fail(Q_NEED_MORE); return false; }
+          made.start = L.start; made.len = 0; made.fwd = P.n_opt; made.rev = n_res; made.flags = HB_MULTI; made.gap_dir = 0; made.extra = 0;
+          for (int a = 0; a < n_res; a++) P.opt[P.n_opt++] = res[a];
+          keep = true;
+        }
+      }
+      if (keep) {
+        if (cur_off + n_new + 1 > P.cap_blocks) { w.fail(Q_NEED_MORE); return false; }
+        P.blk[cur_off + n_new] = made; P.child[cur_off + n_new] = (int16_t)i; P.up[cur_off + n_new] = -1;
+        P.up[prev_off + i] = (int16_t)n_new;
+        n_new++;
+      } else P.up[prev_off + i] = -1;
+    }
+    if (n_new == 0) break;
+    P.level_off[level + 1] = cur_off + n_new; P.n_levels = level + 1;
+    prev_off = cur_off; n_prev = n_new; level++;
+  }
+  return true;
+}
 XM_FN bool pyr_build(WS& w, MatePath& m) {
   Pyr& P = m.pyr;
   const int len = m.q.len;
@@ -322,8 +466,8 @@ XM_FN bool pyr_build(WS& w, MatePath& m) {
   }
 #endif
   P.level_off[0] = 0; P.level_off[1] = len; P.n_levels = 1;
-  // IUPAC-ambiguous query bases need MultiHashBlocks (HashBlock_ParentRow.java:97-120), which the device does not build
-  if (amb) { w.fail(Q_AMBIGUOUS_QUERY); return false; }
+  P.opt = nullptr; P.n_opt = 0; P.cap_opt = 0;
+  if (amb) return pyr_build_ambiguous(w, m);  // IUPAC-ambiguous query bases: MultiHashBlocks, scalar build
   int prev_off = 0, n_prev = len, level = 1;
   XM_NOUNROLL
   while (n_prev >= 2) {
@@ -450,7 +594,7 @@ XM_HD inline int path_max_allowed(WS& w, MatePath& m, const HB& b) {  // :205-21
   if (b.rmr()) return 5;
   return b.used + 1;
 }
-XM_HD inline bool path_advance(WS& w, MatePath& m) {  // advanceToNextPosition :143-195 (multi-blocks cannot occur: ambiguous queries are rejected)
+XM_HD inline bool path_advance(WS& w, MatePath& m) {  // advanceToNextPosition :143-195 
   const HB single = m.cur;
   if (max_gapmer_used(single.len) < w.ix->min_interesting && w.ix->gapmers) path_move_up_or_right(w, m);
   else {
@@ -465,6 +609,10 @@ XM_HD inline bool path_advance(WS& w, MatePath& m) {  // advanceToNextPosition :
       if (typical <= w.ix->min_interesting && w.ix->gapmers) path_move_up_or_right(w, m);
       else { if (m.batch_index > 0) path_move_down(w, m); else path_move_right(w, m); }
     }
+  }
+  XM_NOUNROLL
+  while (m.cur_valid && (m.cur.flags & HB_MULTI)) {  // skipMultiblocks :130-140
+    if (m.batch_index > 0) path_move_down(w, m); else path_move_right(w, m);
   }
   return m.cur_valid && w.status == 0;
 }

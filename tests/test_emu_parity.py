@@ -31,8 +31,6 @@ def run_both(oracle_db, params, batch, window, max_used, upload_index=True, uplo
 
 @pytest.mark.parametrize("case", V["api_cases"], ids=[c["name"] for c in V["api_cases"]])
 def test_junit_api_cases(case):
-    if any(ch not in "ACGT" for s in case["seqs"] for ch in s):
-        pytest.skip("ambiguous query")
     db = xo.Oracle([("reference-0", case["reference"])], dup=dict(min_copies=2, window=1))
     batch = parity.batch_from_texts([case["seqs"]], [case["expected_inner"]], [case["per_penalty"]])
     max_used = max(len(s) for s in case["seqs"]) + 2
@@ -76,3 +74,37 @@ def test_library_index_builder_matches_host_tables():
     for c in range(db.num_contigs()):
         assert np.array_equal(db.dup_starts(c), emu.get_duplications(c)), c
     emu.close()
+
+
+def ambiguate(batch, seed, rate, codes=(15, 15, 15, 5, 10, 3, 12, 7)):
+    """Replaces a fraction of the query bases by IUPAC-ambiguous codes that still contain the original base (N mostly, some
+    two- and three-base codes), in the QV 4-bit packing the batch carries."""
+    rng = np.random.default_rng(seed)
+    packed = batch["packed"].copy()
+    off = batch["seq_word_off"]
+    for s, ln in enumerate(batch["seq_len"]):
+        k = rng.binomial(int(ln), rate)
+        if s % 7 == 0:
+            k += 2  # some reads with several, including adjacent ones
+        for pos in rng.integers(0, int(ln), size=k).tolist() + ([1, 2] if s % 7 == 0 and ln > 3 else []):
+            wi = int(off[s]) + (pos >> 2)
+            sh = (pos & 3) << 2
+            old = (int(packed[wi]) >> sh) & 15
+            code = int(codes[int(rng.integers(0, len(codes)))]) | old
+            packed[wi] = np.uint16((int(packed[wi]) & ~(15 << sh)) | (code << sh))
+    out = dict(batch)
+    out["packed"] = packed
+    return out
+
+
+@pytest.mark.parametrize("paired", [False, True], ids=["single", "paired"])
+def test_reads_with_ambiguous_bases(paired):
+    """IUPAC-ambiguous QUERY bases: MultiHashBlocks in the query pyramid (M/HashBlock_ParentRow.java:69-191), stepped past by the
+    seed walk (M/HashBlockPath.java:130-140), scored with the ambiguity penalty (M/AlignmentParameters.java:156-180)."""
+    ref = synth.random_reference(200000, seed=31, n_contigs=2, repeat_fraction=0.05, repeat_len=(200, 1000))
+    db = xo.Oracle([(n, synth.codes_to_text(s)) for n, s in ref], sort_by_length=True, dup=dict(min_copies=2, window=1000))
+    contigs = [db.contig(i) for i in range(db.num_contigs())]
+    batch = ambiguate(synth.simulate_reads(contigs, 1500, 120, seed=32 + paired, sub_rate=0.01, indel_rate=0.002, paired=paired), 33, 0.01)
+    a, b = run_both(db, synth.DEFAULT_PARAMS, batch, 1000, 120)
+    assert (b["q_status"] == 0).all()
+    parity.assert_same_results(a, b, "ambiguous reads %s" % ("paired" if paired else "single"))

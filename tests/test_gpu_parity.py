@@ -28,8 +28,6 @@ def test_junit_api_cases_on_gpu():
     """Every Api.alignOnce case of the reference's AlignerWorker_Test (host uploads its tables, as the Java host would)."""
     ran = 0
     for case in V["api_cases"]:
-        if any(ch not in "ACGT" for s in case["seqs"] for ch in s):
-            continue
         db = xo.Oracle([("reference-0", case["reference"])], dup=dict(min_copies=2, window=1))
         batch = parity.batch_from_texts([case["seqs"]], [case["expected_inner"]], [case["per_penalty"]])
         g = gpu_from_oracle(db, case["params"], max(len(s) for s in case["seqs"]) + 2, 1, True, True)
@@ -150,4 +148,19 @@ def test_depth_planes_vs_counts_oracle(paired):
         assert np.array_equal(have, want[c]), "contig %d" % c
         total += int(have.sum())
     assert total > 0
+    g.close()
+
+
+@pytest.mark.parametrize("paired", [False, True], ids=["single", "paired"])
+def test_reads_with_ambiguous_bases(paired):
+    """IUPAC-ambiguous QUERY bases (MultiHashBlocks, M/HashBlock_ParentRow.java:69-191; skipMultiblocks, M/HashBlockPath.java:130-140)."""
+    from test_emu_parity import ambiguate
+    ref = synth.random_reference(300000, seed=131, n_contigs=2, repeat_fraction=0.05, repeat_len=(200, 1000))
+    db = xo.Oracle([(n, synth.codes_to_text(s)) for n, s in ref], sort_by_length=True, dup=dict(min_copies=2, window=1000))
+    contigs = [db.contig(i) for i in range(db.num_contigs())]
+    batch = ambiguate(synth.simulate_reads(contigs, 8000, 150, seed=132 + paired, sub_rate=0.01, indel_rate=0.002, paired=paired), 133, 0.01)
+    g = gpu_from_oracle(db, synth.DEFAULT_PARAMS, 150, 1000, False, False)
+    got = g.align_batch(batch, strict=True)
+    want = db.align_batch(synth.DEFAULT_PARAMS, batch, threads=8)
+    parity.assert_same_results(want, got, "ambiguous reads paired=%s" % paired)
     g.close()
