@@ -45,6 +45,7 @@ struct LaunchD {
   int32_t* out_full; int* n_out_full;     // queries to re-run after growing the result arena
   char* arenas; long long arena_bytes;
   int last_tier;
+  int exp_groups;                         // experiment: distinct query streams per block (XM_EXP_GROUPS, default 1)
   int exp_dup;                            // experiment (XM_EXP_DUP=n): every warp of a block aligns the same n queries, results discarded by overwrite
   long long* q_cycles;                    // optional per-query cost probe (XM_QCYCLES=1): clock64 ticks of the tier that finished it
 };
@@ -72,7 +73,8 @@ __global__ void __launch_bounds__(EASY ? XM_BLOCK : XM_FULL_BLOCK, EASY ? XM_MIN
     int t = 0;
     if (L.exp_dup > 0) {
       if (dup_i >= L.exp_dup) break;
-      t = (int)(((long long)blockIdx.x * L.exp_dup + dup_i) % L.n_ids);
+      // exp_groups distinct query streams per block: warps with the same (warp % groups) align the same queries
+      t = (int)((((long long)blockIdx.x * L.exp_groups + (warp_in_block % L.exp_groups)) * L.exp_dup + dup_i) % L.n_ids);
       dup_i++;
     } else {
       if (lane == 0) t = atomicAdd(L.ticket, 1);
@@ -576,7 +578,8 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
       L.need_more_key = nullptr;
       if (tier < 0 && h->sort_hard) { if (!h->d_keys_a.ensure((size_t)n_ids * 4) || !h->d_keys_b.ensure((size_t)n_ids * 4)) { h->err = "out of device memory"; return XM_ERR_CUDA; } L.need_more_key = (int32_t*)h->d_keys_a.p; }
       L.exp_dup = 0;
-      if (tier >= 0) { if (const char* e = getenv("XM_EXP_DUP")) L.exp_dup = atoi(e); }
+      L.exp_groups = 1;
+      if (tier >= 0) { if (const char* e = getenv("XM_EXP_DUP")) L.exp_dup = atoi(e); if (const char* e = getenv("XM_EXP_GROUPS")) L.exp_groups = atoi(e) > 0 ? atoi(e) : 1; }
       bool time_it = (round == 0 && tier == -1);
       CK(cudaEventRecord(h->ev2, st));
       if (tier < 0) xm_align_kernel<true><<<blocks, block, 0, st>>>(L);

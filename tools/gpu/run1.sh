@@ -1,3 +1,2 @@
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/s14_pytest.log 2>&1; tail -3 gpurun_out/s14_pytest.log
-timeout 600 python bench.py --no-cpu-baseline > gpurun_out/s14_bench.json 2> gpurun_out/s14_bench.err; tail -3 gpurun_out/s14_bench.err; python -c "
-import json;d=json.load(open('gpurun_out/s14_bench.json'));print({k:d[k] for k in ['value','ms_per_step','e2e','gpu_launches','first_pass','full_pass']})"
+echo "== unrolled"; XM_LIB_PATH=$PWD/mapper_b200/libxm_unroll.so timeout 300 python tools/probe_qcycles.py --reads 1000000 2>&1 | sed -n 1,4p | cut -c1-220
+echo "== default"; timeout 300 python tools/probe_qcycles.py --reads 1000000 2>&1 | sed -n 1,4p | cut -c1-220
