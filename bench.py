@@ -319,6 +319,9 @@ def main():
             n_sample = min(a.reads, a.cpu_sample)
             run, _ = cpu_arm(a, ref, batch, n_sample, cores)
             dt, rc = run()
+            # the oracle's results for the sample double as a parity check of this run's device results (bit for bit, doubles included)
+            line["parity"] = dict(reads=n_sample, identical_to_oracle=bool(same_prefix(rc, r, n_sample)),
+                                  note="all eleven result arrays of the first `reads` queries of rank 0 compared with the CPU oracle")
             line["cpu_baseline"] = dict(value=n_sample / dt, unit=UNIT, cores=cores, kind="port",
                                         sample="%d reads of the same workload, %.1f s on %d threads; C++ restatement of mathjeff/Mapper @ ae7f346a (no JVM available)" % (n_sample, dt, cores))
         _emit(line)
@@ -327,6 +330,20 @@ def main():
         dist.destroy_process_group()
     g.close()
     return 0
+
+
+def same_prefix(want, got, n):
+    """True if the result arrays of the first n queries of `got` equal `want` (a result for exactly those n queries) bit for bit."""
+    c = int(got["q_comp_off"][n]); ch = int(got["comp_choice_off"][c]); sa = int(got["choice_sa_off"][ch]); bl = int(got["sa_block_off"][sa])
+    sizes = dict(q_comp_off=n + 1, comp_choice_off=c + 1, choice_sa_off=ch + 1, sa_block_off=sa + 1, choice_f64=4 * ch, sa_f64=2 * sa,
+                 choice_inner=ch, sa_contig=sa, blocks=4 * bl, q_status=n, sa_reversed=sa)
+    for k, m in sizes.items():
+        x, y = np.ascontiguousarray(want[k]), np.ascontiguousarray(got[k][:m])
+        if x.dtype != y.dtype:
+            x = x.astype(y.dtype)
+        if len(x) != m or x.tobytes() != y.tobytes():
+            return False
+    return True
 
 
 def _emit(line):
