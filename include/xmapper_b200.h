@@ -147,6 +147,16 @@ enum xm_stat {
 int64_t xm_results_array(const xm_results* r, int which, const void** ptr);
 void xm_release_results(xm_results* r);
 
+/* SAM bodies of the batch `r` came from, formatted on the device from its result arrays and the packed reads of the batch
+ * (replaces QV/SamWriter.java:118-352 formatQueryAlignments/formatQueryAlignment/getSamFlags/getMappingQuality/formatNumber:
+ * one line per sequence alignment, in query order; header lines and the file writer stay with the host).
+ * Must be called before the next xm_align_batch on the handle (the device copy of the results is reused by it).
+ * seq_names: the names of all sequences of the batch back to back (Sequence.getSourceName()), seq_name_off[n_sequences + 1];
+ * contig_names / contig_name_off[n_contigs + 1]: Sequence.getName() of the contigs in xm_set_reference order.
+ * *text stays valid until xm_release_results(r) or the next xm_format_sam on r. */
+int xm_format_sam(xm_handle* h, xm_results* r, const char* seq_names, const int64_t* seq_name_off, const char* contig_names, const int64_t* contig_name_off,
+                  const char** text, int64_t* n_bytes);
+
 /* Per-position count planes for --out-vcf/--out-mutations (QV/MatchDatabase.java:16-59, QV/Alignments.java:89-150,
  * QV/DirectionalAlignments.java:20-55): reference-base depth in int32 units of 1/100 per
  * [region: 0 middle, 1 end][direction: 0 forward, 1 reverse][position].  xm_counts_enable allocates the planes on

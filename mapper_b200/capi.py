@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("XM_LIB_PATH") or os.path.join(HERE, "libxmapper_b200.
 EXPORTS = ["xm_create", "xm_destroy", "xm_last_error", "xm_set_reference", "xm_set_index_length", "xm_finish_index",
            "xm_build_index", "xm_get_index_length", "xm_index_info", "xm_set_duplications", "xm_build_duplications",
            "xm_get_duplications", "xm_align_batch", "xm_align_batch_device", "xm_results_array", "xm_release_results",
-           "xm_counts_enable", "xm_counts_device_ptr", "xm_counts_fetch"]
+           "xm_counts_enable", "xm_counts_device_ptr", "xm_counts_fetch", "xm_format_sam"]
 
 RESULT_ARRAYS = [("q_comp_off", np.int64), ("comp_choice_off", np.int64), ("choice_sa_off", np.int64), ("sa_block_off", np.int64),
                  ("choice_f64", np.float64), ("sa_f64", np.float64), ("choice_inner", np.int32), ("sa_contig", np.int32),
@@ -195,6 +195,33 @@ class XMapper:
                                    _ptr(batch["expected_inner"]), _ptr(batch["per_penalty"]), C.byref(r))
         self._ok(rc, allow=() if strict else (-4,))
         return self._take(r, copy)
+
+    def align_batch_sam(self, batch, seq_names, contig_names, strict=False):
+        """Aligns a host batch and returns (results, SAM text): the text is formatted on the device (xm_format_sam) from the result
+        arrays while they are still resident.  seq_names: one name per sequence (mate) of the batch; contig_names: xm_set_reference order."""
+        nq = len(batch["n_seqs"])
+        r = C.c_void_p()
+        rc = self.L.xm_align_batch(self.h, nq, _ptr(batch["packed"]), _ptr(batch["seq_word_off"]), _ptr(batch["seq_len"]), _ptr(batch["n_seqs"]),
+                                   _ptr(batch["expected_inner"]), _ptr(batch["per_penalty"]), C.byref(r))
+        self._ok(rc, allow=() if strict else (-4,))
+        try:
+            sam = self.format_sam(r, seq_names, contig_names)
+        finally:
+            out = self._take(r, True)
+        return out, sam
+
+    def format_sam(self, r, seq_names, contig_names):
+        def blob(names):
+            enc = [n.encode() for n in names]
+            off = np.zeros(len(enc) + 1, dtype=np.int64)
+            if enc:
+                off[1:] = np.cumsum([len(e) for e in enc])
+            return b"".join(enc) + b"\0", off
+        sb, so = blob(seq_names)
+        cb, co = blob(contig_names)
+        text, n = C.c_char_p(), C.c_int64()
+        self._ok(self.L.xm_format_sam(self.h, r, sb, _ptr(so), cb, _ptr(co), C.byref(text), C.byref(n)))
+        return C.string_at(text, n.value).decode()
 
     def align_batch_device(self, nq, d_packed, n_words, d_seq_word_off, d_seq_len, d_n_seqs, d_expected, d_per, max_seq_len, strict=False, copy=True):
         """All arguments are device pointers (ints) on this handle's GPU."""

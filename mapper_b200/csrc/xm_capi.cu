@@ -202,6 +202,147 @@ __global__ void xm_csr_fill_kernel(OutArena out, int nq, const long long* base, 
   c.q_comp_off[q + 1] = i_comp;
 }
 
+// ---- SAM bodies on the device (QV/SamWriter.java:118-352) ----
+// One thread per query walks its records in the reference's order (components, choices, sequence alignments) twice:
+// xm_sam_kernel<false> measures the text, an exclusive scan places the queries, xm_sam_kernel<true> writes it.
+struct SamD {
+  CsrD c;                                   // the result CSR of the batch, still resident from xm_align_batch
+  const char* seq_names; const int64_t* seq_name_off;        // one name per SEQUENCE (mate)
+  const char* contig_names; const int64_t* contig_name_off;
+  long long* q_len;                         // per query: bytes of text (count pass), then exclusive offsets
+  char* text;
+};
+struct SamOut {
+  char* p; long long n;
+  __device__ __forceinline__ void ch(char c) { if (p) p[n] = c; n++; }
+  __device__ void str(const char* s, long long len) { for (long long i = 0; i < len; i++) ch(s[i]); }
+  __device__ void lit(const char* s) { while (*s) ch(*s++); }
+  __device__ void num(long long v) {  // "" + int
+    if (v < 0) { ch('-'); v = -v; }
+    char d[20]; int k = 0;
+    do { d[k++] = (char)('0' + (int)(v % 10)); v /= 10; } while (v);
+    while (k) ch(d[--k]);
+  }
+  // Java Float.toString of a finite float: shortest digits that identify it; decimal form for 1e-3 <= |v| < 1e7, else d.dddE<n>
+  __device__ void jfloat(float v) {
+    if (v == 0.0f) { if (signbit(v)) ch('-'); lit("0.0"); return; }
+    if (v < 0) { ch('-'); v = -v; }
+    const double s = (double)v;
+    // powers of ten are exact doubles up to 1e22; negative exponents divide by the exact power instead of multiplying by an inexact one
+    auto p10 = [](int k) { double r = 1.0; for (int i = 0; i < k; i++) r *= 10.0; return r; };
+    auto scale = [&](double x, int ex) { return ex >= 0 ? x * p10(ex) : x / p10(-ex); };  // x * 10^ex
+    int e10 = (int)floor(log10(s));
+    if (scale(1.0, e10) > s) e10--;
+    if (scale(1.0, e10 + 1) <= s) e10++;
+    unsigned long long D = 0; int p = 1;
+    for (p = 1; p <= 9; p++) {
+      const int ex = e10 - p + 1;               // candidate = D * 10^ex with p digits
+      D = (unsigned long long)rint(scale(s, -ex));
+      if ((float)scale((double)D, ex) == v) break;
+    }
+    if (p > 9) p = 9;
+    { unsigned long long lim = 1; for (int i = 0; i < p; i++) lim *= 10; if (D >= lim) { D /= 10; e10++; } }  // rounding carried into a new digit
+    while (p > 1 && D % 10 == 0) { D /= 10; p--; }
+    char dg[12];
+    { unsigned long long t = D; for (int i = p - 1; i >= 0; i--) { dg[i] = (char)('0' + (int)(t % 10)); t /= 10; } }
+    if (s >= 1e-3 && s < 1e7) {
+      if (e10 >= 0) {
+        for (int i = 0; i <= e10; i++) ch(i < p ? dg[i] : '0');
+        ch('.');
+        if (p > e10 + 1) { for (int i = e10 + 1; i < p; i++) ch(dg[i]); } else ch('0');
+      } else {
+        lit("0.");
+        for (int i = 0; i < -e10 - 1; i++) ch('0');
+        for (int i = 0; i < p; i++) ch(dg[i]);
+      }
+    } else {
+      ch(dg[0]); ch('.');
+      if (p > 1) { for (int i = 1; i < p; i++) ch(dg[i]); } else ch('0');
+      ch('E'); num(e10);
+    }
+  }
+  __device__ void score(const char* tag, double penalty) {  // formatSequencePenalty / formatQueryPenalty / formatNumber :263-277
+    const float sc = (float)(-1 * penalty);
+    const double scaled = (double)sc * (double)10000.0f;
+    const long long r = (long long)floor(scaled + 0.5);        // Math.round(double)
+    const float rounded = (float)r / 10000.0f;                 // long / float -> float
+    lit(tag); lit("f:"); jfloat(rounded);
+  }
+};
+template <bool WRITE>
+__global__ void xm_sam_kernel(SamD S, BatchD batch, int nq) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  SamOut o; o.n = 0; o.p = WRITE ? S.text + S.q_len[q] : nullptr;
+  const CsrD& c = S.c;
+  const long long s0 = batch.first_seq[q];
+  const long long comp0 = c.q_comp_off[q], comp1 = c.q_comp_off[q + 1];
+  const int n_comp = (int)(comp1 - comp0);
+  int having = 0;                                  // getNumQueriesHavingAlignments :85-93
+  for (long long cc = comp0; cc < comp1; cc++) if (c.comp_choice_off[cc + 1] > c.comp_choice_off[cc]) having++;
+  for (long long cc = comp0; cc < comp1; cc++) {   // formatQueryAlignments :118-137
+    const int sub = (int)(cc - comp0);
+    const long long k0 = c.comp_choice_off[cc], k1 = c.comp_choice_off[cc + 1];
+    double min_pen = 2147483647.0;
+    for (long long k = k0; k < k1; k++) { const double pen = c.choice_f64[4 * k + 3]; if (pen < min_pen) min_pen = pen; }
+    for (long long k = k0; k < k1; k++) {
+      const double pen = c.choice_f64[4 * k + 3];
+      const bool has_min = (pen - min_pen) <= fabs(min_pen) / 100000;
+      const long long a0 = c.choice_sa_off[k], a1 = c.choice_sa_off[k + 1];
+      const int n_sa = (int)(a1 - a0);
+      const bool multi = n_sa > 1 || n_comp > 1;   // queryHadMultipleSequences :279-285
+      for (long long a = a0; a < a1; a++) {        // formatQueryAlignment :139-223
+        const int i = (int)(a - a0);
+        const int mate = (n_comp == 2) ? sub : i;
+        const long long sid = s0 + mate;
+        const int qlen = batch.seq_len[sid];
+        const bool rev = c.sa_reversed[a] != 0;
+        const long long other = (n_sa == 2) ? (a == a0 ? a0 + 1 : a0) : -1;  // getPaired :334-342
+        o.str(S.seq_names + S.seq_name_off[sid], S.seq_name_off[sid + 1] - S.seq_name_off[sid]); o.ch('\t');
+        int flags = 0;                             // getSamFlags :288-331
+        if (rev) flags += 16;
+        if (multi) {
+          flags += 1;
+          if (n_sa > 1) { flags += 2; if (other >= 0 && c.sa_reversed[other] != 0) flags += 32; }
+          if (!(n_sa > 1 || having > 1)) flags += 8;
+          const int seq_index = sub + i;
+          flags += (seq_index == 0) ? 64 : 128;
+        }
+        if (!has_min) flags += 256;
+        o.num(flags); o.ch('\t');
+        const int contig = c.sa_contig[a];
+        o.str(S.contig_names + S.contig_name_off[contig], S.contig_name_off[contig + 1] - S.contig_name_off[contig]); o.ch('\t');
+        const int32_t* blk = c.blocks + 4 * c.sa_block_off[a];
+        const int n_blk = (int)(c.sa_block_off[a + 1] - c.sa_block_off[a]);
+        o.num((long long)blk[1] + 1); o.ch('\t');  // POS :344-346
+        o.num(has_min ? 255 : 0); o.ch('\t');      // MAPQ :242-261
+        int consumed = 0;                          // CIGAR :166-190
+        for (int b = 0; b < n_blk; b++) {
+          const int as = blk[4 * b], al = blk[4 * b + 2], bl = blk[4 * b + 3];
+          if (as != consumed) { o.num(as); o.ch('S'); consumed = as; }  // (the reference throws if this happens after the first block)
+          if (al == bl) { o.num(al); o.ch('M'); } else if (al > bl) { o.num(al); o.ch('I'); } else { o.num(bl); o.ch('D'); }
+          consumed += al;
+        }
+        if (consumed < qlen) { o.num(qlen - consumed); o.ch('S'); }
+        o.ch('\t');
+        if (other >= 0) {
+          const int oc = c.sa_contig[other];
+          o.str(S.contig_names + S.contig_name_off[oc], S.contig_name_off[oc + 1] - S.contig_name_off[oc]); o.ch('\t');
+          o.num((long long)c.blocks[4 * c.sa_block_off[other] + 1] + 1); o.ch('\t');
+        } else o.lit("*\t0\t");
+        o.num(qlen); o.ch('\t');                   // TLEN (sic: the query length)
+        SeqView qv; qv.w = batch.packed + batch.seq_word_off[sid]; qv.len = qlen; qv.rc = rev ? 1 : 0; qv.bytes = nullptr; qv.b0 = 0; qv.bn = 0;
+        for (int t = 0; t < qlen; t++) o.ch("-ACMGRSVTWYHKDBN"[qv.at(t)]);  // SEQ: text of sequenceA (the reverse complement for reversed alignments)
+        o.lit("\t*\t");
+        if (multi) { o.score("cs:", pen); o.ch('\t'); }
+        o.score("AS:", c.sa_f64[2 * a]);
+        o.ch('\n');
+      }
+    }
+  }
+  if (!WRITE) S.q_len[q] = o.n;
+}
+
 // ---- per-position reference-base depth planes (QV/MatchDatabase.java:34-59, QV/Alignments.java:89-156,
 // QV/WeightedAlignment.java:19-28, QV/QueryAlignment.java:97-120,203-214, QV/DirectionalAlignments.java:20-28) ----
 // One thread per query; walks every sequence alignment of every choice and adds (int)(weight * 100) for each
@@ -308,6 +449,8 @@ struct PinnedPool {
 };
 struct xm_results {
   ResultsHost r;
+  uint64_t serial = 0; int nq = 0;           // which xm_align_batch of the handle produced it
+  std::vector<char> sam;                     // text of the latest xm_format_sam
   std::shared_ptr<PinnedPool> pool; void* slab = nullptr; size_t slab_cap = 0;
   ~xm_results() { if (slab && pool) pool->give(slab, slab_cap); }
 };
@@ -328,6 +471,8 @@ struct xm_handle {
   DevBuf d_packed, d_seq_word_off, d_seq_len, d_n_seqs, d_expected, d_per, d_first_seq, d_chunk;
   DevBuf d_q, d_choices, d_sas, d_blocks, d_misc, d_ids_a, d_ids_b, d_ids_full, d_ws, d_qcycles;
   DevBuf d_csr_cnt, d_csr_base, d_csr_tmp, d_csr_slab, d_keys_a, d_keys_b, d_sort_tmp;
+  DevBuf d_sam_len, d_sam_text, d_sam_names, d_sam_name_off, d_sam_cnames, d_sam_cname_off;
+  BatchD last_batch{}; uint64_t batch_serial = 0;   // what xm_format_sam reads: the batch and CSR slab of the latest xm_align_batch
   std::shared_ptr<PinnedPool> pinned = std::make_shared<PinnedPool>();
   bool probe_cycles = false, sort_hard = true;
   long long cap_choices = 0, cap_sas = 0, cap_blocks = 0;
@@ -420,7 +565,7 @@ void xm_destroy(xm_handle* h) {
   cudaSetDevice(h->device);
   DevBuf* bufs[] = {&h->d_words, &h->d_word_off, &h->d_len, &h->d_gstart, &h->d_tables, &h->d_dup_off, &h->d_dup_starts, &h->d_packed, &h->d_seq_word_off,
                     &h->d_seq_len, &h->d_n_seqs, &h->d_expected, &h->d_per, &h->d_first_seq, &h->d_chunk, &h->d_q, &h->d_choices, &h->d_sas, &h->d_blocks,
-                    &h->d_misc, &h->d_ids_a, &h->d_ids_b, &h->d_ids_full, &h->d_ws, &h->d_qcycles, &h->d_csr_cnt, &h->d_csr_base, &h->d_csr_tmp, &h->d_csr_slab, &h->d_keys_a, &h->d_keys_b, &h->d_sort_tmp, &h->d_planes, &h->d_contig_off};
+                    &h->d_misc, &h->d_ids_a, &h->d_ids_b, &h->d_ids_full, &h->d_ws, &h->d_qcycles, &h->d_csr_cnt, &h->d_csr_base, &h->d_csr_tmp, &h->d_csr_slab, &h->d_keys_a, &h->d_keys_b, &h->d_sort_tmp, &h->d_sam_len, &h->d_sam_text, &h->d_sam_names, &h->d_sam_name_off, &h->d_sam_cnames, &h->d_sam_cname_off, &h->d_planes, &h->d_contig_off};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : h->d_buckets) b.release();
   for (auto& b : h->d_positions) b.release();
@@ -676,6 +821,7 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
     CK(cudaMemcpyAsync(R->slab, d, slab_bytes, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     R->r.slab = (const char*)R->slab;
+    h->last_batch = L.batch; R->serial = ++h->batch_serial; R->nq = nq;
     R->r.stats[XM_STAT_D2H_BYTES] = (int64_t)(slab_bytes + sizeof(misc) + 32);
   }
   float ms = 0;
@@ -724,6 +870,56 @@ int xm_align_batch(xm_handle* h, int32_t nq, const uint16_t* packed4, const int6
                                  (const uint8_t*)h->d_n_seqs.p, (const double*)h->d_expected.p, (const double*)h->d_per.p, max_len, out);
   if (*out) (*out)->r.stats[XM_STAT_H2D_BYTES] = (int64_t)((size_t)n_words * 2 + ((size_t)n_seqs_total + 1) * 8 + (size_t)n_seqs_total * 4 + (size_t)nq * 17);
   return rc;
+}
+
+int xm_format_sam(xm_handle* h, xm_results* r, const char* seq_names, const int64_t* seq_name_off, const char* contig_names, const int64_t* contig_name_off,
+                  const char** text, int64_t* n_bytes) {
+  if (!h || !r || !seq_names || !seq_name_off || !contig_names || !contig_name_off || !text || !n_bytes) return XM_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  if (r->serial != h->batch_serial || r->r.slab == nullptr) { h->err = "xm_format_sam: the results are not those of the handle's latest xm_align_batch (their device copy is gone)"; return XM_ERR_STATE; }
+  const int nq = r->nq;
+  *text = ""; *n_bytes = 0;
+  if (nq == 0) return XM_OK;
+  cudaStream_t st = h->stream;
+  // number of sequences = first_seq[nq] on the device; the host passes name offsets for all of them
+  long long n_seq_total = 0;
+  CK(cudaMemcpy(&n_seq_total, h->last_batch.first_seq + nq, 8, cudaMemcpyDeviceToHost));
+  const int n_contigs = h->m.n_contigs;
+  const size_t names_bytes = (size_t)seq_name_off[n_seq_total], cnames_bytes = (size_t)contig_name_off[n_contigs];
+  if (!h->d_sam_names.ensure(names_bytes + 16) || !h->d_sam_name_off.ensure(((size_t)n_seq_total + 1) * 8) || !h->d_sam_cnames.ensure(cnames_bytes + 16) ||
+      !h->d_sam_cname_off.ensure(((size_t)n_contigs + 1) * 8) || !h->d_sam_len.ensure(((size_t)nq + 1) * 8)) { h->err = "out of device memory (sam)"; return XM_ERR_CUDA; }
+  CK(cudaMemcpyAsync(h->d_sam_names.p, seq_names, names_bytes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->d_sam_name_off.p, seq_name_off, ((size_t)n_seq_total + 1) * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->d_sam_cnames.p, contig_names, cnames_bytes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->d_sam_cname_off.p, contig_name_off, ((size_t)n_contigs + 1) * 8, cudaMemcpyHostToDevice, st));
+  SamD S;
+  char* d = (char*)h->d_csr_slab.p;
+  const int64_t* off = r->r.slab_off;
+  S.c.q_comp_off = (int64_t*)(d + off[0]); S.c.comp_choice_off = (int64_t*)(d + off[1]); S.c.choice_sa_off = (int64_t*)(d + off[2]); S.c.sa_block_off = (int64_t*)(d + off[3]);
+  S.c.choice_f64 = (double*)(d + off[4]); S.c.sa_f64 = (double*)(d + off[5]); S.c.choice_inner = (int32_t*)(d + off[6]); S.c.sa_contig = (int32_t*)(d + off[7]);
+  S.c.blocks = (int32_t*)(d + off[8]); S.c.q_status = (int32_t*)(d + off[9]); S.c.sa_reversed = (uint8_t*)(d + off[10]);
+  S.seq_names = (const char*)h->d_sam_names.p; S.seq_name_off = (const int64_t*)h->d_sam_name_off.p;
+  S.contig_names = (const char*)h->d_sam_cnames.p; S.contig_name_off = (const int64_t*)h->d_sam_cname_off.p;
+  S.q_len = (long long*)h->d_sam_len.p; S.text = nullptr;
+  CK(cudaMemsetAsync((char*)h->d_sam_len.p + (size_t)nq * 8, 0, 8, st));
+  xm_sam_kernel<false><<<(nq + 127) / 128, 128, 0, st>>>(S, h->last_batch, nq);
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, (const long long*)nullptr, (long long*)nullptr, nq + 1, st);
+  if (!h->d_csr_tmp.ensure(tb + 16)) { h->err = "out of device memory (sam)"; return XM_ERR_CUDA; }
+  CK(cub::DeviceScan::ExclusiveSum(h->d_csr_tmp.p, tb, (const long long*)S.q_len, S.q_len, nq + 1, st));
+  long long total = 0;
+  CK(cudaMemcpyAsync(&total, S.q_len + nq, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (!h->d_sam_text.ensure((size_t)total + 16)) { h->err = "out of device memory (sam text)"; return XM_ERR_CUDA; }
+  S.text = (char*)h->d_sam_text.p;
+  xm_sam_kernel<true><<<(nq + 127) / 128, 128, 0, st>>>(S, h->last_batch, nq);
+  CK(cudaGetLastError());
+  r->sam.resize((size_t)total + 1);
+  CK(cudaMemcpyAsync(r->sam.data(), S.text, (size_t)total, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  r->sam[(size_t)total] = 0;
+  *text = r->sam.data(); *n_bytes = total;
+  return XM_OK;
 }
 
 int64_t xm_results_array(const xm_results* r, int which, const void** ptr) { if (!r || !ptr) return -1; return r->r.array(which, ptr); }

@@ -83,6 +83,8 @@ def ambiguate(batch, seed, rate, codes=(15, 15, 15, 5, 10, 3, 12, 7)):
     packed = batch["packed"].copy()
     off = batch["seq_word_off"]
     for s, ln in enumerate(batch["seq_len"]):
+        if ln < 1:
+            continue
         k = rng.binomial(int(ln), rate)
         if s % 7 == 0:
             k += 2  # some reads with several, including adjacent ones

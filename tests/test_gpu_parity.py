@@ -164,3 +164,40 @@ def test_reads_with_ambiguous_bases(paired):
     want = db.align_batch(synth.DEFAULT_PARAMS, batch, threads=8)
     parity.assert_same_results(want, got, "ambiguous reads paired=%s" % paired)
     g.close()
+
+
+def test_sam_bodies_on_gpu():
+    """T/SamWriter_Test.java: the five exact SAM bodies, aligned AND formatted on the device (xm_format_sam)."""
+    for case in V["sam_cases"]:
+        db = xo.Oracle([(case["ref_name"], case["reference"])], sort_by_length=False, dup=case["dup"])
+        batch = parity.batch_from_texts([case["seqs"]], [case["expected_inner"]], [case["per_penalty"]])
+        g = gpu_from_oracle(db, case["params"], max(len(s) for s in case["seqs"]) + 2, 1, True, True)
+        _, sam = g.align_batch_sam(batch, case["names"], [case["ref_name"]], strict=True)
+        assert sam == case["expected_sam"], case["name"]
+        g.close()
+
+
+@pytest.mark.parametrize("paired", [False, True], ids=["single", "paired"])
+def test_sam_random_reads_vs_oracle(paired):
+    """Device SAM text == the Python restatement of QV/SamWriter.java (pinned by the JUnit bodies) on reads with substitutions,
+    indels, soft clips at contig ends, ambiguous bases, unaligned mates and multiple choices."""
+    import sam_oracle
+    from test_emu_parity import ambiguate
+    ref = synth.random_reference(120000, seed=141, n_contigs=3, repeat_fraction=0.1, repeat_len=(150, 600))
+    db = xo.Oracle([(n, synth.codes_to_text(s)) for n, s in ref], sort_by_length=True, dup=dict(min_copies=2, window=1000))
+    contigs = [db.contig(i) for i in range(db.num_contigs())]
+    batch = ambiguate(synth.simulate_reads(contigs, 4000, 100, seed=142 + paired, sub_rate=0.02, indel_rate=0.004, paired=paired, inner_mean=80.0, inner_sd=25.0), 143, 0.003)
+    assert batch["seq_len"].min() > 0
+    n_seqs = int(batch["n_seqs"].astype(np.int64).sum())
+    names = ["read%d/%d" % (i // (2 if paired else 1), i % 2 + 1) for i in range(n_seqs)]
+    cnames = [db.contig(i)[0] for i in range(db.num_contigs())]
+    g = gpu_from_oracle(db, synth.DEFAULT_PARAMS, 100, 1000, False, False)
+    got, sam = g.align_batch_sam(batch, names, cnames, strict=True)
+    want = sam_oracle.format_sam(got, batch, names, cnames)
+    assert len(sam) > 100000
+    if sam != want:
+        a, b = sam.split("\n"), want.split("\n")
+        for x, y in zip(a, b):
+            assert x == y
+    assert sam == want
+    g.close()

@@ -72,3 +72,26 @@ def test_paths_counter(case):
 @pytest.mark.parametrize("text", V["symmetry_cases"])
 def test_hash_symmetry(text):
     assert xo.hash_symmetry(text) > 0
+
+
+# ---- T/SamWriter_Test.java: exact SAM bodies (pins tests/sam_oracle.py, the checker of xm_format_sam) ----
+@pytest.mark.parametrize("case", V["sam_cases"], ids=[c["name"] for c in V["sam_cases"]])
+def test_sam_bodies(case):
+    import parity
+    import sam_oracle
+    db = xo.Oracle([(case["ref_name"], case["reference"])], sort_by_length=False, dup=case["dup"])
+    batch = parity.batch_from_texts([case["seqs"]], [case["expected_inner"]], [case["per_penalty"]])
+    r = db.align_batch(case["params"], batch)
+    assert sam_oracle.format_sam(r, batch, case["names"], [case["ref_name"]]) == case["expected_sam"]
+
+
+def test_java_float_formatting():
+    import sam_oracle
+    assert sam_oracle.format_number(0.0) == "f:0.0"
+    assert sam_oracle.format_number(1.5) == "f:-1.5"
+    assert sam_oracle.format_number(0.1 / 3) == "f:-0.0333"
+    assert sam_oracle.format_number(12.3456789) == "f:-12.3457"
+    assert sam_oracle.format_number(0.0001) == "f:-1.0E-4"
+    assert sam_oracle.format_number(1500.12341) == "f:-1500.1234"
+    assert sam_oracle.java_float_str(1.0e7) == "1.0E7"
+    assert sam_oracle.java_float_str(123456.7) == "123456.7"
