@@ -157,7 +157,7 @@ def main():
     g = capi.XMapper(synth.DEFAULT_PARAMS, device=local_rank)
     t0 = time.time()
     g.set_reference([synth.pack_contig(s) for _, s in ref], [len(s) for _, s in ref])
-    g.build_index(a.read_len, threads=max(1, cores // max(1, world)))
+    g.build_index(a.read_len)  # on the device
     g.build_duplications(-1, -1, 2, 1000)
     t_index = time.time() - t0
     if a.counts:

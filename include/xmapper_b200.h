@@ -77,6 +77,8 @@ int xm_finish_index(xm_handle* h, int32_t min_interesting_size, int32_t max_buil
 
 /* Alternative to the two calls above: build every table for numBasepairsUsed <= max_used from the uploaded
  * reference inside the library (HashBlock_Database.hashSequenceThroughSize/addHashblocks, :490-618).
+ * n_threads == 0: built on the device (pyramid + gapmer kernel over reference slices, radix sorts, PackedMap fill kernel);
+ * n_threads > 0: the library's host builder with that many threads (bit-identical tables; kept as the cross-check).
  * Unambiguous references only in this round (returns XM_ERR_ARG otherwise). */
 int xm_build_index(xm_handle* h, int32_t max_used, int32_t n_threads);
 /* Reads back a table (for parity tests against the host's PackedMaps). Pass NULL arrays to query sizes. */

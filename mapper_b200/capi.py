@@ -135,7 +135,8 @@ class XMapper:
         self._ok(self.L.xm_finish_index(self.h, int(min_interesting), int(max_built)))
 
     def build_index(self, max_used, threads=0):
-        self._ok(self.L.xm_build_index(self.h, int(max_used), int(threads or (os.cpu_count() or 1))))
+        """threads == 0: the device builder; threads > 0: the library's host builder (kept as its cross-check)."""
+        self._ok(self.L.xm_build_index(self.h, int(max_used), int(threads)))
 
     def index_info(self):
         a, b = C.c_int32(), C.c_int32()

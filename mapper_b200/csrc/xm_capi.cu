@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_run_length_encode.cuh>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -200,6 +201,169 @@ __global__ void xm_csr_fill_kernel(OutArena out, int nq, const long long* base, 
     c.comp_choice_off[i_comp] = i_ch;
   }
   c.q_comp_off[q + 1] = i_comp;
+}
+
+// ---- hash-block index built on the device (M/HashBlock_Database.java:490-665 + M/PackedMap.java:99-153 semantics) ----
+// xm_index_emit_kernel: one warp per reference slice builds the slice's hash-block pyramid level by level (lanes take 32
+//   block pairs per round, ballot compaction - the query pyramid's scheme) and, per level, emits (numBasepairsUsed, bucket,
+//   global position) for every block's gapmer in its primary and/or secondary polarity.
+// Two radix sorts order the entries by (used, bucket, position); a run-length pass yields the bucket counts; xm_index_runs /
+// xm_index_fill write the PackedMap words (offset | overfull | count, empty buckets carry the running offset) and compact
+// the positions of the buckets that are not overfull.  The tables are bit-identical to the host builder's.
+struct IndexBuildD {
+  RefD ref;
+  const int* slice_contig; const int* slice_start; int n_slices, slice_len;
+  int hi, min_interesting, gapmers;
+  const int* cap;                      // hi + 1 capacities
+  char* arenas; long long arena_bytes; // per warp: two level buffers
+  unsigned long long* keys; uint32_t* vals; unsigned long long cap_entries;
+  unsigned long long* n_entries; int* ticket;
+};
+__device__ __forceinline__ int32_t ext_hash_lane(const SeqView& seq, int from, int n, int dir, bool complement) {  // one block per LANE
+  int32_t h = 0;
+  for (int k = 0; k < n; k++) {
+    uint8_t c = seq.at(from + dir * k);
+    if (complement) c = bp_complement(c);
+    h = wadd(wmul(h, 7654337), ext_char_to_int(c));
+  }
+  return h;
+}
+__device__ __forceinline__ bool gapmer_lane(const HB& b, const SeqView& seq, HB& out) {  // HashBlock.withGapAndExtension :67-150
+  if (b.gap_dir == 0) { out = b; return true; }
+  int target = b.len + (jabs(b.fwd > b.rev ? b.fwd : b.rev) % 3) + b.extra;
+  int gap = b.len / 2;
+  int ext = target - gap;
+  int32_t h;
+  HB r;
+  if (b.gap_dir < 0) {
+    int ext_end = b.start - gap, ext_start = ext_end - ext;
+    if (ext_start < 0) return false;
+    h = ext_hash_lane(seq, ext_end - 1, ext, -1, false);
+    r.start = ext_start; r.len = ext + gap + b.len;
+  } else {
+    int ext_start = b.end() + gap, ext_end = ext_start + ext;
+    if (ext_end > seq.len) return false;
+    h = ext_hash_lane(seq, ext_start, ext, 1, true);
+    r.start = b.start; r.len = b.len + gap + ext;
+  }
+  r.fwd = wadd(b.fwd, h); r.rev = wadd(b.rev, h);
+  r.used = b.len + ext;
+  r.gap_dir = 0; r.flags = 0; r.extra = 0; r.ident = 0;
+  out = r;
+  return true;
+}
+__global__ void __launch_bounds__(128) xm_index_emit_kernel(IndexBuildD B) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int cap_lvl = B.slice_len + B.hi + 2 + 32;
+  HB16* buf0 = (HB16*)(B.arenas + warp * B.arena_bytes);
+  HB16* buf1 = buf0 + cap_lvl;
+  while (true) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(B.ticket, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= B.n_slices) break;
+    const int contig = B.slice_contig[t], s = B.slice_start[t];
+    const SeqView seq = B.ref.contig(contig, 0);
+    const int e = min(seq.len, s + B.slice_len);
+    const int ext_end = min(seq.len, e + B.hi + 2);
+    const long long g_fwd = B.ref.gstart[2 * contig], g_rev = B.ref.gstart[2 * contig + 1];
+    HB16* cur = buf0; HB16* nxt = buf1;
+    int n_cur = ext_end - s;
+    for (int k = lane; k < n_cur; k += 32) cur[k] = base_block16(seq.at(s + k), k);
+    __syncwarp();
+    while (n_cur > 0) {
+      bool any_short = false;
+      for (int base = 0; base < n_cur; base += 32) {
+        const int idx = base + lane;
+        HB16 c16; bool valid = false;
+        if (idx < n_cur) { c16 = cur[idx]; valid = (s + (int)c16.start) < e; }
+        if (__ballot_sync(0xffffffffu, valid) == 0) break;   // starts ascend: nothing further lies in the slice
+        bool prim = false, sec = false; HB g;
+        if (valid) {
+          if ((int)c16.len <= B.hi) {
+            any_short = true;
+            HB b; b.start = s + c16.start; b.len = c16.len; b.used = c16.len; b.fwd = c16.fwd; b.rev = c16.rev; b.gap_dir = c16.gap_dir; b.flags = c16.flags; b.extra = c16.extra; b.ident = 0;
+            bool ok = true;
+            if (B.gapmers) ok = gapmer_lane(b, seq, g); else g = b;
+            if (ok && g.used >= B.min_interesting && g.used <= B.hi) {
+              const bool rml = g.rml(), rmr = g.rmr();
+              prim = (rml != rmr) ? rml : (g.fwd >= g.rev);
+              sec = (rml != rmr) ? rmr : (g.fwd <= g.rev);   // HashBlock.isSecondaryPolarity :339-343
+            }
+          }
+        }
+        const unsigned pm = __ballot_sync(0xffffffffu, prim), sm = __ballot_sync(0xffffffffu, sec);
+        const int total = __popc(pm) + __popc(sm);
+        if (total) {
+          unsigned long long at = 0;
+          if (lane == 0) at = atomicAdd(B.n_entries, (unsigned long long)total);
+          at = __shfl_sync(0xffffffffu, at, 0);
+          if (B.keys != nullptr && at + total <= B.cap_entries) {
+            const int c = B.cap[(prim || sec) ? g.used : 0];
+            if (prim) { int r = g.fwd % c; if (r < 0) r += c; const unsigned long long o = at + __popc(pm & lt_mask); B.keys[o] = ((unsigned long long)g.used << 32) | (unsigned)r; B.vals[o] = (uint32_t)(g_fwd + g.start); }
+            if (sec) { int r = g.rev % c; if (r < 0) r += c; const unsigned long long o = at + __popc(pm) + __popc(sm & lt_mask); B.keys[o] = ((unsigned long long)g.used << 32) | (unsigned)r; B.vals[o] = (uint32_t)(g_rev + (seq.len - g.end())); }
+          }
+        }
+      }
+      if (!__any_sync(0xffffffffu, any_short)) break;
+      int n_new = 0;
+      __syncwarp();
+      for (int base = 0; base < n_cur - 1; base += 32) {
+        const int i = base + lane;
+        bool keep = false; HB16 L, R;
+        if (i < n_cur - 1) { L = cur[i]; R = cur[i + 1]; keep = ((int)L.start + (int)L.len >= (int)R.start) && ((L.flags & 2) || (R.flags & 1)); }
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        if (keep) nxt[n_new + __popc(mask & lt_mask)] = merge_blocks16(L, R);
+        n_new += __popc(mask);
+      }
+      __syncwarp();
+      HB16* tmp = cur; cur = nxt; nxt = tmp; n_cur = n_new;
+    }
+  }
+}
+// per run r of equal (used, bucket): kept[r] = count unless the bucket is overfull
+__global__ void xm_index_runs_kernel(const unsigned long long* run_key, const int* run_cnt, int n_runs, long long* kept) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > n_runs) return;
+  if (r == n_runs) { kept[r] = 0; return; }
+  const int n = (int)(run_key[r] >> 32);
+  int mx = n * n; if (mx < 5) mx = 5; if (mx > 32766) mx = 32766;
+  kept[r] = run_cnt[r] > mx ? 0 : run_cnt[r];
+}
+// first_run[n] = first run whose used >= n (n = 0 .. hi + 1)
+__global__ void xm_index_first_run_kernel(const unsigned long long* run_key, int n_runs, int hi, int* first_run) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n > hi + 1) return;
+  int lo = 0, h = n_runs;
+  while (lo < h) { int mid = (lo + h) >> 1; if ((int)(run_key[mid] >> 32) < n) lo = mid + 1; else h = mid; }
+  first_run[n] = lo;
+}
+struct IndexFillD {
+  const unsigned long long* run_key; const int* run_cnt; const long long* run_start; const long long* kept_off; int n_runs;
+  const int* first_run; const int* cap; const long long* bucket_base;   // per used: offset of its bucket words in `buckets`
+  const uint32_t* sorted_pos; unsigned long long* buckets; uint32_t* positions;  // positions: all lengths back to back, in kept_off order
+};
+__global__ void xm_index_fill_kernel(IndexFillD F) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= F.n_runs) return;
+  const int n = (int)(F.run_key[r] >> 32); const unsigned bucket = (unsigned)F.run_key[r];
+  const long long base_n = F.kept_off[F.first_run[n]];
+  const long long off = F.kept_off[r] - base_n;
+  const int cnt = F.run_cnt[r];
+  const bool over = (F.kept_off[r + 1] - F.kept_off[r]) == 0 && cnt > 0;
+  unsigned long long* bw = F.buckets + F.bucket_base[n];
+  // empty buckets between the previous run of this length and this one carry the running offset (= this run's offset)
+  unsigned first_empty = 0;
+  if (r > F.first_run[n]) first_empty = (unsigned)F.run_key[r - 1] + 1;
+  for (unsigned b = first_empty; b < bucket; b++) bw[b] = ((unsigned long long)off << 24);
+  bw[bucket] = ((unsigned long long)off << 24) | ((unsigned long long)(over ? 1 : 0) << 16) | (unsigned long long)(over ? 0 : (cnt & 0xFFFF));
+  if (r + 1 == F.first_run[n + 1]) {  // last run of this length: the tail of the table
+    const long long end_off = F.kept_off[r + 1] - base_n;
+    for (unsigned b = bucket + 1; b < (unsigned)F.cap[n]; b++) bw[b] = ((unsigned long long)end_off << 24);
+  }
+  if (!over) { const long long src = F.run_start[r], dst = F.kept_off[r]; for (int k = 0; k < cnt; k++) F.positions[dst + k] = F.sorted_pos[src + k]; }
 }
 
 // ---- SAM bodies on the device (QV/SamWriter.java:118-352) ----
@@ -595,9 +759,114 @@ int xm_finish_index(xm_handle* h, int32_t min_interesting, int32_t max_built) {
   h->m.finish_index(min_interesting, max_built);
   return XM_OK;
 }
+// xm_build_index(h, max_used, 0): the tables of M/HashBlock_Database.java built by the kernels above
+static int build_index_device(xm_handle* h, int max_used) {
+  HostModel& M = h->m;
+  int hi = 0; std::vector<int> cap;
+  if (!M.index_plan(max_used, hi, cap, h->err)) return XM_ERR_ARG;
+  if (hi > 16000) { h->err = "xm_build_index: lengths above 16000 are not supported by the device builder (16-bit block coordinates within a slice)"; return XM_ERR_ARG; }
+  int key_bits = 33; while ((1 << (key_bits - 32)) <= hi) key_bits++;   // sort key = used << 32 | bucket
+  cudaStream_t st = h->stream;
+  auto up = [&](DevBuf& b, const void* src, size_t bytes) -> bool { return b.ensure(bytes ? bytes : 16) && (!bytes || cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess); };
+  if (!up(h->d_words, M.words.data(), M.words.size() * 2) || !up(h->d_word_off, M.word_off.data(), M.word_off.size() * 8) ||
+      !up(h->d_len, M.len.data(), M.len.size() * 4) || !up(h->d_gstart, M.gstart.data(), M.gstart.size() * 8)) { h->err = "device upload failed (reference)"; return XM_ERR_CUDA; }
+  IndexBuildD B;
+  B.ref.n_contigs = M.n_contigs; B.ref.words = (const uint16_t*)h->d_words.p; B.ref.word_off = (const int64_t*)h->d_word_off.p;
+  B.ref.len = (const int32_t*)h->d_len.p; B.ref.gstart = (const int64_t*)h->d_gstart.p; B.ref.total_fr = M.total_fr;
+  const int slice_len = 8192;
+  std::vector<int> sc, ss;
+  for (int c = 0; c < M.n_contigs; c++) for (int s0 = 0; s0 < M.len[(size_t)c]; s0 += slice_len) { sc.push_back(c); ss.push_back(s0); }
+  DevBuf d_sc, d_ss, d_cap, d_cnt, d_keys_a, d_keys_b, d_vals_a, d_vals_b, d_tmp, d_run_key, d_run_cnt, d_nruns, d_cnt64, d_kept, d_first, d_bbase, d_buckets, d_pos;
+  struct Free { std::vector<DevBuf*> v; ~Free() { for (DevBuf* b : v) b->release(); } } fr;
+  fr.v = {&d_sc, &d_ss, &d_cap, &d_cnt, &d_keys_a, &d_keys_b, &d_vals_a, &d_vals_b, &d_tmp, &d_run_key, &d_run_cnt, &d_nruns, &d_cnt64, &d_kept, &d_first, &d_bbase, &d_buckets, &d_pos};
+  if (!up(d_sc, sc.data(), sc.size() * 4) || !up(d_ss, ss.data(), ss.size() * 4) || !up(d_cap, cap.data(), cap.size() * 4) || !d_cnt.ensure(64)) { h->err = "out of device memory (index build)"; return XM_ERR_CUDA; }
+  B.slice_contig = (const int*)d_sc.p; B.slice_start = (const int*)d_ss.p; B.n_slices = (int)sc.size(); B.slice_len = slice_len;
+  B.hi = hi; B.min_interesting = M.min_interesting; B.gapmers = M.gapmers; B.cap = (const int*)d_cap.p;
+  const int blocks = h->sm_count * 8, warps = blocks * 4;
+  B.arena_bytes = (((long long)(slice_len + hi + 2 + 32) * 2 * (long long)sizeof(HB16)) + 255) & ~255LL;
+  if (!h->d_ws.ensure((size_t)warps * (size_t)B.arena_bytes)) { h->err = "out of device memory (index build workspace)"; return XM_ERR_CUDA; }
+  B.arenas = (char*)h->d_ws.p;
+  B.n_entries = (unsigned long long*)d_cnt.p; B.ticket = (int*)((char*)d_cnt.p + 16);
+  // pass 1 counts the entries, pass 2 writes them
+  B.keys = nullptr; B.vals = nullptr; B.cap_entries = 0;
+  CK(cudaMemsetAsync(d_cnt.p, 0, 64, st));
+  xm_index_emit_kernel<<<blocks, 128, 0, st>>>(B);
+  unsigned long long E = 0;
+  CK(cudaMemcpyAsync(&E, d_cnt.p, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  M.tables.assign((size_t)hi + 1, HostTable());
+  if (E >= (1ull << 31)) { h->err = "xm_build_index: more than 2^31 index entries"; return XM_ERR_ARG; }
+  if (E > 0) {
+    if (!d_keys_a.ensure(E * 8) || !d_keys_b.ensure(E * 8) || !d_vals_a.ensure(E * 4) || !d_vals_b.ensure(E * 4)) { h->err = "out of device memory (index entries)"; return XM_ERR_CUDA; }
+    B.keys = (unsigned long long*)d_keys_a.p; B.vals = (uint32_t*)d_vals_a.p; B.cap_entries = E;
+    CK(cudaMemsetAsync(d_cnt.p, 0, 64, st));
+    xm_index_emit_kernel<<<blocks, 128, 0, st>>>(B);
+    CK(cudaGetLastError());
+    const int n = (int)E;
+    // (used, bucket, position) order: sort by position, then a stable sort by (used << 32 | bucket)
+    size_t t1 = 0, t2 = 0, t3 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, (const uint32_t*)d_vals_a.p, (uint32_t*)d_vals_b.p, (const unsigned long long*)d_keys_a.p, (unsigned long long*)d_keys_b.p, n, 0, 32, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, t2, (const unsigned long long*)d_keys_b.p, (unsigned long long*)d_keys_a.p, (const uint32_t*)d_vals_b.p, (uint32_t*)d_vals_a.p, n, 0, key_bits, st);
+    if (!d_run_key.ensure(E * 8) || !d_run_cnt.ensure(E * 4) || !d_nruns.ensure(16)) { h->err = "out of device memory (index runs)"; return XM_ERR_CUDA; }
+    cub::DeviceRunLengthEncode::Encode(nullptr, t3, (const unsigned long long*)d_keys_a.p, (unsigned long long*)d_run_key.p, (int*)d_run_cnt.p, (int*)d_nruns.p, n, st);
+    size_t tb = t1 > t2 ? t1 : t2; if (t3 > tb) tb = t3;
+    if (!d_tmp.ensure(tb + (size_t)E * 8 + 4096)) { h->err = "out of device memory (index sort)"; return XM_ERR_CUDA; }
+    size_t q = tb;
+    CK(cub::DeviceRadixSort::SortPairs(d_tmp.p, q, (const uint32_t*)d_vals_a.p, (uint32_t*)d_vals_b.p, (const unsigned long long*)d_keys_a.p, (unsigned long long*)d_keys_b.p, n, 0, 32, st));
+    q = tb;
+    CK(cub::DeviceRadixSort::SortPairs(d_tmp.p, q, (const unsigned long long*)d_keys_b.p, (unsigned long long*)d_keys_a.p, (const uint32_t*)d_vals_b.p, (uint32_t*)d_vals_a.p, n, 0, key_bits, st));
+    q = tb;
+    CK(cub::DeviceRunLengthEncode::Encode(d_tmp.p, q, (const unsigned long long*)d_keys_a.p, (unsigned long long*)d_run_key.p, (int*)d_run_cnt.p, (int*)d_nruns.p, n, st));
+    int n_runs = 0;
+    CK(cudaMemcpyAsync(&n_runs, d_nruns.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // offsets: run_start = scan of counts, kept_off = scan of the counts of the buckets that are not overfull
+    if (!d_cnt64.ensure(((size_t)n_runs + 1) * 16) || !d_kept.ensure(((size_t)n_runs + 1) * 16) || !d_first.ensure(((size_t)hi + 2) * 4)) { h->err = "out of device memory (index offsets)"; return XM_ERR_CUDA; }
+    long long* kept = (long long*)d_kept.p; long long* kept_off = kept + (n_runs + 1);
+    long long* cnt64 = (long long*)d_cnt64.p; long long* run_start = cnt64 + (n_runs + 1);
+    xm_index_runs_kernel<<<(n_runs + 256) / 256, 256, 0, st>>>((const unsigned long long*)d_run_key.p, (const int*)d_run_cnt.p, n_runs, kept);
+    CK(cudaMemsetAsync(cnt64, 0, ((size_t)n_runs + 1) * 8, st));  // widen the int32 counts to int64 for the scan
+    CK(cudaMemcpy2DAsync(cnt64, 8, d_run_cnt.p, 4, 4, (size_t)n_runs, cudaMemcpyDeviceToDevice, st));
+    q = tb; CK(cub::DeviceScan::ExclusiveSum(d_tmp.p, q, (const long long*)kept, kept_off, n_runs + 1, st));
+    q = tb; CK(cub::DeviceScan::ExclusiveSum(d_tmp.p, q, (const long long*)cnt64, run_start, n_runs + 1, st));
+    xm_index_first_run_kernel<<<(hi + 2 + 255) / 256, 256, 0, st>>>((const unsigned long long*)d_run_key.p, n_runs, hi, (int*)d_first.p);
+    std::vector<int> first((size_t)hi + 2);
+    CK(cudaMemcpyAsync(first.data(), d_first.p, first.size() * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::vector<long long> koff((size_t)hi + 2);
+    for (int k = 0; k <= hi + 1; k++) CK(cudaMemcpy(&koff[(size_t)k], kept_off + first[(size_t)k], 8, cudaMemcpyDeviceToHost));
+    std::vector<long long> bbase((size_t)hi + 2, 0);
+    long long words = 0;
+    for (int k = 0; k <= hi; k++) { bbase[(size_t)k] = words; if (first[(size_t)k + 1] > first[(size_t)k]) words += cap[(size_t)k]; }
+    const long long n_pos = koff[(size_t)hi + 1];
+    if (!up(d_bbase, bbase.data(), bbase.size() * 8) || !d_buckets.ensure((size_t)words * 8 + 16) || !d_pos.ensure((size_t)n_pos * 4 + 16)) { h->err = "out of device memory (index tables)"; return XM_ERR_CUDA; }
+    IndexFillD F;
+    F.run_key = (const unsigned long long*)d_run_key.p; F.run_cnt = (const int*)d_run_cnt.p; F.run_start = run_start; F.kept_off = kept_off; F.n_runs = n_runs;
+    F.first_run = (const int*)d_first.p; F.cap = (const int*)d_cap.p; F.bucket_base = (const long long*)d_bbase.p;
+    F.sorted_pos = (const uint32_t*)d_vals_a.p; F.buckets = (unsigned long long*)d_buckets.p; F.positions = (uint32_t*)d_pos.p;
+    xm_index_fill_kernel<<<(n_runs + 255) / 256, 256, 0, st>>>(F);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    for (int k = 1; k <= hi; k++) {
+      if (first[(size_t)k + 1] <= first[(size_t)k]) continue;   // no block of this length: PackedMap(1, 1)
+      HostTable& T = M.tables[(size_t)k];
+      T.capacity = cap[(size_t)k]; T.max_count = HostModel::max_count_for(k, 5);
+      T.buckets.resize((size_t)T.capacity);
+      CK(cudaMemcpy(T.buckets.data(), (const unsigned long long*)d_buckets.p + bbase[(size_t)k], (size_t)T.capacity * 8, cudaMemcpyDeviceToHost));
+      const long long np = koff[(size_t)k + 1] - koff[(size_t)k];
+      T.positions.resize((size_t)np);
+      if (np) CK(cudaMemcpy(T.positions.data(), (const uint32_t*)d_pos.p + koff[(size_t)k], (size_t)np * 4, cudaMemcpyDeviceToHost));
+    }
+  }
+  M.max_built = hi; M.index_finished = true; M.generation++;
+  return XM_OK;
+}
+
 int xm_build_index(xm_handle* h, int32_t max_used, int32_t n_threads) {
   if (!h) return XM_ERR_ARG;
   if (h->m.n_contigs < 1) { h->err = "reference not set"; return XM_ERR_STATE; }
+  if (n_threads <= 0) { CK(cudaSetDevice(h->device)); return build_index_device(h, max_used); }  // the device builder; n_threads > 0: the host builder it is checked against
   if (!h->m.build_index(max_used, n_threads, h->err)) return XM_ERR_ARG;
   return XM_OK;
 }

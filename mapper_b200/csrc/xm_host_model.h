@@ -111,6 +111,15 @@ struct HostModel {
 
   struct Entry { uint32_t bucket, pos; };
 
+  // what both index builders start from: minInterestingSize :51-55, the longest length built and the capacity per length
+  bool index_plan(int max_used, int& hi, std::vector<int>& cap, std::string& err) {
+    if (ref_ambiguous) { err = "xm_build_index: reference contains IUPAC-ambiguous bases (MultiHashBlock expansion of the reference is host-side in this round; upload the tables with xm_set_index_length)"; return false; }
+    min_interesting = j2i(std::max((std::log((double)(total_forward + 1)) / std::log(4.0)) - 2, 1.0));
+    hi = std::max(max_used, 2 * choose_min_dup_len());
+    cap.assign((size_t)hi + 1, 1);
+    for (int n = 1; n <= hi; n++) { int c = estimate_capacity(n); cap[(size_t)n] = c < 1 ? 1 : c; }
+    return true;
+  }
   bool build_index(int max_used, int n_threads, std::string& err) {
     if (ref_ambiguous) { err = "xm_build_index: reference contains IUPAC-ambiguous bases (MultiHashBlock expansion is host-side in this round; upload the tables with xm_set_index_length)"; return false; }
     min_interesting = j2i(std::max((std::log((double)(total_forward + 1)) / std::log(4.0)) - 2, 1.0));  // :51-55

@@ -75,19 +75,24 @@ def test_edge_cases():
     g.close()
 
 
-def test_library_index_builder_on_gpu_box():
-    ref = synth.random_reference(300000, seed=61, n_contigs=2, repeat_fraction=0.1, repeat_len=(100, 800))
+@pytest.mark.parametrize("threads", [0, 4], ids=["device", "host"])
+def test_library_index_builder_on_gpu_box(threads):
+    """xm_build_index: the device builder (threads=0) and the host builder it is checked against both reproduce the oracle's
+    HashBlock_Database tables (M/HashBlock_Database.java:490-665, M/PackedMap.java:99-153): capacity, max count, overfull buckets,
+    bucket offsets and positions."""
+    ref = synth.random_reference(300000, seed=61, n_contigs=3, repeat_fraction=0.1, repeat_len=(100, 800))
     db = xo.Oracle([(n, synth.codes_to_text(s)) for n, s in ref], sort_by_length=True, dup=dict(min_copies=2, window=1000))
     built = db.build_through(100)
     g = capi.XMapper(synth.DEFAULT_PARAMS, device=0)
     parity.feed_reference(g, db)
-    g.build_index(100)
+    g.build_index(100, threads=threads)
     mi, mb = g.index_info()
     assert mi == db.min_interesting()
     for n in range(1, min(built, mb) + 1):
         t0, t1 = db.table(n), g.get_index_length(n)
-        assert t0["capacity"] == t1["capacity"] and t0["max_count"] == t1["max_count"]
-        assert np.array_equal(t0["overfull"], t1["overfull"]) and np.array_equal(t0["positions"], t1["positions"])
+        assert t0["capacity"] == t1["capacity"] and t0["max_count"] == t1["max_count"], n
+        assert np.array_equal(t0["overfull"], t1["overfull"]) and np.array_equal(t0["positions"], t1["positions"]), n
+        assert np.array_equal(t0["offsets"], t1["offsets"]), n
     g.close()
 
 

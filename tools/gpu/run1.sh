@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/s15_pytest.log 2>&1; tail -25 gpurun_out/s15_pytest.log | cut -c1-250
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/s16_pytest.log 2>&1; tail -25 gpurun_out/s16_pytest.log | cut -c1-250
