@@ -474,42 +474,31 @@ XM_FN int pa_search(WS& w, PathState& S, PaOverflow* ovf, int cap_ovf, int& last
   PaQueue Q;
   Q.init(S.ent, S.ent_cap, ovf, cap_ovf);
   int qrc = 0;
-  // seeding :120-150.  activePenalty is 0 here, estimates are never negative: no clamping needed.
+  // seeding :120-150.  activePenalty is 0 here, estimates are never negative: no clamping needed.  One loop (one copy of
+  // the queue code) walks the free-start nodes :120-139 and then the query-overhang nodes :140-150.
   {
     const int start_x = S.start_x, start_y = S.start_y;
-    if (B >= A) {
-      double sisp = S.prm.starting_ins_start();
-      if (!may_extend) sisp = XM_DISALLOWED;
-      const int cnt = imax(0, B - A) + 1;
-      XM_NOUNROLL
-      for (int i = 0; i < cnt && qrc == 0; i++) {
-        PNode n; n.pen = 0; n.ins_x = sisp; n.ins_y = XM_DISALLOWED;
-        const int x = start_x, y = start_y + i * step;
-        qrc = Q.push(pa_estimate(S, x, y, n, 0), x, y);
-        const int idx = x * H + y; nodes[idx] = n; flags[idx] = 1;
-      }
-    } else {
-      const int cnt = imax(0, A - B) + 1;
-      XM_NOUNROLL
-      for (int i = 0; i < cnt && qrc == 0; i++) {
-        PNode n; n.pen = 0; n.ins_x = XM_DISALLOWED; n.ins_y = XM_DISALLOWED;
-        const int x = start_x + i * step, y = start_y;
-        qrc = Q.push(pa_estimate(S, x, y, n, 0), x, y);
-        const int idx = x * H + y; nodes[idx] = n; flags[idx] = 1;
-      }
-    }
-    if (may_extend) {
-      const int cnt = j2i(S.an->max_ins / del_ext);
-      XM_NOUNROLL
-      for (int i = 1; i < cnt && qrc == 0; i++) {
-        const int xa = start_x + i * step;
-        PNode n; n.pen = i * unaligned; n.ins_x = XM_DISALLOWED; n.ins_y = XM_DISALLOWED;
+    const bool along_y = B >= A;
+    double sisp = XM_DISALLOWED;
+    if (along_y && may_extend) sisp = S.prm.starting_ins_start();
+    const int cnt1 = (along_y ? imax(0, B - A) : imax(0, A - B)) + 1;
+    const int cnt2 = may_extend ? imax(0, j2i(S.an->max_ins / del_ext) - 1) : 0;
+    XM_NOUNROLL
+    for (int i = 0; i < cnt1 + cnt2 && qrc == 0; i++) {
+      PNode n; int x, y;
+      if (i < cnt1) {
+        n.pen = 0; n.ins_x = along_y ? sisp : XM_DISALLOWED; n.ins_y = XM_DISALLOWED;
+        x = along_y ? start_x : start_x + i * step; y = along_y ? start_y + i * step : start_y;
+      } else {
+        const int k = i - cnt1 + 1;
+        x = start_x + k * step; y = start_y;
+        n.pen = k * unaligned; n.ins_x = XM_DISALLOWED; n.ins_y = XM_DISALLOWED;
         // outside the lattice the reference still queues the node (saveNode ignores x < 0; x > width is stored but
         // never read), and popping it can end the search when its priority exceeds the budget
-        if (xa < -32000 || xa > 32000) { qrc = 1; break; }
-        qrc = Q.push(pa_estimate(S, xa, start_y, n, 0), xa, start_y);
-        if (xa >= 0 && xa < S.W) { const int idx = xa * H + start_y; nodes[idx] = n; flags[idx] = 1; }
+        if (x < -32000 || x > 32000) { qrc = 1; break; }
       }
+      qrc = Q.push(pa_estimate(S, x, y, n, 0), x, y);
+      if (x >= 0 && x < S.W) { const int idx = x * H + y; nodes[idx] = n; flags[idx] = 1; }
     }
   }
   unsigned long long steps = 0;
