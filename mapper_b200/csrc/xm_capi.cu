@@ -23,7 +23,9 @@ using namespace xm;
 // ---------------------------------------------------------------- kernels
 // first pass: blocks of 4 warps, 8 per SM.  full kernel: ONE block per SM of up to 32 warps, each warp owning one
 // query at a time.
+#ifndef XM_BLOCK
 #define XM_BLOCK 128
+#endif
 #ifndef XM_MIN_BLOCKS
 #define XM_MIN_BLOCKS 8
 #endif
