@@ -218,7 +218,8 @@ def main():
     barrier()
     wall_dev = time.time() - t0
     # ---- timed: end to end through the C ABI with host buffers (H2D + kernels + D2H + result assembly) ----
-    step_host()
+    keep = [step_host() for _ in range(2)]  # untimed warm-up of the host path: staging buffers and BOTH pinned result slabs (a caller holds one result while the next batch runs)
+    del keep
     barrier()
     t0 = time.time()
     h2d = d2h = 0

@@ -12,6 +12,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_run_length_encode.cuh>
 #include <memory>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -648,6 +649,8 @@ struct xm_handle {
   DevBuf d_planes, d_contig_off; long long n_plane_ints = 0;
 };
 
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return XM_ERR_CUDA; } } while (0)
 
 static int mirror_model(xm_handle* h) {
@@ -1058,6 +1061,8 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
   unsigned long long misc[20];
   CK(cudaMemcpyAsync(misc, h->d_misc.p, sizeof(misc), cudaMemcpyDeviceToHost, st));
   // CSR assembly on the device, then one transfer into a pinned slab
+  const bool host_times = getenv("XM_HOST_TIMES") != nullptr;
+  const double t_csr0 = now_ms();
   const long long stride = (long long)nq + 1;
   size_t scan_tmp = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (const long long*)nullptr, (long long*)nullptr, (int)stride, st);
@@ -1092,6 +1097,7 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
     CK(cudaMemcpyAsync(R->slab, d, slab_bytes, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     R->r.slab = (const char*)R->slab;
+    if (host_times) fprintf(stderr, "[xm]   csr assembly + slab D2H (%.0f MB): %.1f ms\n", (double)slab_bytes / 1e6, now_ms() - t_csr0);
     h->last_batch = L.batch; R->serial = ++h->batch_serial; R->nq = nq;
     R->r.stats[XM_STAT_D2H_BYTES] = (int64_t)(slab_bytes + sizeof(misc) + 32);
   }
@@ -1117,6 +1123,8 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
 int xm_align_batch(xm_handle* h, int32_t nq, const uint16_t* packed4, const int64_t* seq_word_off, const int32_t* seq_len, const uint8_t* n_seqs,
                    const double* expected_inner, const double* per_penalty, xm_results** out) {
   if (!h || nq < 0 || !out || (nq > 0 && (!packed4 || !seq_word_off || !seq_len || !n_seqs))) return XM_ERR_ARG;
+  const bool host_times = getenv("XM_HOST_TIMES") != nullptr;
+  const double t_in = now_ms();
   CK(cudaSetDevice(h->device));
   long long n_seqs_total = 0;
   for (int i = 0; i < nq; i++) { if (n_seqs[i] < 1 || n_seqs[i] > 2) { h->err = "n_seqs_per_query must be 1 or 2"; return XM_ERR_ARG; } n_seqs_total += n_seqs[i]; }
@@ -1137,9 +1145,11 @@ int xm_align_batch(xm_handle* h, int32_t nq, const uint16_t* packed4, const int6
     CK(cudaMemcpyAsync(h->d_per.p, per_penalty ? per_penalty : zeros.data(), (size_t)nq * 8, cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
   }
+  const double t_h2d = now_ms();
   int rc = xm_align_batch_device(h, nq, (const uint16_t*)h->d_packed.p, n_words, (const int64_t*)h->d_seq_word_off.p, (const int32_t*)h->d_seq_len.p,
                                  (const uint8_t*)h->d_n_seqs.p, (const double*)h->d_expected.p, (const double*)h->d_per.p, max_len, out);
   if (*out) (*out)->r.stats[XM_STAT_H2D_BYTES] = (int64_t)((size_t)n_words * 2 + ((size_t)n_seqs_total + 1) * 8 + (size_t)n_seqs_total * 4 + (size_t)nq * 17);
+  if (host_times && *out) fprintf(stderr, "[xm] xm_align_batch: validate+H2D %.1f ms, device call %.1f ms (kernels %.1f ms)\n", t_h2d - t_in, now_ms() - t_h2d, (double)(*out)->r.stats[XM_STAT_KERNEL_NS] / 1e6);
   return rc;
 }
 

@@ -1,2 +1,1 @@
-for b in 512 1024; do echo "== easy block $b"; XM_LIB_PATH=$PWD/mapper_b200/libxm_e$b.so timeout 300 python tools/probe_qcycles.py --reads 1000000 2>&1 | sed -n 1,2p | cut -c1-160; done
-echo "== default"; timeout 300 python tools/probe_qcycles.py --reads 1000000 2>&1 | sed -n 1,2p | cut -c1-160
+XM_HOST_TIMES=1 timeout 600 python bench.py --no-cpu-baseline --steps 2 --warmup 2 2>&1 >/dev/null | grep "\[xm\]" | tail -8
