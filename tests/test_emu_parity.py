@@ -110,3 +110,31 @@ def test_reads_with_ambiguous_bases(paired):
     a, b = run_both(db, synth.DEFAULT_PARAMS, batch, 1000, 120)
     assert (b["q_status"] == 0).all()
     parity.assert_same_results(a, b, "ambiguous reads %s" % ("paired" if paired else "single"))
+
+
+PARAM_VARIANTS = {
+    "no-gapmers": dict(enable_gapmers=0),
+    "cheap-indels": dict(ins_start=0.8, ins_ext=0.3, del_start=0.7, del_ext=0.25),
+    "loose-error-rate": dict(max_error_rate=0.2),
+    "no-span-one-match": dict(max_penalty_span=0.0, max_num_matches=1),
+    "costly-mutation": dict(mutation=2.0, ambiguity=0.3, unaligned=0.25, max_penalty_span=1.5),
+}
+
+
+def variant_params(name):
+    p = dict(synth.DEFAULT_PARAMS)
+    p.update(PARAM_VARIANTS[name])
+    return p
+
+
+@pytest.mark.parametrize("name", sorted(PARAM_VARIANTS), ids=sorted(PARAM_VARIANTS))
+def test_parameter_variants(name):
+    """Non-default AlignmentParameters (M/AlignmentParameters.java:6-37, --no-gapmers M/Mapper.java:51): the penalty model is data, not code."""
+    p = variant_params(name)
+    ref = synth.random_reference(150000, seed=41, n_contigs=2, repeat_fraction=0.08, repeat_len=(150, 800))
+    db = xo.Oracle([(n, synth.codes_to_text(s)) for n, s in ref], sort_by_length=True, gapmers=bool(p.get("enable_gapmers", 1)), dup=dict(min_copies=2, window=1000))
+    contigs = [db.contig(i) for i in range(db.num_contigs())]
+    for paired in (False, True):
+        batch = synth.simulate_reads(contigs, 700, 100, seed=43 + paired, sub_rate=0.02, indel_rate=0.004, paired=paired, inner_mean=150.0, inner_sd=20.0)
+        a, b = run_both(db, p, batch, 1000, 100)
+        parity.assert_same_results(a, b, "%s paired=%s" % (name, paired))

@@ -206,3 +206,20 @@ def test_sam_random_reads_vs_oracle(paired):
             assert x == y
     assert sam == want
     g.close()
+
+
+@pytest.mark.parametrize("name", ["no-gapmers", "cheap-indels", "loose-error-rate", "no-span-one-match", "costly-mutation"])
+def test_parameter_variants(name):
+    """Non-default AlignmentParameters and --no-gapmers through the C ABI (index and duplication table built by the library)."""
+    from test_emu_parity import variant_params
+    p = variant_params(name)
+    ref = synth.random_reference(200000, seed=151, n_contigs=2, repeat_fraction=0.08, repeat_len=(150, 800))
+    db = xo.Oracle([(n, synth.codes_to_text(s)) for n, s in ref], sort_by_length=True, gapmers=bool(p.get("enable_gapmers", 1)), dup=dict(min_copies=2, window=1000))
+    contigs = [db.contig(i) for i in range(db.num_contigs())]
+    g = gpu_from_oracle(db, p, 120, 1000, False, False)
+    for paired in (False, True):
+        batch = synth.simulate_reads(contigs, 4000, 120, seed=153 + paired, sub_rate=0.02, indel_rate=0.004, paired=paired, inner_mean=150.0, inner_sd=20.0)
+        got = g.align_batch(batch, strict=True)
+        want = db.align_batch(p, batch, threads=8)
+        parity.assert_same_results(want, got, "%s paired=%s" % (name, paired))
+    g.close()

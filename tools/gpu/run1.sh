@@ -1,1 +1,1 @@
-XM_HOST_TIMES=1 timeout 600 python bench.py --no-cpu-baseline --steps 2 --warmup 2 2>&1 >/dev/null | grep "\[xm\]" | tail -8
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/s18_pytest.log 2>&1; tail -25 gpurun_out/s18_pytest.log | cut -c1-250
