@@ -223,3 +223,36 @@ def test_parameter_variants(name):
         want = db.align_batch(p, batch, threads=8)
         parity.assert_same_results(want, got, "%s paired=%s" % (name, paired))
     g.close()
+
+
+def test_consecutive_batches_and_result_lifetime():
+    """One handle, many xm_align_batch calls of different sizes (0, 1, odd, larger than the previous), results of earlier batches kept
+    alive (zero-copy views into the pinned slabs) while later ones run; xm_format_sam refuses results whose device copy is gone."""
+    import ctypes as C
+    ref = synth.random_reference(150000, seed=161, n_contigs=2, repeat_fraction=0.05, repeat_len=(200, 600))
+    db = xo.Oracle([(n, synth.codes_to_text(s)) for n, s in ref], sort_by_length=True, dup=dict(min_copies=2, window=1000))
+    contigs = [db.contig(i) for i in range(db.num_contigs())]
+    g = gpu_from_oracle(db, synth.DEFAULT_PARAMS, 150, 1000, False, False)
+    kept = []
+    for i, n in enumerate([1, 0, 777, 5000, 33, 12000, 2]):
+        if n == 0:
+            batch = parity.batch_from_texts([])
+        else:
+            batch = synth.simulate_reads(contigs, n, 150, seed=170 + i, sub_rate=0.015, indel_rate=0.002, paired=(i % 2 == 1))
+        got = g.align_batch(batch, strict=True, copy=False)
+        want = db.align_batch(synth.DEFAULT_PARAMS, batch, threads=4)
+        kept.append((want, got))
+    for want, got in kept:  # every earlier result is still intact
+        parity.assert_same_results(want, {k: v for k, v in got.items() if k != "_owner"}, "kept result")
+    # SAM text can only be produced for the latest batch of the handle
+    batch = synth.simulate_reads(contigs, 10, 150, seed=190)
+    r1, r2 = C.c_void_p(), C.c_void_p()
+    args = lambda b: (len(b["n_seqs"]), capi._ptr(b["packed"]), capi._ptr(b["seq_word_off"]), capi._ptr(b["seq_len"]), capi._ptr(b["n_seqs"]), capi._ptr(b["expected_inner"]), capi._ptr(b["per_penalty"]))
+    assert g.L.xm_align_batch(g.h, *args(batch), C.byref(r1)) == 0
+    assert g.L.xm_align_batch(g.h, *args(batch), C.byref(r2)) == 0
+    names = ["r%d" % i for i in range(10)]
+    with pytest.raises(capi.XmError):
+        g.format_sam(r1, names, ["c0", "c1"])
+    assert g.format_sam(r2, names, ["c0", "c1"]).count("\n") >= 9
+    g.L.xm_release_results(r1); g.L.xm_release_results(r2)
+    g.close()
