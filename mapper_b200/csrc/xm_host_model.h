@@ -255,36 +255,51 @@ struct HostModel {
       }
       blocks.clear();
     };
+    // The per-bucket grouping (the expensive part) is independent across buckets: threads build the `blocks` of chunks of
+    // 10000 buckets in parallel; the chunks are then merged in the reference's order (saveDuplications every 10000 hashcodes).
+    const int chunk_len = 10000;
+    unsigned hw = std::thread::hardware_concurrency();
+    const int n_thr = (int)std::max(1u, std::min(hw ? hw : 1u, 32u));
     for (int bl = min_len; bl <= max_len && bl <= max_built; bl++) {
       const HostTable& T = tables[(size_t)bl];
-      std::map<int, std::map<int, Dup>> blocks;
-      for (int hc = 0; hc < T.capacity; hc++) {
-        if (!T.buckets.empty()) {
+      const int n_chunks = (T.capacity + chunk_len - 1) / chunk_len;
+      std::vector<std::map<int, std::map<int, Dup>>> chunk_blocks((size_t)n_chunks);
+      auto scan_chunk = [&](int ci) {
+        std::map<int, std::map<int, Dup>>& blocks = chunk_blocks[(size_t)ci];
+        const int hc_end = std::min(T.capacity, (ci + 1) * chunk_len);
+        for (int hc = ci * chunk_len; hc < hc_end; hc++) {
+          if (T.buckets.empty()) continue;
           uint64_t word = T.buckets[(size_t)hc];
           int cnt = (int)(word & 0xFFFF);
-          if (!((word >> 16) & 1) && cnt >= min_copies) {
-            // lookupByForwardHash :41-52: every stored position plus its reverse complement (using numBasepairsUsed as the length)
-            std::map<std::string, std::set<std::pair<int, int>>> by_text;
-            int prefix = (bl + 3) / 4;
-            for (int k = 0; k < 2 * cnt; k++) {
-              int64_t g = T.positions[(size_t)(word >> 24) + (size_t)(k % cnt)];
-              int sid = (int)(std::upper_bound(gstart.begin(), gstart.end(), g) - gstart.begin()) - 1;
-              int st = (int)(g - gstart[(size_t)sid]);
-              if (k >= cnt) { sid ^= 1; st = len[(size_t)(sid >> 1)] - st - bl; }
-              SeqView v = contig_view(sid >> 1, sid & 1);
-              std::string text; bool amb = false;
-              for (int i = 0; i < prefix; i++) { uint8_t c = v.at(st + i); if (bp_is_ambiguous(c)) amb = true; text.push_back((char)c); }
-              for (int i = 0; i < prefix; i++) { uint8_t c = v.at(st + bl - prefix + i); if (bp_is_ambiguous(c)) amb = true; text.push_back((char)c); }
-              if (!amb) by_text[text].insert({sid, st});
-            }
-            for (auto& g : by_text) {
-              Dup d{bl, (int)g.second.size()};
-              if (d.count >= min_copies) for (auto& u : g.second) blocks[u.first][u.second] = d;
-            }
+          if (((word >> 16) & 1) || cnt < min_copies) continue;
+          // lookupByForwardHash :41-52: every stored position plus its reverse complement (using numBasepairsUsed as the length)
+          std::map<std::string, std::set<std::pair<int, int>>> by_text;
+          int prefix = (bl + 3) / 4;
+          for (int k = 0; k < 2 * cnt; k++) {
+            int64_t g = T.positions[(size_t)(word >> 24) + (size_t)(k % cnt)];
+            int sid = (int)(std::upper_bound(gstart.begin(), gstart.end(), g) - gstart.begin()) - 1;
+            int st = (int)(g - gstart[(size_t)sid]);
+            if (k >= cnt) { sid ^= 1; st = len[(size_t)(sid >> 1)] - st - bl; }
+            SeqView v = contig_view(sid >> 1, sid & 1);
+            std::string text; bool amb = false;
+            for (int i = 0; i < prefix; i++) { uint8_t c = v.at(st + i); if (bp_is_ambiguous(c)) amb = true; text.push_back((char)c); }
+            for (int i = 0; i < prefix; i++) { uint8_t c = v.at(st + bl - prefix + i); if (bp_is_ambiguous(c)) amb = true; text.push_back((char)c); }
+            if (!amb) by_text[text].insert({sid, st});
+          }
+          for (auto& g : by_text) {
+            Dup d{bl, (int)g.second.size()};
+            if (d.count >= min_copies) for (auto& u : g.second) blocks[u.first][u.second] = d;
           }
         }
-        if (hc % 10000 == 9999 || hc == T.capacity - 1) save(blocks);
+      };
+      if (n_thr == 1 || n_chunks < 2) { for (int ci = 0; ci < n_chunks; ci++) scan_chunk(ci); }
+      else {
+        std::atomic<int> next_chunk(0);
+        std::vector<std::thread> th;
+        for (int t = 0; t < std::min(n_thr, n_chunks); t++) th.emplace_back([&]() { while (true) { int ci = next_chunk.fetch_add(1); if (ci >= n_chunks) break; scan_chunk(ci); } });
+        for (auto& x : th) x.join();
       }
+      for (int ci = 0; ci < n_chunks; ci++) save(chunk_blocks[(size_t)ci]);
     }
     dup_starts.assign((size_t)n_contigs, {});
     for (int c = 0; c < n_contigs; c++) for (auto& e : all[(size_t)2 * c]) dup_starts[(size_t)c].push_back(e.first);
