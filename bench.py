@@ -237,16 +237,16 @@ def main():
     if a.counts:
         ptr, n_int = g.counts_device_ptr()
         if world > 1:
-            # wrap the library's device buffer without copying and all-reduce it in place over NVLink (int32 sum: exact, order-free)
-            from mapper_b200 import shard
-            planes = shard.wrap_device_planes(ptr, n_int, torch.device("cuda", local_rank))
+            # the library's own NCCL all-reduce of the planes (xm_comm_init / xm_counts_reduce; int32 sum: exact, order-free);
+            # torch.distributed only carries the 128-byte NCCL id from rank 0 to the others
+            uid = torch.tensor(list(g.comm_unique_id() if rank == 0 else bytes(128)), dtype=torch.uint8, device="cuda")
+            dist.broadcast(uid, 0)
+            g.comm_init(world, rank, bytes(uid.cpu().tolist()))
             barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            shard.allreduce_planes_(planes)
-            e1.record()
+            t0 = time.time()
+            g.counts_reduce()  # once: the planes must stay the sum over ranks (includes NCCL's first-call channel setup)
             torch.cuda.synchronize()
-            allreduce_ms = e0.elapsed_time(e1)
+            allreduce_ms = 1000.0 * (time.time() - t0)
 
     # max over ranks
     tvals = torch.tensor([dev_ns / 1e9, wall_dev, wall_e2e, align_ns / 1e9], dtype=torch.float64, device="cuda")

@@ -168,6 +168,15 @@ int xm_counts_enable(xm_handle* h, double query_end_fraction);
 int xm_counts_device_ptr(xm_handle* h, void** d_ptr, int64_t* n_int32);
 int xm_counts_fetch(xm_handle* h, int32_t contig, int32_t* out /* 4 * contig length */);
 
+/* Multi-GPU reduction of the count planes inside the library (NCCL over NVLink; libnccl.so.2 is loaded at run time).
+ * One process (or thread) per GPU, as the reference runs one AlignerWorker per thread and MatchDatabase merges them
+ * (QV/MatchDatabase.java:16-59): rank 0 calls xm_comm_unique_id and hands the 128 bytes to the others by any means,
+ * every rank calls xm_comm_init on its handle (collective), and after the last batch xm_counts_reduce (collective, blocking)
+ * leaves the int32 sum over all ranks in every rank's planes (exact and order-free); xm_counts_fetch then reads them. */
+int xm_comm_unique_id(uint8_t* id128);
+int xm_comm_init(xm_handle* h, int32_t n_ranks, int32_t rank, const uint8_t* id128);
+int xm_counts_reduce(xm_handle* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,7 +15,8 @@ LIB_PATH = os.environ.get("XM_LIB_PATH") or os.path.join(HERE, "libxmapper_b200.
 EXPORTS = ["xm_create", "xm_destroy", "xm_last_error", "xm_set_reference", "xm_set_index_length", "xm_finish_index",
            "xm_build_index", "xm_get_index_length", "xm_index_info", "xm_set_duplications", "xm_build_duplications",
            "xm_get_duplications", "xm_align_batch", "xm_align_batch_device", "xm_results_array", "xm_release_results",
-           "xm_counts_enable", "xm_counts_device_ptr", "xm_counts_fetch", "xm_format_sam"]
+           "xm_counts_enable", "xm_counts_device_ptr", "xm_counts_fetch", "xm_format_sam",
+           "xm_comm_unique_id", "xm_comm_init", "xm_counts_reduce"]
 
 RESULT_ARRAYS = [("q_comp_off", np.int64), ("comp_choice_off", np.int64), ("choice_sa_off", np.int64), ("sa_block_off", np.int64),
                  ("choice_f64", np.float64), ("sa_f64", np.float64), ("choice_inner", np.int32), ("sa_contig", np.int32),
@@ -240,6 +241,20 @@ class XMapper:
         p, n = C.c_void_p(), C.c_int64()
         self._ok(self.L.xm_counts_device_ptr(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def comm_unique_id(self):
+        buf = (C.c_uint8 * 128)()
+        rc = self.L.xm_comm_unique_id(buf)
+        if rc != 0:
+            raise XmError("xm_comm_unique_id: status %d (libnccl not loadable?)" % rc)
+        return bytes(buf)
+
+    def comm_init(self, n_ranks, rank, unique_id):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._ok(self.L.xm_comm_init(self.h, int(n_ranks), int(rank), buf))
+
+    def counts_reduce(self):
+        self._ok(self.L.xm_counts_reduce(self.h))
 
     def counts_fetch(self, contig):
         out = np.zeros(4 * self.contig_lengths[contig], dtype=np.int32)

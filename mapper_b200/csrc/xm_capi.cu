@@ -13,6 +13,8 @@
 #include <cub/device/device_run_length_encode.cuh>
 #include <memory>
 #include <chrono>
+#include <dlfcn.h>
+#include <nccl.h>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -626,6 +628,34 @@ struct xm_results {
   ~xm_results() { if (slab && pool) pool->give(slab, slab_cap); }
 };
 
+// ---- NCCL, loaded at run time (the host process may already carry its own libnccl; no link-time dependency) ----
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+static NcclApi& nccl_api() {
+  static NcclApi a;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);   // the copy the process already loaded (e.g. torch's), else the system one
+    if (!a.lib) a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!a.lib) a.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!a.lib) return;
+    a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.lib, "ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.lib, "ncclCommInitRank");
+    a.AllReduce = (decltype(a.AllReduce))dlsym(a.lib, "ncclAllReduce");
+    a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.lib, "ncclCommDestroy");
+    a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.lib, "ncclGetErrorString");
+    a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.CommDestroy && a.GetErrorString;
+  });
+  return a;
+}
+
 struct xm_handle {
   HostModel m;
   int device = 0, sm_count = 148, blocks_per_sm = 4;
@@ -651,6 +681,7 @@ struct xm_handle {
   // counts
   bool counts_enabled = false; double end_fraction = 0.1;
   DevBuf d_planes, d_contig_off; long long n_plane_ints = 0;
+  ncclComm_t comm = nullptr; int comm_ranks = 0;   // xm_comm_init: the communicator xm_counts_reduce uses
 };
 
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -737,6 +768,7 @@ int xm_create(const xm_params* p, int device, xm_handle** out) {
 void xm_destroy(xm_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  if (h->comm && nccl_api().ok) { nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
   DevBuf* bufs[] = {&h->d_words, &h->d_word_off, &h->d_len, &h->d_gstart, &h->d_tables, &h->d_dup_off, &h->d_dup_starts, &h->d_packed, &h->d_seq_word_off,
                     &h->d_seq_len, &h->d_n_seqs, &h->d_expected, &h->d_per, &h->d_first_seq, &h->d_chunk, &h->d_q, &h->d_choices, &h->d_sas, &h->d_blocks,
                     &h->d_misc, &h->d_ids_a, &h->d_ids_b, &h->d_ids_full, &h->d_ws, &h->d_qcycles, &h->d_csr_cnt, &h->d_csr_base, &h->d_csr_tmp, &h->d_csr_slab, &h->d_keys_a, &h->d_keys_b, &h->d_sort_tmp, &h->d_sam_len, &h->d_sam_text, &h->d_sam_names, &h->d_sam_name_off, &h->d_sam_cnames, &h->d_sam_cname_off, &h->d_planes, &h->d_contig_off};
@@ -1222,6 +1254,39 @@ int xm_counts_enable(xm_handle* h, double query_end_fraction) {
   CK(cudaMemset(h->d_planes.p, 0, (size_t)h->n_plane_ints * 4));
   CK(cudaMemcpy(h->d_contig_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice));
   h->end_fraction = query_end_fraction; h->counts_enabled = true;
+  return XM_OK;
+}
+int xm_comm_unique_id(uint8_t* id128) {
+  if (!id128) return XM_ERR_ARG;
+  NcclApi& N = nccl_api();
+  if (!N.ok) return XM_ERR_STATE;
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  if (N.GetUniqueId(&id) != ncclSuccess) return XM_ERR_CUDA;
+  memcpy(id128, &id, 128);
+  return XM_OK;
+}
+int xm_comm_init(xm_handle* h, int32_t n_ranks, int32_t rank, const uint8_t* id128) {
+  if (!h || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return XM_ERR_ARG;
+  NcclApi& N = nccl_api();
+  if (!N.ok) { h->err = "libnccl.so.2 could not be loaded"; return XM_ERR_STATE; }
+  CK(cudaSetDevice(h->device));
+  if (h->comm) { N.CommDestroy(h->comm); h->comm = nullptr; }
+  ncclUniqueId id; memcpy(&id, id128, 128);
+  ncclResult_t r = N.CommInitRank(&h->comm, n_ranks, id, rank);
+  if (r != ncclSuccess) { h->err = std::string("ncclCommInitRank: ") + N.GetErrorString(r); h->comm = nullptr; return XM_ERR_CUDA; }
+  h->comm_ranks = n_ranks;
+  return XM_OK;
+}
+int xm_counts_reduce(xm_handle* h) {
+  if (!h || !h->counts_enabled) return XM_ERR_STATE;
+  if (!h->comm) { h->err = "xm_counts_reduce: xm_comm_init was not called"; return XM_ERR_STATE; }
+  NcclApi& N = nccl_api();
+  CK(cudaSetDevice(h->device));
+  // int32 sums are exact and order-free: every rank ends with the planes of the whole run (QV/DirectionalAlignments.java:20-28)
+  ncclResult_t r = N.AllReduce(h->d_planes.p, h->d_planes.p, (size_t)h->n_plane_ints, ncclInt32, ncclSum, h->comm, h->stream);
+  if (r != ncclSuccess) { h->err = std::string("ncclAllReduce: ") + N.GetErrorString(r); return XM_ERR_CUDA; }
+  CK(cudaStreamSynchronize(h->stream));
   return XM_OK;
 }
 int xm_counts_device_ptr(xm_handle* h, void** d_ptr, int64_t* n_int32) {
