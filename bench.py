@@ -162,6 +162,13 @@ def main():
     t_index = time.time() - t0
     if a.counts:
         g.counts_enable(0.1)
+        if world > 1:
+            # xm_comm_init / xm_counts_reduce: torch.distributed only carries the 128-byte NCCL id from rank 0 to the others.
+            # The first reduce runs here, on planes that are still all zero, so that NCCL's channel setup is not in the timed one.
+            uid = torch.tensor(list(g.comm_unique_id() if rank == 0 else bytes(128)), dtype=torch.uint8, device="cuda")
+            dist.broadcast(uid, 0)
+            g.comm_init(world, rank, bytes(uid.cpu().tolist()))
+            g.counts_reduce()
     mi, mb = g.index_info()
     index_bytes = 0
     for n in range(mb + 1):
@@ -237,14 +244,9 @@ def main():
     if a.counts:
         ptr, n_int = g.counts_device_ptr()
         if world > 1:
-            # the library's own NCCL all-reduce of the planes (xm_comm_init / xm_counts_reduce; int32 sum: exact, order-free);
-            # torch.distributed only carries the 128-byte NCCL id from rank 0 to the others
-            uid = torch.tensor(list(g.comm_unique_id() if rank == 0 else bytes(128)), dtype=torch.uint8, device="cuda")
-            dist.broadcast(uid, 0)
-            g.comm_init(world, rank, bytes(uid.cpu().tolist()))
             barrier()
             t0 = time.time()
-            g.counts_reduce()  # once: the planes must stay the sum over ranks (includes NCCL's first-call channel setup)
+            g.counts_reduce()  # the library's own NCCL all-reduce of the planes (int32 sum: exact, order-free), once: the planes stay the sum over ranks
             torch.cuda.synchronize()
             allreduce_ms = 1000.0 * (time.time() - t0)
 
