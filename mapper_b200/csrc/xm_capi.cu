@@ -748,7 +748,7 @@ int xm_create(const xm_params* p, int device, xm_handle** out) {
   if (const char* e = getenv("XM_FULL_WARPS")) { int v = atoi(e); if (v >= 1 && v <= XM_FULL_BLOCK / 32) h->full_warps = v; }
   cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3);
-  size_t stack = 32 * 1024;
+  size_t stack = 8 * 1024;  // the call graph has no cycle any more: ptxas reports 3.5 KB for the deepest chain; 8 KB leaves margin without reserving 10 GB of local memory
   if (const char* e = getenv("XM_STACK_BYTES")) stack = (size_t)atoll(e);
   cudaDeviceSetLimit(cudaLimitStackSize, stack);
   if (const char* e = getenv("XM_WS_BYTES")) h->ws_budget = (size_t)atoll(e);
