@@ -54,6 +54,7 @@ struct LaunchD {
   int32_t* need_more_key;                 // first pass: cost estimate per entry of need_more (nullptr otherwise)
   int32_t* out_full; int* n_out_full;     // queries to re-run after growing the result arena
   char* arenas; long long arena_bytes;
+  char* big_arenas; long long big_arena_bytes; int n_big; int* big_busy;  // pool of next-tier-sized arenas: a query that outgrows its warp's arena is re-run at once in a free one
   int last_tier;
   int exp_groups;                         // experiment: distinct query streams per block (XM_EXP_GROUPS, default 1)
   int exp_dup;                            // experiment (XM_EXP_DUP=n): every warp of a block aligns the same n queries, results discarded by overwrite
@@ -107,6 +108,23 @@ __global__ void __launch_bounds__(EASY ? XM_BLOCK : XM_FULL_BLOCK, EASY ? XM_MIN
     __syncwarp();
     int status = w.status;
     if (status == Q_HARD) status = Q_NEED_MORE;
+    if (!EASY && status == Q_NEED_MORE && L.n_big > 0) {
+      // escalate in place: grab a free big arena (no waiting - if none is free the query goes to the next tier as before)
+      int slot = -1;
+      if (lane == 0) {
+        for (int i = 0; i < L.n_big; i++) { const int j = (int)((warp + i) % L.n_big); if (atomicCAS(&L.big_busy[j], 0, 1) == 0) { slot = j; break; } }
+      }
+      slot = __shfl_sync(0xffffffffu, slot, 0);
+      if (slot >= 0) {
+        rec.status = 0; rec.n_comp = 1; rec.n_choice[0] = 0; rec.n_choice[1] = 0; rec.choice_first[0] = 0; rec.choice_first[1] = 0;
+        if (!ws_init(w, L.big_arenas + (long long)slot * L.big_arena_bytes, L.big_arena_bytes, &L.ref, &L.ix, &L.dup, L.prm, q)) w.status = Q_NEED_MORE;
+        else align_query<EASY>(w, L.out, rec);
+        __syncwarp();
+        status = w.status;
+        __threadfence();
+        if (lane == 0) atomicExch(&L.big_busy[slot], 0);
+      }
+    }
     if (status == Q_NEED_MORE) {
       if (L.last_tier) status = Q_WORKSPACE;
       else if (lane == 0) { int k = atomicAdd(L.n_need_more, 1); L.need_more[k] = qi; if (L.need_more_key) L.need_more_key[k] = w.hard_hint; }
@@ -671,11 +689,12 @@ struct xm_handle {
   // batch staging + results + workspace
   DevBuf d_packed, d_seq_word_off, d_seq_len, d_n_seqs, d_expected, d_per, d_first_seq, d_chunk;
   DevBuf d_q, d_choices, d_sas, d_blocks, d_misc, d_ids_a, d_ids_b, d_ids_full, d_ws, d_qcycles;
-  DevBuf d_csr_cnt, d_csr_base, d_csr_tmp, d_csr_slab, d_keys_a, d_keys_b, d_sort_tmp;
+  DevBuf d_csr_cnt, d_csr_base, d_csr_tmp, d_csr_slab, d_keys_a, d_keys_b, d_sort_tmp, d_big, d_big_busy;
   DevBuf d_sam_len, d_sam_text, d_sam_names, d_sam_name_off, d_sam_cnames, d_sam_cname_off;
   BatchD last_batch{}; uint64_t batch_serial = 0;   // what xm_format_sam reads: the batch and CSR slab of the latest xm_align_batch
   std::shared_ptr<PinnedPool> pinned = std::make_shared<PinnedPool>();
   bool probe_cycles = false, sort_hard = true;
+  int big_pool = 64;  // XM_BIG_POOL: next-tier arenas available inside a full-kernel launch (0 = off)
   long long cap_choices = 0, cap_sas = 0, cap_blocks = 0;
   size_t ws_budget = (size_t)128 << 30;  // clamped to 60 % of the free device memory in xm_create
   // counts
@@ -744,6 +763,7 @@ int xm_create(const xm_params* p, int device, xm_handle** out) {
   { int nb = 0; if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, xm_align_kernel<true>, XM_BLOCK, 0) == cudaSuccess && nb > 0) h->blocks_per_sm = nb; }
   if (const char* e = getenv("XM_BLOCKS_PER_SM")) { int v = atoi(e); if (v > 0) h->blocks_per_sm = v; }
   if (const char* e = getenv("XM_SORT_HARD")) h->sort_hard = atoi(e) != 0;
+  if (const char* e = getenv("XM_BIG_POOL")) { int v = atoi(e); if (v >= 0 && v <= 1024) h->big_pool = v; }
   if (const char* e = getenv("XM_FULL_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) h->full_blocks_per_sm = v; }
   if (const char* e = getenv("XM_FULL_WARPS")) { int v = atoi(e); if (v >= 1 && v <= XM_FULL_BLOCK / 32) h->full_warps = v; }
   cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
@@ -773,7 +793,7 @@ void xm_destroy(xm_handle* h) {
   if (h->comm && nccl_api().ok) { nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
   DevBuf* bufs[] = {&h->d_words, &h->d_word_off, &h->d_len, &h->d_gstart, &h->d_tables, &h->d_dup_off, &h->d_dup_starts, &h->d_packed, &h->d_seq_word_off,
                     &h->d_seq_len, &h->d_n_seqs, &h->d_expected, &h->d_per, &h->d_first_seq, &h->d_chunk, &h->d_q, &h->d_choices, &h->d_sas, &h->d_blocks,
-                    &h->d_misc, &h->d_ids_a, &h->d_ids_b, &h->d_ids_full, &h->d_ws, &h->d_qcycles, &h->d_csr_cnt, &h->d_csr_base, &h->d_csr_tmp, &h->d_csr_slab, &h->d_keys_a, &h->d_keys_b, &h->d_sort_tmp, &h->d_sam_len, &h->d_sam_text, &h->d_sam_names, &h->d_sam_name_off, &h->d_sam_cnames, &h->d_sam_cname_off, &h->d_planes, &h->d_contig_off};
+                    &h->d_misc, &h->d_ids_a, &h->d_ids_b, &h->d_ids_full, &h->d_ws, &h->d_qcycles, &h->d_csr_cnt, &h->d_csr_base, &h->d_csr_tmp, &h->d_csr_slab, &h->d_keys_a, &h->d_keys_b, &h->d_sort_tmp, &h->d_big, &h->d_big_busy, &h->d_sam_len, &h->d_sam_text, &h->d_sam_names, &h->d_sam_name_off, &h->d_sam_cnames, &h->d_sam_cname_off, &h->d_planes, &h->d_contig_off};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : h->d_buckets) b.release();
   for (auto& b : h->d_positions) b.release();
@@ -1035,6 +1055,17 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
       CK(cudaMemsetAsync(d_ints, 0, 8, st));  // ticket, n_need_more
       L.ids = ids; L.n_ids = n_ids; L.need_more = next_ids; L.arenas = (char*)h->d_ws.p; L.arena_bytes = arena; L.last_tier = (tier == XM_NUM_TIERS - 1);
       L.need_more_key = nullptr;
+      L.big_arenas = nullptr; L.big_arena_bytes = 0; L.n_big = 0; L.big_busy = nullptr;
+      if (tier >= 0 && tier + 1 < XM_NUM_TIERS && h->big_pool > 0) {
+        // a small pool of next-tier arenas inside this launch: the rare queries that outgrow their arena do not wait for a launch of their own
+        const long long big = tier_arena_bytes(tier + 1, max_seq_len, 2, (long long)h->ws_budget, (long long)h->sm_count * h->full_blocks_per_sm * h->full_warps);
+        int n_big = h->big_pool;
+        while (n_big > 0 && (long long)n_big * big > (long long)h->ws_budget / 4) n_big /= 2;
+        if (n_big > 0 && big > arena && h->d_big.ensure((size_t)n_big * (size_t)big) && h->d_big_busy.ensure((size_t)n_big * 4)) {
+          CK(cudaMemsetAsync(h->d_big_busy.p, 0, (size_t)n_big * 4, st));
+          L.big_arenas = (char*)h->d_big.p; L.big_arena_bytes = big; L.n_big = n_big; L.big_busy = (int*)h->d_big_busy.p;
+        }
+      }
       if (tier < 0 && h->sort_hard) { if (!h->d_keys_a.ensure((size_t)n_ids * 4) || !h->d_keys_b.ensure((size_t)n_ids * 4)) { h->err = "out of device memory"; return XM_ERR_CUDA; } L.need_more_key = (int32_t*)h->d_keys_a.p; }
       L.exp_dup = 0;
       L.exp_groups = 1;
