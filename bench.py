@@ -285,7 +285,7 @@ def main():
         # measured DRAM traffic of the two kernels (one ncu capture of this command, profiles/): only quoted for the workload it was taken on
         traffic = {}
         try:
-            t = json.load(open(os.path.join(ROOT, "profiles", "r1n_traffic.json")))
+            t = json.load(open(os.path.join(ROOT, "profiles", "r1o_traffic.json")))
             if t["workload"] == dict(reads=a.reads, read_len=a.read_len, paired=bool(a.paired)) and a.ref_bases == 5000000:
                 traffic = t
         except Exception:
