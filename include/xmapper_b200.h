@@ -118,6 +118,9 @@ int xm_align_batch_device(xm_handle* h, int32_t n_queries, const uint16_t* d_pac
  *                        sa_f64[2a..] = penalty, alignedPenalty (QV/SequenceAlignment.java:18-24);
  *                        blocks sa_block_off[a] .. [a+1]
  *   block b           -> blocks[4b..] = aStart, bStart, aLen, bLen (QV/AlignedBlock.java:6-19)
+ * The arrays are assembled on the device and arrive in ONE transfer in a pinned host slab owned by the xm_results (the
+ * pointers xm_results_array returns are views into it: a JNI/FFM host maps them as direct buffers); the slab goes back to a
+ * small pool of the handle at xm_release_results.  Results of earlier batches stay valid while later batches run.
  */
 enum xm_array {
   XM_Q_COMP_OFF = 0, XM_COMP_CHOICE_OFF = 1, XM_CHOICE_SA_OFF = 2, XM_SA_BLOCK_OFF = 3, /* int64 */
@@ -129,7 +132,7 @@ enum xm_array {
 };
 enum xm_stat {
   XM_STAT_KERNEL_NS = 0,        /* device time of all kernels of this batch (CUDA events) */
-  XM_STAT_LAUNCHES = 1,         /* kernel launches */
+  XM_STAT_LAUNCHES = 1,         /* launches of this library's own kernels (cub scans/sorts not counted) */
   XM_STAT_TIER0_QUERIES = 2, XM_STAT_TIER1_QUERIES = 3, XM_STAT_TIER2_QUERIES = 4,
   XM_STAT_PROBES = 5,           /* bucket-count probes (HashBlockPath.java:143-223) */
   XM_STAT_SEEDS = 6,            /* emitted seeds */
