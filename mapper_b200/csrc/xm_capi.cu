@@ -641,9 +641,9 @@ struct PinnedPool {
 struct xm_results {
   ResultsHost r;
   uint64_t serial = 0; int nq = 0;           // which xm_align_batch of the handle produced it
-  std::vector<char> sam;                     // text of the latest xm_format_sam
+  void* sam = nullptr; size_t sam_cap = 0;   // pinned text of the latest xm_format_sam (from the same pool as the slab)
   std::shared_ptr<PinnedPool> pool; void* slab = nullptr; size_t slab_cap = 0;
-  ~xm_results() { if (slab && pool) pool->give(slab, slab_cap); }
+  ~xm_results() { if (slab && pool) pool->give(slab, slab_cap); if (sam && pool) pool->give(sam, sam_cap); }
 };
 
 // ---- NCCL, loaded at run time (the host process may already carry its own libnccl; no link-time dependency) ----
@@ -1266,11 +1266,14 @@ int xm_format_sam(xm_handle* h, xm_results* r, const char* seq_names, const int6
   S.text = (char*)h->d_sam_text.p;
   xm_sam_kernel<true><<<(nq + 127) / 128, 128, 0, st>>>(S, h->last_batch, nq);
   CK(cudaGetLastError());
-  r->sam.resize((size_t)total + 1);
-  CK(cudaMemcpyAsync(r->sam.data(), S.text, (size_t)total, cudaMemcpyDeviceToHost, st));
+  if (!r->pool) r->pool = h->pinned;
+  if (r->sam && r->sam_cap < (size_t)total + 1) { r->pool->give(r->sam, r->sam_cap); r->sam = nullptr; }
+  if (!r->sam) r->sam = r->pool->take((size_t)total + 1, r->sam_cap);
+  if (!r->sam) { h->err = "out of pinned host memory (sam text)"; return XM_ERR_CUDA; }
+  CK(cudaMemcpyAsync(r->sam, S.text, (size_t)total, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  r->sam[(size_t)total] = 0;
-  *text = r->sam.data(); *n_bytes = total;
+  ((char*)r->sam)[(size_t)total] = 0;
+  *text = (const char*)r->sam; *n_bytes = total;
   return XM_OK;
 }
 
