@@ -339,10 +339,26 @@ struct PaQueue {
 #else
     for (int b = 0; b < 32; b++) if (bhead[b] >= 0 && bkey[b] == pri) { ent[btail[b]].next = id; btail[b] = id; return 0; }
 #endif
-    // spill array: first position with key >= pri
+    // spill array: first position with key >= pri.  On the device the lanes probe 32 pivots per round (a 32-ary search: two
+    // dependent loads for up to 1024 buckets, where a binary search chases ten)
     int lo = ovf_lo, hi = ovf_hi;
+#if defined(__CUDA_ARCH__)
+    XM_NOUNROLL
+    while (hi - lo > 0) {
+      const int n = hi - lo;
+      const int stride = (n + 31) >> 5;                       // 32 pivots: the LAST element of each chunk of `stride`
+      const int at = lo + imin(n, (lane + 1) * stride) - 1;
+      const bool less = ovf[at].key < pri;                     // monotone over lanes (ascending keys)
+      const int k = __popc(__ballot_sync(0xffffffffu, less));  // chunks entirely below pri
+      const int nlo = lo + imin(n, k * stride);
+      if (k >= 32 || nlo >= hi) { lo = hi; break; }
+      hi = lo + imin(n, (k + 1) * stride); lo = nlo;
+      if (stride == 1) { break; }                              // chunk k is one element and it is >= pri
+    }
+#else
     XM_NOUNROLL
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (ovf[mid].key < pri) lo = mid + 1; else hi = mid; }
+#endif
     if (lo < ovf_hi && ovf[lo].key == pri) { ent[ovf[lo].tail].next = id; ovf[lo].tail = id; return 0; }
 #if defined(__CUDA_ARCH__)
     const unsigned fre = __ballot_sync(0xffffffffu, bhead < 0);
