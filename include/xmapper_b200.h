@@ -95,9 +95,12 @@ int xm_build_duplications(xm_handle* h, int32_t min_len, int32_t max_len, int32_
 int xm_get_duplications(xm_handle* h, int32_t contig, int32_t* n, int32_t* starts);
 
 /* AlignerWorker.process(): aligns n_queries queries. Query q owns n_seqs_per_query[q] (1 or 2) consecutive
- * sequences; sequence s is seq_len[s] bases at packed4 + seq_word_off[s] (16-bit words). expected_inner /
- * spacing_per_penalty are Query.expectedInnerDistance / spacingDeviationPerUnitPenalty (QV/Query.java:17-30),
- * ignored for single-sequence queries. Blocking; one call at a time per handle. */
+ * sequences; sequence s is seq_len[s] bases at packed4 + seq_word_off[s] (16-bit words). seq_word_off holds
+ * n_sequences + 1 entries: the last one is the total number of 16-bit words of packed4 (what gets copied to the device).
+ * expected_inner / spacing_per_penalty are Query.expectedInnerDistance / spacingDeviationPerUnitPenalty
+ * (QV/Query.java:17-30), ignored for single-sequence queries; NULL means 0.0 / 1.0 for every query.
+ * *out is set to NULL first and only receives results when the call returns XM_OK or XM_ERR_QUERY (per-query failures,
+ * see q_status); on every other error nothing is allocated for the caller to release. Blocking. */
 int xm_align_batch(xm_handle* h, int32_t n_queries, const uint16_t* packed4, const int64_t* seq_word_off,
                    const int32_t* seq_len, const uint8_t* n_seqs_per_query, const double* expected_inner,
                    const double* spacing_per_penalty, xm_results** out);

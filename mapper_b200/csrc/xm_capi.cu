@@ -1,8 +1,9 @@
 // xmapper_b200 — CUDA kernels + the C ABI (include/xmapper_b200.h).
-// One query per thread; queries are handed out dynamically (atomic ticket) to a persistent grid sized from the
-// SM count.  Every thread owns a private workspace arena in HBM; queries that exhaust the arena of one tier are
-// collected and re-run from scratch in the next tier (bigger arenas, fewer threads).  There is no CPU path: the
-// host only stages inputs, launches, and reshapes the result arena.
+// One query per WARP (warp-uniform control flow, lane-parallel inner loops); queries are handed out dynamically
+// (atomic ticket) to a persistent grid sized from the SM count.  Every warp owns a private workspace arena in HBM;
+// queries that exhaust the arena of one tier are collected and re-run from scratch in the next tier (bigger arenas,
+// fewer warps).  The alignment path has no CPU implementation: the host only stages inputs and launches; the result
+// arrays, the SAM text and the count records are assembled by kernels.
 #include "../../include/xmapper_b200.h"
 #include "xm_align.h"
 #include "xm_host_model.h"
@@ -766,11 +767,21 @@ int xm_create(const xm_params* p, int device, xm_handle** out) {
   if (const char* e = getenv("XM_BIG_POOL")) { int v = atoi(e); if (v >= 0 && v <= 1024) h->big_pool = v; }
   if (const char* e = getenv("XM_FULL_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) h->full_blocks_per_sm = v; }
   if (const char* e = getenv("XM_FULL_WARPS")) { int v = atoi(e); if (v >= 1 && v <= XM_FULL_BLOCK / 32) h->full_warps = v; }
-  cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-  cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3);
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+      cudaEventCreate(&h->ev2) != cudaSuccess || cudaEventCreate(&h->ev3) != cudaSuccess) {
+    fprintf(stderr, "xmapper_b200: stream/event creation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+    xm_destroy(h); return XM_ERR_CUDA;
+  }
   size_t stack = 8 * 1024;  // the call graph has no cycle any more: ptxas reports 3.5 KB for the deepest chain; 8 KB leaves margin without reserving 10 GB of local memory
   if (const char* e = getenv("XM_STACK_BYTES")) stack = (size_t)atoll(e);
-  cudaDeviceSetLimit(cudaLimitStackSize, stack);
+  {  // the limit belongs to the whole primary context (the JVM, torch, other handles): only ever raise it
+    size_t cur = 0;
+    if (cudaDeviceGetLimit(&cur, cudaLimitStackSize) != cudaSuccess) cur = 0;
+    if (cur < stack && cudaDeviceSetLimit(cudaLimitStackSize, stack) != cudaSuccess) {
+      fprintf(stderr, "xmapper_b200: cannot raise the device stack limit to %zu bytes: %s\n", stack, cudaGetErrorString(cudaGetLastError()));
+      xm_destroy(h); return XM_ERR_CUDA;
+    }
+  }
   if (const char* e = getenv("XM_WS_BYTES")) h->ws_budget = (size_t)atoll(e);
   if (const char* e = getenv("XM_QCYCLES")) h->probe_cycles = atoi(e) != 0;
   size_t free_b = 0, total_b = 0;
@@ -798,7 +809,7 @@ void xm_destroy(xm_handle* h) {
   for (auto& b : h->d_buckets) b.release();
   for (auto& b : h->d_positions) b.release();
   if (h->stream) cudaStreamDestroy(h->stream);
-  cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3);
+  for (cudaEvent_t e : {h->ev0, h->ev1, h->ev2, h->ev3}) if (e) cudaEventDestroy(e);
   delete h;
 }
 const char* xm_last_error(const xm_handle* h) { return h ? h->err.c_str() : "null handle"; }
@@ -815,6 +826,14 @@ int xm_set_reference(xm_handle* h, int32_t n, const uint16_t* const* packed4, co
 int xm_set_index_length(xm_handle* h, int32_t n_used, int32_t capacity, int32_t max_count, const int64_t* offsets, const uint8_t* overfull, const uint32_t* positions) {
   if (!h || n_used < 0 || capacity < 1 || !offsets) return XM_ERR_ARG;
   if (max_count > 32766) { h->err = "max_count > 32766"; return XM_ERR_ARG; }
+  if (offsets[0] != 0) { h->err = "xm_set_index_length: offsets[0] != 0"; return XM_ERR_ARG; }
+  for (int32_t b = 0; b < capacity; b++) {
+    const int64_t cnt = offsets[b + 1] - offsets[b];
+    if (cnt < 0) { h->err = "xm_set_index_length: offsets are not non-decreasing"; return XM_ERR_ARG; }
+    if (cnt > 65535 || (cnt > max_count && !(overfull && overfull[b]))) { h->err = "xm_set_index_length: a bucket that is not overfull holds more than max_count positions"; return XM_ERR_ARG; }
+  }
+  if (offsets[capacity] >= (1LL << 40)) { h->err = "xm_set_index_length: more than 2^40 positions"; return XM_ERR_ARG; }
+  if (offsets[capacity] > 0 && !positions) return XM_ERR_ARG;
   h->m.set_index_length(n_used, capacity, max_count, offsets, overfull, positions);
   return XM_OK;
 }
@@ -965,15 +984,22 @@ int xm_get_duplications(xm_handle* h, int32_t contig, int32_t* n, int32_t* start
 
 int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, int64_t n_words, const int64_t* d_seq_word_off, const int32_t* d_seq_len,
                           const uint8_t* d_n_seqs, const double* d_expected, const double* d_per, int32_t max_seq_len, xm_results** out) {
+  if (out) *out = nullptr;
   if (!h || nq < 0 || !out) return XM_ERR_ARG;
   CK(cudaSetDevice(h->device));
   int rc = mirror_model(h);
   if (rc != XM_OK) return rc;
   (void)n_words;
   cudaStream_t st = h->stream;
-  xm_results* R = new xm_results();
+  // the device copy of the previous batch's results (CSR slab, first_seq) is about to be overwritten: results handed out
+  // earlier must not pass xm_format_sam's "latest batch" check any more, whether or not this call succeeds
+  ++h->batch_serial;
+  // owned here until the call succeeds (or ends with XM_ERR_QUERY, where the results are still delivered): every early
+  // error return frees the results and gives the pinned slab back to the pool
+  std::unique_ptr<xm_results> R_owner(new xm_results());
+  xm_results* R = R_owner.get();
   R->r.stats.assign(XM_STAT_COUNT, 0);
-  if (nq == 0) { R->r.assemble(0, nullptr, nullptr, nullptr, nullptr); *out = R; return XM_OK; }
+  if (nq == 0) { R->r.assemble(0, nullptr, nullptr, nullptr, nullptr); R->serial = h->batch_serial; R->nq = 0; *out = R_owner.release(); return XM_OK; }
   // first_seq = exclusive scan of n_seqs
   const int chunk = 4096;
   int n_chunks = (nq + chunk - 1) / chunk;
@@ -1169,7 +1195,7 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
     CK(cudaStreamSynchronize(st));
     R->r.slab = (const char*)R->slab;
     if (host_times) fprintf(stderr, "[xm]   csr assembly + slab D2H (%.0f MB): %.1f ms\n", (double)slab_bytes / 1e6, now_ms() - t_csr0);
-    h->last_batch = L.batch; R->serial = ++h->batch_serial; R->nq = nq;
+    h->last_batch = L.batch; R->serial = h->batch_serial; R->nq = nq;
     R->r.stats[XM_STAT_D2H_BYTES] = (int64_t)(slab_bytes + sizeof(misc) + 32);
   }
   float ms = 0;
@@ -1185,7 +1211,7 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
   R->r.stats[XM_STAT_STRAIGHT] = (int64_t)misc[6]; R->r.stats[XM_STAT_PATH_CALLS] = (int64_t)misc[7]; R->r.stats[XM_STAT_PATH_STEPS] = (int64_t)misc[8];
   R->r.stats[XM_STAT_PATH_CELLS] = (int64_t)misc[9];
   for (int i = 0; i < 7; i++) R->r.stats[XM_STAT_CYC_SEED + i] = (int64_t)misc[10 + i];
-  *out = R;
+  *out = R_owner.release();
   const int32_t* q_status = (const int32_t*)(R->r.slab + R->r.slab_off[9]);
   for (int i = 0; i < nq; i++) if (q_status[i] != 0) { h->err = "at least one query could not be aligned on the device (see q_status)"; return XM_ERR_QUERY; }
   return XM_OK;
@@ -1193,6 +1219,7 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
 
 int xm_align_batch(xm_handle* h, int32_t nq, const uint16_t* packed4, const int64_t* seq_word_off, const int32_t* seq_len, const uint8_t* n_seqs,
                    const double* expected_inner, const double* per_penalty, xm_results** out) {
+  if (out) *out = nullptr;
   if (!h || nq < 0 || !out || (nq > 0 && (!packed4 || !seq_word_off || !seq_len || !n_seqs))) return XM_ERR_ARG;
   const bool host_times = getenv("XM_HOST_TIMES") != nullptr;
   const double t_in = now_ms();
@@ -1202,8 +1229,10 @@ int xm_align_batch(xm_handle* h, int32_t nq, const uint16_t* packed4, const int6
   int max_len = 1;
   for (long long s = 0; s < n_seqs_total; s++) if (seq_len[s] > max_len) max_len = seq_len[s];
   int64_t n_words = nq > 0 ? seq_word_off[n_seqs_total] : 0;
-  std::vector<double> zeros;
-  if (!expected_inner || !per_penalty) { zeros.assign((size_t)nq + 1, 0.0); }
+  // Query.java:17-30 defaults for hosts that pass no spacing model: expected inner distance 0, one base of deviation per unit penalty
+  std::vector<double> zeros, ones;
+  if (!expected_inner) zeros.assign((size_t)nq + 1, 0.0);
+  if (!per_penalty) ones.assign((size_t)nq + 1, 1.0);
   if (!h->d_packed.ensure((size_t)n_words * 2 + 16) || !h->d_seq_word_off.ensure(((size_t)n_seqs_total + 1) * 8) || !h->d_seq_len.ensure((size_t)n_seqs_total * 4 + 16) ||
       !h->d_n_seqs.ensure((size_t)nq + 16) || !h->d_expected.ensure((size_t)nq * 8 + 16) || !h->d_per.ensure((size_t)nq * 8 + 16)) { h->err = "out of device memory"; return XM_ERR_CUDA; }
   cudaStream_t st = h->stream;
@@ -1213,7 +1242,7 @@ int xm_align_batch(xm_handle* h, int32_t nq, const uint16_t* packed4, const int6
     CK(cudaMemcpyAsync(h->d_seq_len.p, seq_len, (size_t)n_seqs_total * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_n_seqs.p, n_seqs, (size_t)nq, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_expected.p, expected_inner ? expected_inner : zeros.data(), (size_t)nq * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->d_per.p, per_penalty ? per_penalty : zeros.data(), (size_t)nq * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_per.p, per_penalty ? per_penalty : ones.data(), (size_t)nq * 8, cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
   }
   const double t_h2d = now_ms();
@@ -1228,9 +1257,9 @@ int xm_format_sam(xm_handle* h, xm_results* r, const char* seq_names, const int6
                   const char** text, int64_t* n_bytes) {
   if (!h || !r || !seq_names || !seq_name_off || !contig_names || !contig_name_off || !text || !n_bytes) return XM_ERR_ARG;
   CK(cudaSetDevice(h->device));
-  if (r->serial != h->batch_serial || r->r.slab == nullptr) { h->err = "xm_format_sam: the results are not those of the handle's latest xm_align_batch (their device copy is gone)"; return XM_ERR_STATE; }
   const int nq = r->nq;
   *text = ""; *n_bytes = 0;
+  if (r->serial != h->batch_serial || (nq > 0 && r->r.slab == nullptr)) { h->err = "xm_format_sam: the results are not those of the handle's latest xm_align_batch (their device copy is gone)"; return XM_ERR_STATE; }
   if (nq == 0) return XM_OK;
   cudaStream_t st = h->stream;
   // number of sequences = first_seq[nq] on the device; the host passes name offsets for all of them

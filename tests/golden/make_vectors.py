@@ -308,6 +308,58 @@ symmetry_cases = ["A", "C", "G", "T", "ACGTAACCGGTTACAGATCG",
 basepair_cases = [dict(q="A", r="C", penalty="mutation"), dict(q="A", r="N", penalty="ambiguity"),
                   dict(q="A", r="M", penalty="ambiguity/3")]
 
+
+# --- T/MutationsWriter_Test.java:18-133: seven exact mutations tables (bodies; metadata lines are stripped by the test itself, :145-155) ---
+# buildMutations (:167-203): reference "ref" + its reverse complement (new SequenceDatabase(reference, true)), default HashBlock_Database,
+# DuplicationDetector(db, 1, 2, 2, 1), makeAlignmentParameters (:205-216) = params() above, MatchDatabase(queryEndFraction), query "query".
+_MP = params()
+mutations_cases = [
+    dict(name="testNoMutations", cite="T/MutationsWriter_Test.java:18-29", query="ACGTA", reference="ACGTAAAAAAAAAAAA", filter={}, end_fraction=0, expected=""),
+    dict(name="testOneMutation", cite="T/MutationsWriter_Test.java:31-44", query="AACGTT", reference="AACGTAAAAA", filter={}, end_fraction=0,
+         expected="ref\t6\tA\tT\t1\t1\n"),
+    dict(name="testConsecutiveMutations", cite="T/MutationsWriter_Test.java:46-60", query="ACGTTTAAACCGG", reference="ACGTAAAAACCGG", filter={}, end_fraction=0,
+         expected="ref\t5\tA\tT\t1\t1\nref\t6\tA\tT\t1\t1\n"),
+    dict(name="testInsertion", cite="T/MutationsWriter_Test.java:62-75", query="ACGGACTTACGTCGTTAACCACGA", reference="ACGCTTACGTCGTTAACCACGA", filter={}, end_fraction=0,
+         expected="ref\t3\t--\tGA\t1\t1\n"),
+    dict(name="testDeletion", cite="T/MutationsWriter_Test.java:77-90", query="CACGTAACCGGTTATT", reference="CACGTAAGACCGGTTATT", filter={}, end_fraction=0,
+         expected="ref\t7\tAG\t--\t1\t1\n"),
+    dict(name="testIgnoringMutationWithLowDepth/filtered", cite="T/MutationsWriter_Test.java:92-105", query="ACGTAACTCCGGCTC", reference="ACGTACGTCCGGCTC",
+         filter=dict(minSNPTotalDepth=2), end_fraction=0, expected=""),
+    dict(name="testIgnoringMutationWithLowDepth/unfiltered", cite="T/MutationsWriter_Test.java:107-112", query="ACGTAACTCCGGCTC", reference="ACGTACGTCCGGCTC",
+         filter={}, end_fraction=0, expected="ref\t6\tC\tA\t1\t1\nref\t7\tG\tC\t1\t1\n"),
+    dict(name="testIgnoringIndelNearQueryEnd/filtered", cite="T/MutationsWriter_Test.java:114-128", query="CCTAACGTAACTCTGGCCGCAA", reference="AGGAACCTACGTAACTCTGGCCGCAA",
+         filter=dict(minIndelTotalStartDepth=1), end_fraction=0.5, expected=""),
+    dict(name="testIgnoringIndelNearQueryEnd/unfiltered", cite="T/MutationsWriter_Test.java:130-133", query="CCTAACGTAACTCTGGCCGCAA", reference="AGGAACCTACGTAACTCTGGCCGCAA",
+         filter={}, end_fraction=0, expected="ref\t8\t-\tA\t1\t1\n"),
+]
+for _c in mutations_cases:
+    _c["params"] = _MP
+    _c["dup"] = dict(min_len=1, max_len=2, min_copies=2, window=1)
+
+# --- T/MatchDatabase_Test.java:13-69: hand-built alignments, every reference position must count exactly 1 ---
+match_database_cases = [
+    dict(name="testQueryEndingWithMismatch", cite="T/MatchDatabase_Test.java:13-35", reference="AACCACGA", seqs=["AACCACGT"],
+         alignments=[dict(b_start=0, length=8)], end_fraction=0),
+    dict(name="testOverlappingPairedEndQueries", cite="T/MatchDatabase_Test.java:37-69", reference="AACCACGATTAC", seqs=["AACCACGA", "CACGATTAC"],
+         alignments=[dict(b_start=0, length=8), dict(b_start=3, length=9)], end_fraction=0),
+]
+
+# --- QVT/VcfWriter_Test.java:18-80: VCF bodies from hand-built single-block alignments (SAM "name1 0 contig1 1 255 <n>M") ---
+vcf_cases = [
+    dict(name="simpleTest", cite="QVT/VcfWriter_Test.java:18-34", reference="ACGTAAAAACGTAAAA", seq="ACGT", support=True,
+         expected="contig1\t1\tA\t.\t1\t1,0\t0,0\t.\ncontig1\t2\tC\t.\t1\t1,0\t0,0\t.\ncontig1\t3\tG\t.\t1\t1,0\t0,0\t.\ncontig1\t4\tT\t.\t1\t1,0\t0,0\t.\n"),
+    dict(name="mutationTest", cite="QVT/VcfWriter_Test.java:36-53", reference="ACGTAAAAA", seq="ACGTT", support=True,
+         expected="contig1\t1\tA\t.\t1\t1,0\t0,0\t.\ncontig1\t2\tC\t.\t1\t1,0\t0,0\t.\ncontig1\t3\tG\t.\t1\t1,0\t0,0\t.\ncontig1\t4\tT\t.\t1\t1,0\t0,0\t.\n"
+                  "contig1\t5\tA\tT\t1\t0,0;1,0\t0,0;0,0\tACGT[T]\n"),
+    dict(name="mutationWithoutSupportReads", cite="QVT/VcfWriter_Test.java:55-72", reference="ACGTAAAAA", seq="ACGTT", support=False,
+         expected="contig1\t1\tA\t.\t1\t1,0\t0,0\ncontig1\t2\tC\t.\t1\t1,0\t0,0\ncontig1\t3\tG\t.\t1\t1,0\t0,0\ncontig1\t4\tT\t.\t1\t1,0\t0,0\n"
+                  "contig1\t5\tA\tT\t1\t0,0;1,0\t0,0;0,0\n"),
+    dict(name="oneReadWithMultipleAlignments", cite="QVT/VcfWriter_Test.java:126-145", reference="ACGTAAAAACGTAAAA", seq="ACGT", support=True, starts=[0, 8],
+         expected="".join("contig1\t%d\t%s\t.\t0.5\t0.5,0\t0,0\t.\n" % (p, c) for p, c in zip([1, 2, 3, 4, 9, 10, 11, 12], "ACGTACGT"))),
+    dict(name="readWithThreeAlignments", cite="QVT/VcfWriter_Test.java:181-205", reference="ACGTAAAAACGTCCCCACGT", seq="ACGT", support=True, starts=[0, 8, 16],
+         expected="".join("contig1\t%d\t%s\t.\t0.33\t0.33,0\t0,0\t.\n" % (p, c) for p, c in zip([1, 2, 3, 4, 9, 10, 11, 12, 17, 18, 19, 20], "ACGTACGTACGT"))),
+]
+
 # --- examples/ (config 1): inputs only; the reference ships no expected output (examples/.gitignore) ---
 examples = dict(
     cite="examples/reference.fasta, examples/queries.fasta, examples/test.sh:14",
@@ -321,7 +373,8 @@ examples = dict(
 out = dict(source="mathjeff/Mapper @ ae7f346a JUnit tests (transcribed; see make_vectors.py)",
            api_cases=api_cases, sam_cases=sam_cases, path_aligner_cases=path_cases, hashblock_aligner_cases=hashblock_cases,
            counting_path_cases=counting_cases, paths_counter_cases=paths_counter_cases, symmetry_cases=symmetry_cases,
-           basepair_cases=basepair_cases, examples=examples)
+           basepair_cases=basepair_cases, examples=examples,
+           mutations_cases=mutations_cases, match_database_cases=match_database_cases, vcf_cases=vcf_cases)
 
 if __name__ == "__main__":
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "junit_vectors.json")
