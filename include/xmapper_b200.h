@@ -165,20 +165,38 @@ void xm_release_results(xm_results* r);
 int xm_format_sam(xm_handle* h, xm_results* r, const char* seq_names, const int64_t* seq_name_off, const char* contig_names, const int64_t* contig_name_off,
                   const char** text, int64_t* n_bytes);
 
-/* Per-position count planes for --out-vcf/--out-mutations (QV/MatchDatabase.java:16-59, QV/Alignments.java:89-150,
- * QV/DirectionalAlignments.java:20-55): reference-base depth in int32 units of 1/100 per
- * [region: 0 middle, 1 end][direction: 0 forward, 1 reverse][position].  xm_counts_enable allocates the planes on
- * the device; every later xm_align_batch accumulates into them; xm_counts_device_ptr exposes the device buffer so
- * the multi-GPU driver can all-reduce it in place with NCCL (int32 sum, exact and order-free). */
+/* Count accumulation for --out-vcf/--out-mutations (replaces the MatchDatabase listener: QV/MatchDatabase.java:16-59,
+ * QV/Alignments.java:89-156, QV/DirectionalAlignments.java:20-96).  xm_counts_enable allocates the state on the device; every
+ * later xm_align_batch accumulates into it:
+ *   - dense planes: reference-base depth in int32 units of 1/100 per [region: 0 middle, 1 end][direction: 0 forward, 1 reverse][position]
+ *     (DirectionalAlignments.referenceCounts), read with xm_counts_fetch / xm_counts_device_ptr;
+ *   - a sparse table of variants (alternates, deletions, insertion columns: DirectionalAlignments.alternates), read with
+ *     xm_variants_fetch: entry i has
+ *       keys[i]     = (global forward position) << 21 | region << 20 | direction << 19 | (insertion column + 1) << 3 | allele
+ *                     global forward position = (sum of the lengths of the contigs before it) + position; insertion column + 1 == 0:
+ *                     an allele AT the position (substitution or deletion), k + 1: column k of the insertion after the position;
+ *                     allele = index into "ACGTN-" (AlignmentPosition_DirectionCounts.makeKeys)
+ *       counts[i]   = Variant.count (sum of (int)(weight * 100))
+ *       ex_gid[i]   = example read (Variant.exampleSequence): global sequence id << 1 | 1 if it is the "-rev" view
+ *       ex_index[i] = Variant.exampleIndex (negative: deletion)
+ *     entries are sorted by key; the example is the one DirectionalAlignments.betterExample (:63-96) would have kept.
+ * xm_counts_batch_info (optional, before an xm_align_batch): the global id of the first sequence of the next batch (default: the
+ * sequences are numbered in the order the handle receives them; a host that shards reads over GPUs passes the real ids) and, per
+ * sequence, a key that orders the sequences like their names (Sequence.getName().compareTo, e.g. the rank of the name among the
+ * names of the run; NULL: equal names assumed, ties fall to the id as in :92-95). */
 int xm_counts_enable(xm_handle* h, double query_end_fraction);
+int xm_counts_batch_info(xm_handle* h, int64_t first_sequence_id, const int64_t* seq_order_key, int64_t n_sequences);
 int xm_counts_device_ptr(xm_handle* h, void** d_ptr, int64_t* n_int32);
 int xm_counts_fetch(xm_handle* h, int32_t contig, int32_t* out /* 4 * contig length */);
+int xm_variants_fetch(xm_handle* h, int64_t* n, uint64_t* keys, int32_t* counts, int64_t* ex_gid, int32_t* ex_index /* NULL arrays: size query */);
 
 /* Multi-GPU reduction of the count planes inside the library (NCCL over NVLink; libnccl.so.2 is loaded at run time).
  * One process (or thread) per GPU, as the reference runs one AlignerWorker per thread and MatchDatabase merges them
  * (QV/MatchDatabase.java:16-59): rank 0 calls xm_comm_unique_id and hands the 128 bytes to the others by any means,
- * every rank calls xm_comm_init on its handle (collective), and after the last batch xm_counts_reduce (collective, blocking)
- * leaves the int32 sum over all ranks in every rank's planes (exact and order-free); xm_counts_fetch then reads them. */
+ * every rank calls xm_comm_init on its handle (collective), and xm_counts_reduce (collective, blocking) leaves the int32 sum over
+ * all ranks in every rank's planes (ncclAllReduce: exact and order-free) and the union of all ranks' variant tables, reduced by
+ * key, in every rank's table (sizes all-gathered, entries exchanged with grouped ncclBroadcast, device sort + reduce-by-key).
+ * Call it once, after the last batch: a second call would add the already-summed planes again. */
 int xm_comm_unique_id(uint8_t* id128);
 int xm_comm_init(xm_handle* h, int32_t n_ranks, int32_t rank, const uint8_t* id128);
 int xm_counts_reduce(xm_handle* h);

@@ -16,7 +16,7 @@ EXPORTS = ["xm_create", "xm_destroy", "xm_last_error", "xm_set_reference", "xm_s
            "xm_build_index", "xm_get_index_length", "xm_index_info", "xm_set_duplications", "xm_build_duplications",
            "xm_get_duplications", "xm_align_batch", "xm_align_batch_device", "xm_results_array", "xm_release_results",
            "xm_counts_enable", "xm_counts_device_ptr", "xm_counts_fetch", "xm_format_sam",
-           "xm_comm_unique_id", "xm_comm_init", "xm_counts_reduce"]
+           "xm_comm_unique_id", "xm_comm_init", "xm_counts_reduce", "xm_counts_batch_info", "xm_variants_fetch"]
 
 RESULT_ARRAYS = [("q_comp_off", np.int64), ("comp_choice_off", np.int64), ("choice_sa_off", np.int64), ("sa_block_off", np.int64),
                  ("choice_f64", np.float64), ("sa_f64", np.float64), ("choice_inner", np.int32), ("sa_contig", np.int32),
@@ -236,6 +236,26 @@ class XMapper:
     # ---- per-position counts ----
     def counts_enable(self, query_end_fraction=0.1):
         self._ok(self.L.xm_counts_enable(self.h, C.c_double(query_end_fraction)))
+
+    def counts_batch_info(self, first_sequence_id, order_keys=None):
+        """Before align_batch: global id of the batch's first sequence and (optionally) a name-order key per sequence."""
+        if order_keys is None:
+            self._ok(self.L.xm_counts_batch_info(self.h, C.c_int64(first_sequence_id), None, C.c_int64(0)))
+        else:
+            k = np.ascontiguousarray(order_keys, dtype=np.int64)
+            self._ok(self.L.xm_counts_batch_info(self.h, C.c_int64(first_sequence_id), _ptr(k), C.c_int64(len(k))))
+
+    def variants_fetch(self):
+        """The sparse variant table, decoded: dict of arrays gpos, region, dir, ins (-1: at the position), allele, count, ex_gid, ex_rev, ex_index."""
+        n = C.c_int64()
+        self._ok(self.L.xm_variants_fetch(self.h, C.byref(n), None, None, None, None))
+        m = max(n.value, 1)
+        keys, counts, gid, idx = np.zeros(m, np.uint64), np.zeros(m, np.int32), np.zeros(m, np.int64), np.zeros(m, np.int32)
+        self._ok(self.L.xm_variants_fetch(self.h, C.byref(n), _ptr(keys), _ptr(counts), _ptr(gid), _ptr(idx)))
+        keys, counts, gid, idx = keys[:n.value], counts[:n.value], gid[:n.value], idx[:n.value]
+        return dict(key=keys, gpos=(keys >> np.uint64(21)).astype(np.int64), region=((keys >> np.uint64(20)) & np.uint64(1)).astype(np.int32),
+                    dir=((keys >> np.uint64(19)) & np.uint64(1)).astype(np.int32), ins=((keys >> np.uint64(3)) & np.uint64(0xFFFF)).astype(np.int32) - 1,
+                    allele=(keys & np.uint64(7)).astype(np.int32), count=counts, ex_gid=gid >> 1, ex_rev=(gid & 1).astype(np.int32), ex_index=idx)
 
     def counts_device_ptr(self):
         p, n = C.c_void_p(), C.c_int64()

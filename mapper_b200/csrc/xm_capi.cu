@@ -535,71 +535,6 @@ __global__ void xm_sam_kernel(SamD S, BatchD batch, int nq) {
   if (!WRITE) S.q_len[q] = o.n;
 }
 
-// ---- per-position reference-base depth planes (QV/MatchDatabase.java:34-59, QV/Alignments.java:89-156,
-// QV/WeightedAlignment.java:19-28, QV/QueryAlignment.java:97-120,203-214, QV/DirectionalAlignments.java:20-28) ----
-// One thread per query; walks every sequence alignment of every choice and adds (int)(weight * 100) for each
-// aligned reference position whose (unambiguous) query base equals the reference base.  All weights are Java
-// floats: weight = 1f / numChoices, times 1f / numAlignmentsCoveringIndexB.
-struct CountsD {
-  int32_t* planes;            // [contig_off[c]*4 + ((region*2+dir)*len + pos)]   region: 0 middle, 1 near a query end; dir: 0 forward, 1 reverse
-  const int64_t* contig_off;  // prefix of contig lengths
-  double end_fraction;        // MatchDatabase.queryEndFraction
-};
-__global__ void xm_counts_kernel(RefD ref, BatchD batch, OutArena out, CountsD C, int n_queries) {
-  int qi = blockIdx.x * blockDim.x + threadIdx.x;
-  if (qi >= n_queries) return;
-  const OutQuery& oq = out.q[qi];
-  if (oq.status != 0) return;
-  long long s0 = batch.first_seq[qi];
-  for (int comp = 0; comp < oq.n_comp; comp++) {
-    int nch = oq.n_choice[comp];
-    if (nch < 1) continue;
-    const float weight = 1.0f / (float)nch;  // MatchDatabase.groupByReference :40
-    for (int k = 0; k < nch; k++) {
-      const OutChoice& ch = out.choices[oq.choice_first[comp] + k];
-      // QueryAlignment.computeOverlap :203-214 (alignments found by the aligner are reference-contiguous)
-      int min_overlap = -1, max_overlap = -1;
-      for (int s = 0; s < ch.n_sa; s++) {
-        const OutSA& o = out.sas[ch.sa_first + s];
-        const int32_t* ob = out.blocks + 4 * o.block_first;
-        int mn = ob[1], mx = ob[4 * (o.n_blocks - 1) + 1] + ob[4 * (o.n_blocks - 1) + 3];
-        if (min_overlap < 0 || mn >= min_overlap) min_overlap = mn;
-        if (max_overlap < 0 || mx <= max_overlap) max_overlap = mx;
-      }
-      for (int s = 0; s < ch.n_sa; s++) {
-        const OutSA& sa = out.sas[ch.sa_first + s];
-        int mate = (oq.n_comp == 2) ? comp : s;
-        SeqView qv; qv.w = batch.packed + batch.seq_word_off[s0 + mate]; qv.len = batch.seq_len[s0 + mate]; qv.rc = sa.reversed; qv.bytes = nullptr;
-        SeqView rv = ref.contig(sa.contig, 0);
-        const int32_t* bl0 = out.blocks + 4 * sa.block_first;
-        const int first_start_a = bl0[0];
-        const int last_end_a = bl0[4 * (sa.n_blocks - 1)] + bl0[4 * (sa.n_blocks - 1) + 2];
-        const double end_limit = (double)qv.len * C.end_fraction;  // Alignments.isNearQueryEnd :153-156
-        long long base = C.contig_off[sa.contig] * 4;
-        const int dir = sa.reversed ? 1 : 0;
-        for (int b = 0; b < sa.n_blocks; b++) {
-          const int32_t* bl = bl0 + 4 * b;
-          int a0 = bl[0], b0 = bl[1], al = bl[2], blen = bl[3];
-          if (al != blen) continue;  // insertions / deletions are variant records, not reference-base depth
-          for (int i = 0; i < al; i++) {
-            int qa = a0 + i, rb = b0 + i;
-            uint8_t code = qv.at(qa);
-            if (bp_is_ambiguous(code)) continue;         // DirectionalAlignments.add :21-25
-            if (code != rv.at(rb)) continue;             // alternates are variant records
-            int num = ch.n_sa;
-            if (ch.n_sa >= 2 && (rb < min_overlap || rb >= max_overlap)) num = 1;  // QueryAlignment.getNumAlignmentsCoveringIndexB :97-111
-            float pos_w = (num != 0) ? 1.0f / (float)num : 0.0f;
-            float wgt = weight * pos_w;
-            int dist = min(qa - first_start_a, last_end_a - qa - 1);
-            int region = ((double)dist < end_limit) ? 1 : 0;
-            atomicAdd(&C.planes[base + (long long)(region * 2 + dir) * rv.len + rb], (int32_t)(wgt * 100.0f));
-          }
-        }
-      }
-    }
-  }
-}
-
 // ---------------------------------------------------------------- handle
 struct DevBuf {
   void* p = nullptr; size_t cap = 0;
@@ -614,6 +549,8 @@ struct DevBuf {
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
+
+#include "xm_counts.cuh"
 
 // pinned host slabs for results, recycled between batches (cudaHostAlloc of 100 MB costs tens of ms)
 struct PinnedPool {
@@ -653,6 +590,10 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool ok = false;
@@ -668,9 +609,13 @@ static NcclApi& nccl_api() {
     a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.lib, "ncclGetUniqueId");
     a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.lib, "ncclCommInitRank");
     a.AllReduce = (decltype(a.AllReduce))dlsym(a.lib, "ncclAllReduce");
+    a.Broadcast = (decltype(a.Broadcast))dlsym(a.lib, "ncclBroadcast");
+    a.AllGather = (decltype(a.AllGather))dlsym(a.lib, "ncclAllGather");
+    a.GroupStart = (decltype(a.GroupStart))dlsym(a.lib, "ncclGroupStart");
+    a.GroupEnd = (decltype(a.GroupEnd))dlsym(a.lib, "ncclGroupEnd");
     a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.lib, "ncclCommDestroy");
     a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.lib, "ncclGetErrorString");
-    a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.CommDestroy && a.GetErrorString;
+    a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.Broadcast && a.AllGather && a.GroupStart && a.GroupEnd && a.CommDestroy && a.GetErrorString;
   });
   return a;
 }
@@ -701,7 +646,12 @@ struct xm_handle {
   // counts
   bool counts_enabled = false; double end_fraction = 0.1;
   DevBuf d_planes, d_contig_off; long long n_plane_ints = 0;
-  ncclComm_t comm = nullptr; int comm_ranks = 0;   // xm_comm_init: the communicator xm_counts_reduce uses
+  // sparse variant table (xm_counts.cuh): recs[0, var_n) = reduced entries followed by raw records of the batches since the last reduce
+  DevBuf d_var, d_var_n, d_order, d_var_sizes; VarScratch var_scratch;
+  unsigned long long var_n = 0, var_cap = 0, var_reduced_n = 0;
+  long long next_gid = 0;                       // global id of the first sequence of the next batch (xm_counts_batch_info overrides it)
+  bool have_batch_info = false; long long info_first_gid = 0; std::vector<int64_t> info_order;
+  ncclComm_t comm = nullptr; int comm_ranks = 0, comm_rank = 0;   // xm_comm_init: the communicator xm_counts_reduce uses
 };
 
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -804,7 +754,8 @@ void xm_destroy(xm_handle* h) {
   if (h->comm && nccl_api().ok) { nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
   DevBuf* bufs[] = {&h->d_words, &h->d_word_off, &h->d_len, &h->d_gstart, &h->d_tables, &h->d_dup_off, &h->d_dup_starts, &h->d_packed, &h->d_seq_word_off,
                     &h->d_seq_len, &h->d_n_seqs, &h->d_expected, &h->d_per, &h->d_first_seq, &h->d_chunk, &h->d_q, &h->d_choices, &h->d_sas, &h->d_blocks,
-                    &h->d_misc, &h->d_ids_a, &h->d_ids_b, &h->d_ids_full, &h->d_ws, &h->d_qcycles, &h->d_csr_cnt, &h->d_csr_base, &h->d_csr_tmp, &h->d_csr_slab, &h->d_keys_a, &h->d_keys_b, &h->d_sort_tmp, &h->d_big, &h->d_big_busy, &h->d_sam_len, &h->d_sam_text, &h->d_sam_names, &h->d_sam_name_off, &h->d_sam_cnames, &h->d_sam_cname_off, &h->d_planes, &h->d_contig_off};
+                    &h->d_misc, &h->d_ids_a, &h->d_ids_b, &h->d_ids_full, &h->d_ws, &h->d_qcycles, &h->d_csr_cnt, &h->d_csr_base, &h->d_csr_tmp, &h->d_csr_slab, &h->d_keys_a, &h->d_keys_b, &h->d_sort_tmp, &h->d_big, &h->d_big_busy, &h->d_sam_len, &h->d_sam_text, &h->d_sam_names, &h->d_sam_name_off, &h->d_sam_cnames, &h->d_sam_cname_off, &h->d_planes, &h->d_contig_off, &h->d_var, &h->d_var_n, &h->d_order, &h->d_var_sizes,
+                    &h->var_scratch.keys_a, &h->var_scratch.keys_b, &h->var_scratch.idx_a, &h->var_scratch.idx_b, &h->var_scratch.gathered, &h->var_scratch.out_keys, &h->var_scratch.n_out, &h->var_scratch.tmp};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : h->d_buckets) b.release();
   for (auto& b : h->d_positions) b.release();
@@ -982,6 +933,62 @@ int xm_get_duplications(xm_handle* h, int32_t contig, int32_t* n, int32_t* start
   return XM_OK;
 }
 
+
+// MatchDatabase.addAlignments for the batch whose results sit in L.out: reference-base planes + raw variant records.
+static int var_reduce_now(xm_handle* h) {
+  if (h->var_n == h->var_reduced_n) return XM_OK;
+  unsigned long long n_out = 0;
+  if (!var_sort_reduce((VarRec*)h->d_var.p, h->var_n, h->var_scratch, h->stream, &n_out, h->err)) return XM_ERR_CUDA;
+  h->var_n = n_out; h->var_reduced_n = n_out;
+  return XM_OK;
+}
+static int var_reserve(xm_handle* h, unsigned long long want) {   // keeps recs[0, var_n)
+  if (want <= h->var_cap) return XM_OK;
+  unsigned long long ncap = want + want / 2 + 65536;
+  void* np = nullptr;
+  if (cudaMalloc(&np, (size_t)ncap * sizeof(VarRec)) != cudaSuccess) { cudaGetLastError(); h->err = "out of device memory (variant table)"; return XM_ERR_CUDA; }
+  if (h->var_n) cudaMemcpyAsync(np, h->d_var.p, (size_t)h->var_n * sizeof(VarRec), cudaMemcpyDeviceToDevice, h->stream);
+  cudaStreamSynchronize(h->stream);
+  if (h->d_var.p) cudaFree(h->d_var.p);
+  h->d_var.p = np; h->d_var.cap = (size_t)ncap * sizeof(VarRec); h->var_cap = ncap;
+  return XM_OK;
+}
+static int accumulate_counts(xm_handle* h, const LaunchD& L, int nq, long long n_seqs_total, int& launches) {
+  cudaStream_t st = h->stream;
+  CountsD C; C.planes = (int32_t*)h->d_planes.p; C.contig_off = (const int64_t*)h->d_contig_off.p; C.end_fraction = h->end_fraction;
+  VarOut V; V.order = nullptr;
+  V.first_gid = h->have_batch_info ? h->info_first_gid : h->next_gid;
+  if (h->have_batch_info && !h->info_order.empty()) {
+    if ((long long)h->info_order.size() != n_seqs_total) { h->err = "xm_counts_batch_info: order keys do not match the number of sequences of the batch"; return XM_ERR_ARG; }
+    if (!h->d_order.ensure((size_t)n_seqs_total * 8)) { h->err = "out of device memory"; return XM_ERR_CUDA; }
+    CK(cudaMemcpyAsync(h->d_order.p, h->info_order.data(), (size_t)n_seqs_total * 8, cudaMemcpyHostToDevice, st));
+    V.order = (const int64_t*)h->d_order.p;
+  }
+  h->next_gid = V.first_gid + n_seqs_total; h->have_batch_info = false;
+  int rc = var_reserve(h, h->var_n + (unsigned long long)n_seqs_total * 4 + 4096);   // ~1.6 records per 150 bp read at 1 % differences
+  if (rc != XM_OK) return rc;
+  if (!h->d_var_n.ensure(16)) { h->err = "out of device memory"; return XM_ERR_CUDA; }
+  bool planes = true;
+  while (true) {
+    V.recs = (VarRec*)h->d_var.p; V.n = (unsigned long long*)h->d_var_n.p; V.cap = h->var_cap;
+    CK(cudaMemcpyAsync(h->d_var_n.p, &h->var_n, 8, cudaMemcpyHostToDevice, st));
+    if (planes) xm_counts_kernel<true><<<(nq + 127) / 128, 128, 0, st>>>(h->ref, L.batch, L.out, C, V, nq);
+    else xm_counts_kernel<false><<<(nq + 127) / 128, 128, 0, st>>>(h->ref, L.batch, L.out, C, V, nq);
+    launches++;
+    unsigned long long n_after = 0;
+    CK(cudaMemcpyAsync(&n_after, h->d_var_n.p, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (n_after <= h->var_cap) { h->var_n = n_after; break; }
+    // more records than room: grow and emit the batch's records again (the planes were already updated)
+    rc = var_reserve(h, n_after);
+    if (rc != XM_OK) return rc;
+    planes = false;
+  }
+  if (h->var_n - h->var_reduced_n > (1ull << 24) && h->var_n - h->var_reduced_n > h->var_reduced_n / 2) return var_reduce_now(h);
+  return XM_OK;
+}
+
 int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, int64_t n_words, const int64_t* d_seq_word_off, const int32_t* d_seq_len,
                           const uint8_t* d_n_seqs, const double* d_expected, const double* d_per, int32_t max_seq_len, xm_results** out) {
   if (out) *out = nullptr;
@@ -1150,9 +1157,8 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
     ids = (const int32_t*)h->d_ids_a.p; n_ids = counts[2]; next_ids = (int32_t*)h->d_ids_b.p;
   }
   if (h->counts_enabled) {
-    CountsD C; C.planes = (int32_t*)h->d_planes.p; C.contig_off = (const int64_t*)h->d_contig_off.p; C.end_fraction = h->end_fraction;
-    xm_counts_kernel<<<(nq + 127) / 128, 128, 0, st>>>(h->ref, L.batch, L.out, C, nq);
-    launches++;
+    int rc2 = accumulate_counts(h, L, nq, n_seqs_total, launches);
+    if (rc2 != XM_OK) return rc2;
   }
   // D2H
   unsigned long long misc[20];
@@ -1319,6 +1325,7 @@ int xm_counts_enable(xm_handle* h, double query_end_fraction) {
   CK(cudaMemset(h->d_planes.p, 0, (size_t)h->n_plane_ints * 4));
   CK(cudaMemcpy(h->d_contig_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice));
   h->end_fraction = query_end_fraction; h->counts_enabled = true;
+  h->var_n = 0; h->var_reduced_n = 0; h->next_gid = 0; h->have_batch_info = false;
   return XM_OK;
 }
 int xm_comm_unique_id(uint8_t* id128) {
@@ -1340,7 +1347,7 @@ int xm_comm_init(xm_handle* h, int32_t n_ranks, int32_t rank, const uint8_t* id1
   ncclUniqueId id; memcpy(&id, id128, 128);
   ncclResult_t r = N.CommInitRank(&h->comm, n_ranks, id, rank);
   if (r != ncclSuccess) { h->err = std::string("ncclCommInitRank: ") + N.GetErrorString(r); h->comm = nullptr; return XM_ERR_CUDA; }
-  h->comm_ranks = n_ranks;
+  h->comm_ranks = n_ranks; h->comm_rank = rank;
   return XM_OK;
 }
 int xm_counts_reduce(xm_handle* h) {
@@ -1348,10 +1355,73 @@ int xm_counts_reduce(xm_handle* h) {
   if (!h->comm) { h->err = "xm_counts_reduce: xm_comm_init was not called"; return XM_ERR_STATE; }
   NcclApi& N = nccl_api();
   CK(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
   // int32 sums are exact and order-free: every rank ends with the planes of the whole run (QV/DirectionalAlignments.java:20-28)
-  ncclResult_t r = N.AllReduce(h->d_planes.p, h->d_planes.p, (size_t)h->n_plane_ints, ncclInt32, ncclSum, h->comm, h->stream);
+  ncclResult_t r = N.AllReduce(h->d_planes.p, h->d_planes.p, (size_t)h->n_plane_ints, ncclInt32, ncclSum, h->comm, st);
   if (r != ncclSuccess) { h->err = std::string("ncclAllReduce: ") + N.GetErrorString(r); return XM_ERR_CUDA; }
-  CK(cudaStreamSynchronize(h->stream));
+  // the sparse variant tables: every rank reduces its own, all-gathers the sizes, receives every other rank's entries behind its own
+  // (one broadcast per rank, grouped) and reduces the concatenation - (sum, best example) is associative and commutative, so every
+  // rank ends with the table of the whole run
+  int rc = var_reduce_now(h);
+  if (rc != XM_OK) return rc;
+  const int nr = h->comm_ranks;
+  if (!h->d_var_sizes.ensure((size_t)(nr + 1) * 8)) { h->err = "out of device memory"; return XM_ERR_CUDA; }
+  unsigned long long mine = h->var_n;
+  unsigned long long* d_sizes = (unsigned long long*)h->d_var_sizes.p;
+  CK(cudaMemcpyAsync(d_sizes + nr, &mine, 8, cudaMemcpyHostToDevice, st));
+  r = N.AllGather(d_sizes + nr, d_sizes, 1, ncclUint64, h->comm, st);
+  if (r != ncclSuccess) { h->err = std::string("ncclAllGather: ") + N.GetErrorString(r); return XM_ERR_CUDA; }
+  std::vector<unsigned long long> sizes((size_t)nr);
+  CK(cudaMemcpyAsync(sizes.data(), d_sizes, (size_t)nr * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  unsigned long long total = 0; int me = -1;
+  for (int i = 0; i < nr; i++) total += sizes[(size_t)i];
+  { int rk = 0; /* my rank = the slot that holds my size first; ncclCommUserRank is not loaded, so xm_comm_init recorded it */ rk = h->comm_rank; me = rk; }
+  rc = var_reserve(h, total);
+  if (rc != XM_OK) return rc;
+  if (total > mine) {
+    // layout after the exchange: [mine][rank 0's][rank 1's]... without my own slot
+    VarRec* base = (VarRec*)h->d_var.p;
+    unsigned long long at = mine;
+    N.GroupStart();
+    for (int i = 0; i < nr; i++) {
+      const size_t bytes = (size_t)sizes[(size_t)i] * sizeof(VarRec);
+      if (bytes == 0) continue;
+      if (i == me) r = N.Broadcast(base, base, bytes, ncclUint8, i, h->comm, st);
+      else { r = N.Broadcast(base + at, base + at, bytes, ncclUint8, i, h->comm, st); at += sizes[(size_t)i]; }
+      if (r != ncclSuccess) { N.GroupEnd(); h->err = std::string("ncclBroadcast: ") + N.GetErrorString(r); return XM_ERR_CUDA; }
+    }
+    r = N.GroupEnd();
+    if (r != ncclSuccess) { h->err = std::string("ncclGroupEnd: ") + N.GetErrorString(r); return XM_ERR_CUDA; }
+    h->var_n = total; h->var_reduced_n = 0;
+    rc = var_reduce_now(h);
+    if (rc != XM_OK) return rc;
+  }
+  CK(cudaStreamSynchronize(st));
+  return XM_OK;
+}
+int xm_counts_batch_info(xm_handle* h, int64_t first_sequence_id, const int64_t* seq_order_key, int64_t n_sequences) {
+  if (!h || first_sequence_id < 0 || n_sequences < 0) return XM_ERR_ARG;
+  h->have_batch_info = true; h->info_first_gid = first_sequence_id;
+  h->info_order.clear();
+  if (seq_order_key) h->info_order.assign(seq_order_key, seq_order_key + n_sequences);
+  return XM_OK;
+}
+int xm_variants_fetch(xm_handle* h, int64_t* n, uint64_t* keys, int32_t* counts, int64_t* ex_gid, int32_t* ex_index) {
+  if (!h || !h->counts_enabled) return XM_ERR_STATE;
+  CK(cudaSetDevice(h->device));
+  int rc = var_reduce_now(h);
+  if (rc != XM_OK) return rc;
+  if (n) *n = (int64_t)h->var_n;
+  if (!keys && !counts && !ex_gid && !ex_index) return XM_OK;
+  std::vector<VarRec> host((size_t)h->var_n);
+  if (h->var_n) CK(cudaMemcpy(host.data(), h->d_var.p, (size_t)h->var_n * sizeof(VarRec), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < host.size(); i++) {
+    if (keys) keys[i] = host[i].key;
+    if (counts) counts[i] = host[i].count;
+    if (ex_gid) ex_gid[i] = host[i].ex_gid;
+    if (ex_index) ex_index[i] = host[i].ex_index;
+  }
   return XM_OK;
 }
 int xm_counts_device_ptr(xm_handle* h, void** d_ptr, int64_t* n_int32) {

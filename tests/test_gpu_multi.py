@@ -1,4 +1,5 @@
-"""Two-GPU test of the in-library NCCL reduction of the count planes (xm_comm_init / xm_counts_reduce).  Needs >= 2 GPUs; skipped otherwise."""
+"""Two-GPU test of the in-library NCCL reduction of the count planes and of the sparse variant table (xm_comm_init / xm_counts_reduce:
+ncclAllReduce of the planes, all-gather + device sort/reduce-by-key of the variant entries).  Needs >= 2 GPUs; skipped otherwise."""
 import threading
 
 import numpy as np
@@ -30,9 +31,13 @@ def test_counts_reduce_two_gpus():
 
     # reference: one GPU sees both batches
     g = make(0)
-    for b in batches:
+    firsts = [0, int(batches[0]["n_seqs"].astype(np.int64).sum())]
+    for b, f in zip(batches, firsts):
+        g.counts_batch_info(f)
         g.align_batch(b, strict=True)
     want = [g.counts_fetch(c).copy() for c in range(db.num_contigs())]
+    want_var = g.variants_fetch()
+    assert len(want_var["key"]) > 1000
     g.close()
     # two handles on two GPUs, one batch each, reduced inside the library
     hs = [make(0), make(1)]
@@ -42,6 +47,7 @@ def test_counts_reduce_two_gpus():
     def run(rank):
         try:
             hs[rank].comm_init(2, rank, uid)
+            hs[rank].counts_batch_info(firsts[rank])
             hs[rank].align_batch(batches[rank], strict=True)
             hs[rank].counts_reduce()
         except Exception as e:  # noqa: BLE001
@@ -54,4 +60,7 @@ def test_counts_reduce_two_gpus():
     for rank in range(2):
         for c in range(db.num_contigs()):
             assert np.array_equal(hs[rank].counts_fetch(c), want[c]), (rank, c)
+        have_var = hs[rank].variants_fetch()
+        for k in ("key", "count", "ex_gid", "ex_rev", "ex_index"):
+            assert np.array_equal(have_var[k], want_var[k]), (rank, k)
     [h.close() for h in hs]
