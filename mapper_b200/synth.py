@@ -147,7 +147,7 @@ def simulate_reads(contigs, n_reads, read_len, seed, sub_rate=0.01, indel_rate=0
             frag = COMP[frag[::-1]]
         if paired:
             m1 = _mutate(frag[:read_len + 12], rng, sub_rate, indel_rate)[:read_len]
-            tail = frag[len(frag) - 24 - read_len - 12:len(frag) - 24]
+            tail = frag[max(0, len(frag) - 24 - read_len - 12):len(frag) - 24]  # (a negative start would wrap around to an empty mate)
             m2 = COMP[_mutate(tail, rng, sub_rate, indel_rate)[::-1]][:read_len]
             reads.append(m1)
             reads.append(m2)
@@ -244,3 +244,24 @@ def simulate_reads_fast(contigs, n_reads, read_len, seed, sub_rate=0.01, indel_r
                 expected_inner=np.full(n_reads, inner_mean if paired else 0.0, dtype=np.float64),
                 per_penalty=np.full(n_reads, per_penalty if paired else 1.0, dtype=np.float64),
                 truth=np.stack([cidx, pos, strand], axis=1))
+
+
+def split_queries(reads, max_length):
+    """--split-queries-past-size (M/SequenceSplitter.java:9-38): a read longer than max_length becomes
+    n = (len - 1) // max_length + 1 sub-queries; piece k covers [len * k // n, len * (k + 1) // n).  Host-side, as in the reference
+    (the splitter wraps the FASTA/FASTQ parser); reads: list of uint8 code arrays.  Returns (pieces, parent index per piece)."""
+    pieces, parent = [], []
+    for i, r in enumerate(reads):
+        n = (len(r) - 1) // max_length + 1
+        for k in range(n):
+            pieces.append(r[len(r) * k // n:len(r) * (k + 1) // n])
+            parent.append(i)
+    return pieces, np.array(parent, dtype=np.int64)
+
+
+def batch_from_reads(reads):
+    """Single-sequence queries from a list of uint8 code arrays."""
+    packed, off, slen = pack_reads(reads)
+    n = len(reads)
+    return dict(packed=packed, seq_word_off=off, seq_len=slen, n_seqs=np.ones(n, dtype=np.uint8),
+                expected_inner=np.zeros(n, dtype=np.float64), per_penalty=np.ones(n, dtype=np.float64))

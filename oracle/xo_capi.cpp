@@ -252,6 +252,14 @@ void* xo_align_batch(void* cv, const CParams* cp, int n_queries, const uint16_t*
         for (size_t i = 0; i < n; i++) { own.push_back(makeRC(q.seqs[i])); rcs.push_back(own.back().get()); }
         q.expectedInnerDistance = n > 1 ? expected_inner[qi] : 0;
         q.spacingDeviationPerUnitPenalty = n > 1 ? per_penalty[qi] : 1;
+        bool empty_seq = false;
+        for (size_t i = 0; i < n; i++) if (q.seqs[i]->codes.empty()) empty_seq = true;
+        if (empty_seq) {  // a zero-length sequence: no reference test covers it; both sides refuse it with the same status (the product's Q_INTERNAL)
+          QueryAlns r; r.comps.emplace_back();
+          appendResults(R, r);
+          R.q_status.push_back(-6);
+          continue;
+        }
         try {
           QueryAlns r = w.align(q, rcs);
           appendResults(R, r);
