@@ -1,9 +1,11 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see xo_core.h header).
 // extern "C" surface for ctypes (tests/, bench.py cpu_baseline / --impl reference, smoke()).
 #include "xo_worker.h"
+#include "xo_ancestry.h"
 #include <sstream>
 #include <iomanip>
 #include <cstdlib>
+#include <cstring>
 
 using namespace xo;
 
@@ -14,6 +16,7 @@ struct Ctx {
   std::vector<std::pair<std::string, std::string>> pending;
   std::unique_ptr<Index> index;
   std::unique_ptr<DupDetector> dup;
+  std::vector<std::vector<uint8_t>> ancestors;  // xo_infer_ancestors: forward "-anc" sequences, database order
   std::string lastError;
 };
 
@@ -178,6 +181,21 @@ int xo_create_dup_detector(void* cv, int min_len, int max_len, int min_copies, i
 int xo_dup_detect(void* cv) {
   Ctx* c = (Ctx*)cv;
   try { c->dup->detect(); return 0; } catch (std::exception& e) { c->lastError = e.what(); return -1; }
+}
+// --infer-ancestors (M/Mapper.java:675-681): the context's DupDetector must have been created with min_copies = 3, window = 1
+int xo_infer_ancestors(void* cv, double dissimilarity_threshold, int verify_no_duplicate_analyses) {
+  Ctx* c = (Ctx*)cv;
+  try {
+    AncestryDetector a(c->dup.get(), dissimilarity_threshold);
+    a.verifyNoDuplicateAnalyses = verify_no_duplicate_analyses != 0;
+    c->ancestors = a.run();
+    return (int)c->ancestors.size();
+  } catch (std::exception& e) { c->lastError = e.what(); return -1; }
+}
+void xo_ancestor_codes(void* cv, int contig, uint8_t* out) {
+  Ctx* c = (Ctx*)cv;
+  const auto& v = c->ancestors[(size_t)contig];
+  memcpy(out, v.data(), v.size());
 }
 double xo_dup_granularity(void* cv) { return ((Ctx*)cv)->dup->detectionGranularity(); }
 // duplication start keys on forward contig i
@@ -431,6 +449,53 @@ int xo_test_hash_symmetry(const char* text) {
     }
   }
   return checked;
+}
+
+// T/MultiHashBlock_Test.java:90-117,129-165 — hashString(): for every row, the block at index 0 and its possibilities that end at the
+// end of the sequence.  Returns 1 if hashing `ambiguous` yields a possibility equal (start, end, forward hash) to the single block
+// that spans all of `text`, 0 if not, -1 if `text` itself is not spanned by exactly one block.
+static void xo_hash_string(const Seq* seq, std::vector<HB>& out) {
+  Pyramid p(seq);
+  for (int level = 0;; level++) {
+    Row* row = p.get(level);
+    if (row == nullptr) break;
+    const MB* b = row->get(0);
+    if (b == nullptr) break;
+    if (b->single) { if (b->hb.end() == seq->length()) out.push_back(b->hb); }
+    else for (auto& c : b->poss) if (c.has && c.hb.end() == seq->length()) out.push_back(c.hb);
+  }
+}
+int xo_test_multi_expand(const char* text, const char* ambiguous) {
+  try {
+    auto s = makeSeq("q", text); auto a = makeSeq("q", ambiguous);
+    std::vector<HB> plain, amb;
+    xo_hash_string(s.get(), plain);
+    if (plain.size() != 1) return -1;
+    xo_hash_string(a.get(), amb);
+    for (auto& h : amb) if (h.start == plain[0].start && h.end() == plain[0].end() && h.fwd == plain[0].fwd) return 1;
+    return 0;
+  } catch (std::exception&) { return -2; }
+}
+
+// T/BasepairsTest.java:9-47 — AlignmentParameters.getPenalty(encoded, encoded) (M/AlignmentParameters.java:156-180)
+double xo_test_base_penalty(const CParams* cp, const char* q, const char* r) {
+  Params p = toParams(cp);
+  return p.basePenalty(bp_encode(q[0]), bp_encode(r[0]));
+}
+// T/SequenceDatabase_Test.java:17-41 / T/PackedMap_Test.java:14-48 — encodePosition / decodePosition over sequences whose total
+// length exceeds 2^31 (lengths only: the bases are never touched).  Returns the number of (sequence, offset) pairs that round-trip.
+int64_t xo_test_position_roundtrip(int n_sequences, int64_t length) {
+  std::vector<long long> starts((size_t)n_sequences);
+  long long t = 0;
+  for (int i = 0; i < n_sequences; i++) { starts[(size_t)i] = t; t += length; }   // SequenceDatabase.computeMetrics :240-248
+  int64_t ok = 0;
+  const long long offs[4] = {0, 100, length - 100, length - 1};
+  for (int i = 0; i < n_sequences; i++) for (long long off : offs) {
+    long long enc = starts[(size_t)i] + off;                                       // encodePosition :88-105
+    size_t idx = (size_t)(std::upper_bound(starts.begin(), starts.end(), enc) - starts.begin()) - 1;   // decodePosition :170-209
+    if ((int)idx == i && enc - starts[idx] == off) ok++;
+  }
+  return ok;
 }
 
 }  // extern "C"

@@ -11,6 +11,7 @@
 // the encoded size can differ from the raw size by a few bytes and the outcome depends on add order
 // in the reference itself.  Here a bucket is overfull iff its final entry count > maxCount.
 #pragma once
+#include <memory>
 #include "xo_hash.h"
 #include <set>
 #include <thread>
@@ -303,7 +304,8 @@ struct DupDetector {
   Index* index;
   int minSize, maxSize, minCopies, windowSize;
   bool enableGapmers;
-  struct Dup { int length; int numInstances; };
+  struct DupGroup { int length; std::vector<SeqPos> starts; };  // M/Duplication.java: one object shared by all of its positions
+  struct Dup { int length; int numInstances; std::shared_ptr<DupGroup> group; };
   std::map<const Seq*, std::map<int, Dup>> bySeq;
   bool detected = false;
   std::mutex mu;
@@ -392,7 +394,9 @@ struct DupDetector {
               // removeDuplicatePositions: unique (sequence,start)
               std::set<std::pair<const Seq*, int>> uniq;
               for (auto& p : g.second) uniq.insert({p.seq, p.start});
-              Dup d{blockLength, (int)uniq.size()};
+              Dup d{blockLength, (int)uniq.size(), std::make_shared<DupGroup>()};
+              d.group->length = blockLength;
+              for (auto& u : uniq) d.group->starts.push_back(SeqPos{const_cast<Seq*>(u.first), u.second});
               if (d.numInstances >= minCopies) for (auto& u : uniq) blocks[u.first][u.second] = d;  // groupDuplicationsBySequence :252-269
             }
           }

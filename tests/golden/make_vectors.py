@@ -360,6 +360,32 @@ vcf_cases = [
          expected="".join("contig1\t%d\t%s\t.\t0.33\t0.33,0\t0,0\t.\n" % (p, c) for p, c in zip([1, 2, 3, 4, 9, 10, 11, 12, 17, 18, 19, 20], "ACGTACGTACGT"))),
 ]
 
+# --- T/AncestryDetector_Test.java:10-91: seven exact inferred-ancestor strings.  check() (:93-125): reference + its reverse complement,
+# default HashBlock_Database, DuplicationDetector(db, chooseMin, chooseMax, 3 copies, window 0), dissimilarityThreshold 0.3,
+# setVerifyNoDuplicateAnalyses() ---
+def _anc(name, cite, ref, answer):
+    return dict(name=name, cite=cite, reference=ref, expected=answer, threshold=0.3)
+
+
+_r1, _r2 = "GCCCATTAAAACTGACACGGGTTAC", "GCCCATTAAAACTGACACCGGTTAC"
+_t1, _t2 = "AACGGTGGGAACGGCGGAGCGTCGC", "AACGGTGGGATCGGCGGAGCGTCGC"
+_c1, _c3 = "TTATTGTTAAACCGGTACACC", "TTATTGTTAAACCTGTACACC"
+_p = ["CAACCGGAGAATCTCGATGAGNNNNNNNN", "CAACCGGAGAATCTCGATTAGNNNNNNNN", "CAACCGGAGAATCTCGATGAGNNNNNNNN", "CAACCGGAGAATCTCGATTATNNNNNNNN"]
+_n1 = "GGACGTACGCACGAACGACCGAGCGATGTTT"
+_m1, _m2 = "AACGACGTCTGACGAGTGACGTGGACAACCGGACGGCTC", "AACGACTTCTGACAAGTGACCTGGACATCCGGACAGCTC"
+_b1, _b2, _bs = "AGCGGTGGAACGGCGGAGCGTCGTCAAACCCGGGTTCTCAGTCG", "AGCGGTGGAACGGCGGAGCGTCGTCAAACCCGGGTTCTCAGTCA", "AGACATACAGAAAGAG"
+ancestry_cases = [
+    _anc("basicTest", "T/AncestryDetector_Test.java:10-18", _r1 + _r1 + _r2, _r1 + _r1 + "GCCCATTAAAACTGACACSGGTTAC"),
+    _anc("test2", "T/AncestryDetector_Test.java:20-28", _t1 + _t1 + _t2, _t1 + _t1 + "AACGGTGGGAWCGGCGGAGCGTCGC"),
+    _anc("reverseComplementTest", "T/AncestryDetector_Test.java:30-39", _c1 + rc(_c1) + _c3, _c1 + rc(_c1) + "TTATTGTTAAACCKGTACACC"),
+    _anc("proceedPastTiesTest", "T/AncestryDetector_Test.java:41-54", "".join(_p), _p[0] + _p[1] + _p[2] + "CAACCGGAGAATCTCGATTAKNNNNNNNN"),
+    _anc("noChangesTest", "T/AncestryDetector_Test.java:56-64", _n1 * 3, _n1 * 3),
+    _anc("manyMutationsTest", "T/AncestryDetector_Test.java:66-76", _m1 + _m1 + _m2, _m1 + _m1 + "AACGACKTCTGACRAGTGACSTGGACAWCCGGACRGCTC"),
+    _anc("breakSimilarSectionTest/mutatedAtEnd", "T/AncestryDetector_Test.java:78-85", _b1 * 3 + _b2 + _bs, _b1 * 3 + _b2 + _bs),
+    _anc("breakSimilarSectionTest/mutatedInMiddle", "T/AncestryDetector_Test.java:87-91", _b1 + _b1 + _b2 + _b1 + _bs,
+         _b1 + _b1 + "AGCGGTGGAACGGCGGAGCGTCGTCAAACCCGGGTTCTCAGTCR" + _b1 + _bs),
+]
+
 # --- examples/ (config 1): inputs only; the reference ships no expected output (examples/.gitignore) ---
 examples = dict(
     cite="examples/reference.fasta, examples/queries.fasta, examples/test.sh:14",
@@ -374,7 +400,7 @@ out = dict(source="mathjeff/Mapper @ ae7f346a JUnit tests (transcribed; see make
            api_cases=api_cases, sam_cases=sam_cases, path_aligner_cases=path_cases, hashblock_aligner_cases=hashblock_cases,
            counting_path_cases=counting_cases, paths_counter_cases=paths_counter_cases, symmetry_cases=symmetry_cases,
            basepair_cases=basepair_cases, examples=examples,
-           mutations_cases=mutations_cases, match_database_cases=match_database_cases, vcf_cases=vcf_cases)
+           mutations_cases=mutations_cases, match_database_cases=match_database_cases, vcf_cases=vcf_cases, ancestry_cases=ancestry_cases)
 
 if __name__ == "__main__":
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "junit_vectors.json")

@@ -123,6 +123,18 @@ class Oracle:
         self.L.xo_dup_copy(C.c_void_p(self.h), contig, out.ctypes.data_as(C.c_void_p))
         return out[:n]
 
+    def infer_ancestors(self, dissimilarity_threshold, verify=False):
+        """AncestryDetector.unionRecentAncestors over this reference (the Oracle must have been created with dup=dict(min_copies=3, window=1),
+        M/Mapper.java:675-681).  Returns [(name + "-anc", codes)] in database order."""
+        n = self._ok(self.L.xo_infer_ancestors(C.c_void_p(self.h), C.c_double(dissimilarity_threshold), int(verify)))
+        out = []
+        for i in range(n):
+            name, codes = self.contig(i)
+            buf = np.empty(len(codes), dtype=np.uint8)
+            self.L.xo_ancestor_codes(C.c_void_p(self.h), i, buf.ctypes.data_as(C.c_void_p))
+            out.append((name + "-anc", buf))
+        return out
+
     # ---- alignment ----
     def align(self, params, seqs, expected_inner=0.0, per_penalty=1.0):
         p = make_params(params)
