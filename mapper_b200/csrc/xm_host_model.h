@@ -113,35 +113,105 @@ struct HostModel {
 
   // what both index builders start from: minInterestingSize :51-55, the longest length built and the capacity per length
   bool index_plan(int max_used, int& hi, std::vector<int>& cap, std::string& err) {
-    if (ref_ambiguous) { err = "xm_build_index: reference contains IUPAC-ambiguous bases (MultiHashBlock expansion of the reference is host-side in this round; upload the tables with xm_set_index_length)"; return false; }
+    if (ref_ambiguous) { err = "xm_build_index: the reference contains IUPAC-ambiguous bases; the device builder handles unambiguous references - call xm_build_index with n_threads > 0 (the library's host builder expands MultiHashBlocks) or upload the tables with xm_set_index_length"; return false; }
     min_interesting = j2i(std::max((std::log((double)(total_forward + 1)) / std::log(4.0)) - 2, 1.0));
     hi = std::max(max_used, 2 * choose_min_dup_len());
     cap.assign((size_t)hi + 1, 1);
     for (int n = 1; n <= hi; n++) { int c = estimate_capacity(n); cap[(size_t)n] = c < 1 ? 1 : c; }
     return true;
   }
+  // Blocks of an IUPAC-ambiguous stretch of the reference (an "-anc" reference, M/AncestryDetector.java:323-327): the device core's
+  // MultiHashBlock pyramid (pyr_build -> pyr_build_ambiguous, M/HashBlock_ParentRow.java:69-191) over a window of the contig; calls
+  // emit(block in contig coordinates, is_multi) for every block / possibility whose start lies in [s, e).
+  template <class F>
+  bool ambiguous_window_blocks(int contig, int s, int e, int hi, std::vector<char>& arena, std::string& err, F&& emit) const {
+    SeqView full = contig_view(contig, 0);
+    const int halo = 4 * hi + 256;   // a multi-block's possibilities differ in length; generous so that every possibility of a block that starts before e is complete
+    const int w_end = std::min(full.len, e + halo);
+    const int wlen = w_end - s;
+    if (wlen > 32000) { err = "xm_build_index: hash lengths this long are not supported on IUPAC-ambiguous references (16-bit window coordinates)"; return false; }
+    WS w; memset((void*)&w, 0, sizeof(WS));
+    MatePath m; memset((void*)&m, 0, sizeof(MatePath));
+    SeqView v; v.w = full.w + (s >> 2); v.len = wlen; v.rc = 0; v.bytes = nullptr; v.b0 = 0; v.bn = 0;   // s is a multiple of 4
+    m.q = v;
+    const long long cap = 10LL * wlen + 256;
+    const long long lev_bytes = ((long long)(wlen + 3) * 4 + 15) & ~15LL;
+    const long long need = lev_bytes + cap * 20 + 64 + (192LL << 20);
+    if ((long long)arena.size() < need) arena.resize((size_t)need);
+    char* p = arena.data();
+    Pyr& P = m.pyr;
+    P.cap_levels = wlen + 2; P.cap_blocks = (int)std::min<long long>(cap, 2000000000LL);
+    P.level_off = (int32_t*)p; p += lev_bytes;
+    P.blk = (HB16*)p; p += cap * 16; P.child = (int16_t*)p; p += cap * 2; P.up = (int16_t*)p; p += cap * 2;
+    p += (16 - ((uintptr_t)p & 15)) & 15;
+    w.scratch = p; w.scratch_size = (long long)(arena.data() + arena.size() - p) & ~15LL; w.scratch_top = 0;
+    if (!pyr_build(w, m) || w.status != 0) { err = "xm_build_index: MultiHashBlock expansion of the reference ran out of workspace (status " + std::to_string(w.status) + ")"; return false; }
+    for (int level = 0; level < P.n_levels; level++) {
+      const int n = pyr_level_size(P, level);
+      const HB16* row = P.blk + P.level_off[level];
+      bool any_short = false;
+      for (int i = 0; i < n; i++) {
+        const HB16& c = row[i];
+        if (s + (int)c.start >= e) break;
+        const int k_n = pyr_num_opts(c);
+        for (int k = 0; k < k_n; k++) {
+          const POpt o = pyr_opt(P, c, k);
+          if (!o.has) continue;
+          if ((int)o.hb.len <= hi) any_short = true;
+          HB b; b.start = s + o.hb.start; b.len = o.hb.len; b.used = o.hb.len; b.fwd = o.hb.fwd; b.rev = o.hb.rev; b.gap_dir = o.hb.gap_dir; b.flags = o.hb.flags; b.extra = o.hb.extra; b.ident = 0;
+          emit(b, (c.flags & HB_MULTI) != 0);
+        }
+      }
+      if (!any_short) break;
+    }
+    return true;
+  }
   bool build_index(int max_used, int n_threads, std::string& err) {
-    if (ref_ambiguous) { err = "xm_build_index: reference contains IUPAC-ambiguous bases (MultiHashBlock expansion is host-side in this round; upload the tables with xm_set_index_length)"; return false; }
     min_interesting = j2i(std::max((std::log((double)(total_forward + 1)) / std::log(4.0)) - 2, 1.0));  // :51-55
     int hi = std::max(max_used, 2 * choose_min_dup_len());
     std::vector<int> cap((size_t)hi + 1, 1);
     for (int n = 1; n <= hi; n++) { int c = estimate_capacity(n); cap[(size_t)n] = c < 1 ? 1 : c; }
     struct Slice { int contig, s, e; };
     std::vector<Slice> slices;
-    const int slice_len = 65536;
+    const int slice_len = ref_ambiguous ? 8192 : 65536;
     for (int c = 0; c < n_contigs; c++) for (int s = 0; s < len[c]; s += slice_len) slices.push_back({c, s, std::min(len[c], s + slice_len)});
     int nt = std::max(1, n_threads);
-    std::vector<std::vector<std::vector<Entry>>> parts((size_t)nt);
+    std::vector<std::vector<std::vector<Entry>>> parts((size_t)nt), multi_parts((size_t)nt);
     for (auto& p : parts) p.resize((size_t)hi + 1);
+    for (auto& p : multi_parts) p.resize((size_t)hi + 1);
+    std::vector<std::string> errs((size_t)nt);
     std::atomic<size_t> next(0);
     auto work = [&](int t) {
       std::vector<HB> cur, nxt;
+      std::vector<char> amb_arena;
       while (true) {
         size_t si = next.fetch_add(1);
         if (si >= slices.size()) break;
         const Slice& sl = slices[si];
         SeqView seq = contig_view(sl.contig, 0);
         int ext_end = std::min(seq.len, sl.e + hi + 2);
+        auto add_block = [&](const HB& b, bool is_multi) {
+          HB g;
+          if (gapmers) { if (!with_gap_and_extension(b, seq, g)) return; } else g = b;
+          int n = g.used;
+          if (n < min_interesting || n > hi) return;
+          int c = cap[(size_t)n];
+          bool rml = g.rml(), rmr = g.rmr();
+          bool primary = (rml != rmr) ? rml : (g.fwd >= g.rev);
+          bool secondary = (rml != rmr) ? rmr : (g.fwd <= g.rev);  // HashBlock.isSecondaryPolarity :339-343
+          auto& dst = is_multi ? multi_parts[(size_t)t][(size_t)n] : parts[(size_t)t][(size_t)n];
+          if (primary) { int r = g.fwd % c; if (r < 0) r += c; dst.push_back({(uint32_t)r, (uint32_t)(gstart[2 * sl.contig] + g.start)}); }
+          if (secondary) { int r = g.rev % c; if (r < 0) r += c; dst.push_back({(uint32_t)r, (uint32_t)(gstart[2 * sl.contig + 1] + (seq.len - g.end()))}); }
+        };
+        if (ref_ambiguous) {
+          bool amb = false;
+          const int scan_end = std::min(seq.len, sl.e + 4 * hi + 256);
+          for (int i = sl.s; i < scan_end && !amb; i++) amb = bp_is_ambiguous(seq.at(i));
+          if (amb) {
+            if (!ambiguous_window_blocks(sl.contig, sl.s, sl.e, hi, amb_arena, errs[(size_t)t], add_block)) return;
+            continue;
+          }
+        }
         cur.clear();
         for (int i = sl.s; i < ext_end; i++) cur.push_back(base_block(seq.at(i), i));
         int level = 0;
@@ -150,16 +220,7 @@ struct HostModel {
           for (const HB& b : cur) {
             if (b.start >= sl.e) break;
             if (b.len <= hi) any_short = true;
-            HB g;
-            if (gapmers) { if (!with_gap_and_extension(b, seq, g)) continue; } else g = b;
-            int n = g.used;
-            if (n < min_interesting || n > hi) continue;
-            int c = cap[(size_t)n];
-            bool rml = g.rml(), rmr = g.rmr();
-            bool primary = (rml != rmr) ? rml : (g.fwd >= g.rev);
-            bool secondary = (rml != rmr) ? rmr : (g.fwd <= g.rev);  // HashBlock.isSecondaryPolarity :339-343
-            if (primary) { int r = g.fwd % c; if (r < 0) r += c; parts[(size_t)t][(size_t)n].push_back({(uint32_t)r, (uint32_t)(gstart[2 * sl.contig] + g.start)}); }
-            if (secondary) { int r = g.rev % c; if (r < 0) r += c; parts[(size_t)t][(size_t)n].push_back({(uint32_t)r, (uint32_t)(gstart[2 * sl.contig + 1] + (seq.len - g.end()))}); }
+            add_block(b, false);
           }
           if (!any_short) break;
           level++;
@@ -174,20 +235,38 @@ struct HostModel {
     };
     if (nt == 1) work(0);
     else { std::vector<std::thread> th; for (int t = 0; t < nt; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
+    for (auto& e : errs) if (!e.empty()) { err = e; return false; }
     tables.assign((size_t)hi + 1, HostTable());
     std::atomic<int> nn(1);
     auto fin = [&]() {
       while (true) {
         int n = nn.fetch_add(1);
         if (n > hi) break;
-        size_t total = 0;
-        for (int t = 0; t < nt; t++) total += parts[(size_t)t][(size_t)n].size();
+        size_t total = 0, total_multi = 0;
+        for (int t = 0; t < nt; t++) { total += parts[(size_t)t][(size_t)n].size(); total_multi += multi_parts[(size_t)t][(size_t)n].size(); }
         HostTable& T = tables[(size_t)n];
-        if (total == 0) { T.capacity = 1; T.max_count = 1; continue; }
+        if (total + total_multi == 0) { T.capacity = 1; T.max_count = 1; continue; }
         T.capacity = cap[(size_t)n]; T.max_count = max_count_for(n, 5);
-        std::vector<Entry> all; all.reserve(total);
+        std::vector<Entry> all; all.reserve(total + total_multi);
         for (int t = 0; t < nt; t++) { auto& v = parts[(size_t)t][(size_t)n]; all.insert(all.end(), v.begin(), v.end()); std::vector<Entry>().swap(v); }
         std::sort(all.begin(), all.end(), [](const Entry& a, const Entry& b) { return a.bucket != b.bucket ? a.bucket < b.bucket : a.pos < b.pos; });
+        if (total_multi) {
+          // PackedMap.add(preventDuplicates) :117-131: a possibility of a multi-block that is already in its bucket is skipped (plain
+          // blocks are never de-duplicated among themselves)
+          std::vector<Entry> mm;
+          for (int t = 0; t < nt; t++) { auto& v = multi_parts[(size_t)t][(size_t)n]; mm.insert(mm.end(), v.begin(), v.end()); std::vector<Entry>().swap(v); }
+          auto less = [](const Entry& a, const Entry& b) { return a.bucket != b.bucket ? a.bucket < b.bucket : a.pos < b.pos; };
+          std::sort(mm.begin(), mm.end(), less);
+          std::vector<Entry> keep;
+          for (size_t i = 0; i < mm.size(); i++) {
+            if (i > 0 && mm[i].bucket == mm[i - 1].bucket && mm[i].pos == mm[i - 1].pos) continue;
+            if (std::binary_search(all.begin(), all.end(), mm[i], less)) continue;
+            keep.push_back(mm[i]);
+          }
+          std::vector<Entry> merged(all.size() + keep.size());
+          std::merge(all.begin(), all.end(), keep.begin(), keep.end(), merged.begin(), less);
+          all.swap(merged);
+        }
         T.buckets.assign((size_t)T.capacity, 0);
         size_t i = 0; int64_t off = 0;
         for (int b = 0; b < T.capacity; b++) {

@@ -157,9 +157,12 @@ XM_FN bool with_gap_and_extension(const HB& b, const SeqView& seq, HB& out) {
 XM_INLINE long long pyr_arena_bytes(int len) { return (((long long)(len + 3) * 4 + 15) & ~15LL) + 64 + 20LL * (8LL * len + 64); }
 struct HB16 { int16_t start, len; int32_t fwd, rev; uint8_t flags; int8_t gap_dir; int16_t extra; };
 // One possibility of a MultiHashBlock (M/ConditionalHashBlock.java): the block (valid iff has) that exists when the
-// IUPAC-ambiguous query bases in `mask` (by ordinal among the query's ambiguous positions) take the bases in v0/v1
-// (2 bits per ordinal: A0 C1 G2 T3) - the bit-set form of M/SequenceCondition.java.
-struct POpt { HB16 hb; unsigned long long mask, v0, v1; int has, pad; };
+// IUPAC-ambiguous bases at the positions listed in kv take the listed bases - M/SequenceCondition.java as a short sorted list of
+// (position << 2 | base: A0 C1 G2 T3).  A stored possibility constrains only the ambiguous positions inside its block, and a
+// multi-block with more than 64 possibilities is dropped (HashBlock_ParentRow.java:10,109,165), so the lists stay short; a condition
+// that would need more than POPT_MAX_KEYS entries fails the sequence loudly (Q_AMBIGUOUS_QUERY) instead of being truncated.
+static const int POPT_MAX_KEYS = 31;
+struct POpt { HB16 hb; int32_t n_kv; uint32_t kv[POPT_MAX_KEYS]; int has, pad; };
 static const uint8_t HB_MULTI = 0x80;  // HB16::flags / HB::flags: the entry is a MultiHashBlock; fwd = first POpt, rev = number of POpts
 struct Pyr {
   POpt* opt; int n_opt, cap_opt;   // possibilities of the multi-blocks (only queries with ambiguous bases)
@@ -309,19 +312,24 @@ XM_FN int pyr_find_after(const Pyr& P, int level, int p) {
 // Rare, so built by a scalar pass.  A multi-block occupies one entry of its level like any block (same start, child and
 // up links); the walk only ever asks for its start and steps past it (HashBlockPath.skipMultiblocks :130-140), but its
 // possibilities decide which blocks exist above it, so they are kept in full.
-XM_INLINE bool popt_intersect(const POpt& a, const POpt& b, POpt& out) {  // SequenceCondition.intersect :27-106; false = conflict
-  const unsigned long long common = a.mask & b.mask;
-  unsigned long long c = common;
+XM_INLINE bool popt_intersect(const POpt& a, const POpt& b, POpt& out, bool& overflow) {  // SequenceCondition.intersect :27-106; false = conflict
+  int i = 0, j = 0, n = 0;
+  uint32_t kv[2 * POPT_MAX_KEYS];
   XM_NOUNROLL
-  while (c) {
-    int k = 0;
-    { unsigned long long t = c; while (!(t & 1ull)) { t >>= 1; k++; } }
-    c &= c - 1;
-    const unsigned long long av = (k < 32) ? (a.v0 >> (2 * k)) & 3ull : (a.v1 >> (2 * (k - 32))) & 3ull;
-    const unsigned long long bv = (k < 32) ? (b.v0 >> (2 * k)) & 3ull : (b.v1 >> (2 * (k - 32))) & 3ull;
-    if (av != bv) return false;
+  while (i < a.n_kv && j < b.n_kv) {
+    const uint32_t x = a.kv[i], y = b.kv[j];
+    if ((x >> 2) < (y >> 2)) { kv[n++] = x; i++; }
+    else if ((y >> 2) < (x >> 2)) { kv[n++] = y; j++; }
+    else { if (x != y) return false; kv[n++] = x; i++; j++; }
   }
-  out.mask = a.mask | b.mask; out.v0 = a.v0 | b.v0; out.v1 = a.v1 | b.v1;
+  XM_NOUNROLL
+  while (i < a.n_kv) kv[n++] = a.kv[i++];
+  XM_NOUNROLL
+  while (j < b.n_kv) kv[n++] = b.kv[j++];
+  if (n > POPT_MAX_KEYS) { overflow = true; n = POPT_MAX_KEYS; }
+  out.n_kv = n;
+  XM_NOUNROLL
+  for (int k = 0; k < n; k++) out.kv[k] = kv[k];
   return true;
 }
 XM_INLINE bool hb16_should_merge(const HB16& L, const HB16& R) {  // shouldMergeBlocks :200-208
@@ -331,7 +339,7 @@ XM_INLINE bool hb16_should_merge(const HB16& L, const HB16& R) {  // shouldMerge
 XM_INLINE int pyr_num_opts(const HB16& e) { return (e.flags & HB_MULTI) ? (int)e.rev : 1; }
 XM_INLINE POpt pyr_opt(const Pyr& P, const HB16& e, int k) {
   if (e.flags & HB_MULTI) return P.opt[e.fwd + k];
-  POpt o; o.hb = e; o.mask = 0; o.v0 = 0; o.v1 = 0; o.has = 1; o.pad = 0; return o;
+  POpt o; o.hb = e; o.n_kv = 0; o.has = 1; o.pad = 0; return o;
 }
 struct PExpandFrame { int j, k, found, pad; POpt cond; };
 // HashBlock_ParentRow.expand :137-191 with its recursion unrolled onto `stack`: appends to res[0..n_res)
@@ -349,7 +357,9 @@ XM_FN bool pyr_expand(WS& w, const Pyr& P, const HB16* prev, int n_prev, const H
     const POpt ro = pyr_opt(P, nxt, f.k);
     f.k++;
     POpt inter;
-    if (!popt_intersect(f.cond, ro, inter)) { if (f.found) sp--; continue; }  // :163-167 (break once an intersection was seen)
+    bool overflow = false;
+    if (!popt_intersect(f.cond, ro, inter, overflow)) { if (f.found) sp--; continue; }  // :163-167 (break once an intersection was seen)
+    if (overflow) { w.fail(Q_AMBIGUOUS_QUERY); return false; }
     f.found = 1;
     if (n_res > max_combos) { sp--; continue; }      // :170 return
     if (!ro.has) {                                   // :171-174 look further right under the narrowed condition
@@ -384,15 +394,13 @@ XM_FN bool pyr_build_ambiguous(WS& w, MatePath& m) {
     const uint8_t code = m.q.at(k);
     P.child[k] = -1; P.up[k] = -1;
     if (!bp_is_ambiguous(code)) { P.blk[k] = base_block16(code, k); continue; }
-    if (n_amb >= 64) { w.fail(Q_AMBIGUOUS_QUERY); return false; }  // more than 64 ambiguous bases in one query
     HB16 e; e.start = (int16_t)k; e.len = 1; e.fwd = P.n_opt; e.rev = 0; e.flags = HB_MULTI; e.gap_dir = 0; e.extra = 0;
     XM_NOUNROLL
     for (int o = 0; o < 4; o++) {
       const uint8_t base = (uint8_t)(1 << o);
       if (!bp_can_match(code, base)) continue;
       if (P.n_opt >= P.cap_opt) { w.fail(Q_NEED_MORE); return false; }
-      POpt c; c.hb = base_block16(base, k); c.has = 1; c.pad = 0; c.mask = 1ull << n_amb; c.v0 = 0; c.v1 = 0;
-      if (n_amb < 32) c.v0 = (unsigned long long)o << (2 * n_amb); else c.v1 = (unsigned long long)o << (2 * (n_amb - 32));
+      POpt c; c.hb = base_block16(base, k); c.has = 1; c.pad = 0; c.n_kv = 1; c.kv[0] = ((uint32_t)k << 2) | (uint32_t)o;
       P.opt[P.n_opt++] = c; e.rev++;
     }
     P.blk[k] = e;

@@ -75,3 +75,21 @@ def describe(r, q):
             choices.append(dict(f64=[float(v).hex() for v in r["choice_f64"][4 * k:4 * k + 4]], inner=int(r["choice_inner"][k]), sas=sas))
         out["comps"].append(choices)
     return out
+
+
+def inferred_ancestor_oracle(ref, params, threads=4, window=1000):
+    """--infer-ancestors as M/Mapper.java:666-692 sets it up, with the oracle playing the Java host: the original reference hashed with
+    minInterestingSize = minDuplicationLength and 8 short matches, DuplicationDetector(3 copies, window 1), AncestryDetector with
+    dissimilarityThreshold = MaxErrorRate / MutationPenalty; the aligner then works on the "-anc" reference (IUPAC unions), whose own
+    duplication detector uses 2 copies and the 1000-base window.  ref: list of (name, codes).  Returns (anc oracle, changed positions)."""
+    import xm_oracle as xo
+    texts = [(n, synth.codes_to_text(s)) for n, s in ref]
+    total = sum(len(s) for _, s in ref)
+    min_dup = 1
+    while (1 << min_dup) < total:   # SequenceDatabase.log2RoundUp(totalForwardSize), M/DuplicationDetector.java:17-31
+        min_dup += 1
+    db0 = xo.Oracle(texts, sort_by_length=True, min_interesting=min_dup, max_short=8, threads=threads, dup=dict(min_len=min_dup, max_len=2 * min_dup, min_copies=3, window=1))
+    anc = db0.infer_ancestors(params["max_error_rate"] / params["mutation"])
+    changed = sum(int((a[1] != db0.contig(i)[1]).sum()) for i, a in enumerate(anc))
+    db = xo.Oracle([(n, synth.codes_to_text(s)) for n, s in anc], sort_by_length=False, threads=threads, dup=dict(min_copies=2, window=window))
+    return db, changed

@@ -75,3 +75,19 @@ def test_config4_long_reads_split_past_1000():
     assert [len(p) for p in rag] == [833, 833, 834]
     check(db, g, synth.batch_from_reads(rag), "configs[4] ragged pieces")
     g.close()
+
+
+def test_config4_with_inferred_ancestors():
+    """configs[4] with --infer-ancestors: the aligner works on the inferred-ancestor reference (IUPAC unions in the repeat copies,
+    M/Mapper.java:675-681); index (MultiHashBlock fan-out) and duplication table built by the library; 10 kbp reads split past 1000."""
+    ref = synth.random_reference(2000000, seed=6, n_contigs=10, repeat_fraction=0.08, repeat_copies=(3, 6), repeat_len=(1000, 5000))
+    db, changed = parity.inferred_ancestor_oracle(ref, synth.DEFAULT_PARAMS, threads=THREADS)
+    assert changed > 500
+    g = capi.XMapper(synth.DEFAULT_PARAMS, device=0)
+    parity.feed_reference(g, db)
+    g.build_index(1000, threads=THREADS)
+    g.build_duplications(-1, -1, 2, 1000)
+    long_batch = synth.simulate_reads(ref, 40, 10000, seed=8, sub_rate=0.01, indel_rate=0.005)
+    pieces, _ = synth.split_queries([q[0] for q in synth.unpack_reads(long_batch)], 1000)
+    check(db, g, synth.batch_from_reads(pieces), "configs[4] --infer-ancestors")
+    g.close()
