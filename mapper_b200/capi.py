@@ -16,7 +16,7 @@ EXPORTS = ["xm_create", "xm_destroy", "xm_last_error", "xm_set_reference", "xm_s
            "xm_build_index", "xm_get_index_length", "xm_index_info", "xm_set_duplications", "xm_build_duplications",
            "xm_get_duplications", "xm_align_batch", "xm_align_batch_device", "xm_results_array", "xm_release_results",
            "xm_counts_enable", "xm_counts_device_ptr", "xm_counts_fetch", "xm_format_sam",
-           "xm_comm_unique_id", "xm_comm_init", "xm_counts_reduce", "xm_counts_batch_info", "xm_variants_fetch"]
+           "xm_comm_unique_id", "xm_comm_init", "xm_counts_reduce", "xm_counts_batch_info", "xm_variants_fetch", "xm_measure_peaks"]
 
 RESULT_ARRAYS = [("q_comp_off", np.int64), ("comp_choice_off", np.int64), ("choice_sa_off", np.int64), ("sa_block_off", np.int64),
                  ("choice_f64", np.float64), ("sa_f64", np.float64), ("choice_inner", np.int32), ("sa_contig", np.int32),
@@ -153,6 +153,12 @@ class XMapper:
         self._ok(self.L.xm_get_index_length(self.h, n, C.byref(cap), C.byref(mx), C.byref(npos), _ptr(off), _ptr(over), _ptr(pos)))
         return dict(used=n, capacity=cap.value, max_count=mx.value, offsets=off, overfull=over, positions=pos[:npos.value])
 
+    def index_length_size(self, n):
+        """(capacity, number of positions) of the table for numBasepairsUsed == n, without copying it."""
+        cap, mx, npos = C.c_int32(), C.c_int32(), C.c_int64()
+        self._ok(self.L.xm_get_index_length(self.h, n, C.byref(cap), C.byref(mx), C.byref(npos), None, None, None))
+        return cap.value, npos.value
+
     def set_duplications(self, window, granularity, contig, starts):
         s = np.ascontiguousarray(starts, dtype=np.int32)
         n = len(s)
@@ -245,6 +251,12 @@ class XMapper:
             k = np.ascontiguousarray(order_keys, dtype=np.int64)
             self._ok(self.L.xm_counts_batch_info(self.h, C.c_int64(first_sequence_id), _ptr(k), C.c_int64(len(k))))
 
+    def variants_count(self):
+        """Reduces the variant records accumulated so far (device sort + reduce-by-key) and returns the number of table entries."""
+        n = C.c_int64()
+        self._ok(self.L.xm_variants_fetch(self.h, C.byref(n), None, None, None, None))
+        return n.value
+
     def variants_fetch(self):
         """The sparse variant table, decoded: dict of arrays gpos, region, dir, ins (-1: at the position), allele, count, ex_gid, ex_rev, ex_index."""
         n = C.c_int64()
@@ -256,6 +268,12 @@ class XMapper:
         return dict(key=keys, gpos=(keys >> np.uint64(21)).astype(np.int64), region=((keys >> np.uint64(20)) & np.uint64(1)).astype(np.int32),
                     dir=((keys >> np.uint64(19)) & np.uint64(1)).astype(np.int32), ins=((keys >> np.uint64(3)) & np.uint64(0xFFFF)).astype(np.int32) - 1,
                     allele=(keys & np.uint64(7)).astype(np.int32), count=counts, ex_gid=gid >> 1, ex_rev=(gid & 1).astype(np.int32), ex_index=idx)
+
+    def measure_peaks(self):
+        """Issue-rate micro-benchmarks (warp-instructions/s over the chip): dict(int32, fp64, alu, sm_count, sm_clock_hz)."""
+        out = (C.c_double * 5)()
+        self._ok(self.L.xm_measure_peaks(self.h, out))
+        return dict(int32=out[0], fp64=out[1], alu=out[2], sm_count=int(out[3]), sm_clock_hz=out[4])
 
     def counts_device_ptr(self):
         p, n = C.c_void_p(), C.c_int64()

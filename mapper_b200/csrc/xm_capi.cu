@@ -10,6 +10,8 @@
 #include "xm_results.h"
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_run_length_encode.cuh>
 #include <memory>
@@ -50,6 +52,7 @@ struct LaunchD {
   BatchD batch;
   OutArena out;
   const int32_t* ids; int n_ids;          // queries of this tier (nullptr = identity)
+  const int* n_ids_ptr;                   // non-null: the number of queries is read from the device (left there by the previous launch), n_ids is only its bound
   int* ticket;                            // dynamic work counter
   int32_t* need_more; int* n_need_more;   // queries to re-run in the next tier
   int32_t* need_more_key;                 // first pass: cost estimate per entry of need_more (nullptr otherwise)
@@ -80,6 +83,7 @@ __global__ void __launch_bounds__(EASY ? XM_BLOCK : XM_FULL_BLOCK, EASY ? XM_MIN
   __syncthreads();
   L.prm.pen_tab = s_pen; L.prm.cls_tab = s_cls;
   unsigned long long st[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (L.n_ids_ptr) L.n_ids = *L.n_ids_ptr;
   int dup_i = 0;
   while (true) {
     int t = 0;
@@ -144,25 +148,45 @@ __global__ void __launch_bounds__(EASY ? XM_BLOCK : XM_FULL_BLOCK, EASY ? XM_MIN
   if (lane == 0) for (int i = 0; i < 14; i++) if (st[i]) atomicAdd(&L.out.stats[i], st[i]);
 }
 
-// first_seq[q] = exclusive prefix sum of n_seqs_per_query (single block scan is enough off the hot path; uses a
-// simple two-pass chunked scan)
-__global__ void xm_chunk_sums_kernel(const uint8_t* n_seqs, int n, int chunk, long long* sums) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  long long lo = (long long)c * chunk;
-  if (lo >= n) return;
-  long long hi = lo + chunk < n ? lo + chunk : n;
-  long long s = 0;
-  for (long long i = lo; i < hi; i++) s += n_seqs[i];
-  sums[c] = s;
-}
-__global__ void xm_chunk_scan_kernel(const uint8_t* n_seqs, int n, int chunk, const long long* chunk_off, int64_t* first_seq) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  long long lo = (long long)c * chunk;
-  if (lo >= n) return;
-  long long hi = lo + chunk < n ? lo + chunk : n;
-  long long s = chunk_off[c];
-  for (long long i = lo; i < hi; i++) { first_seq[i] = s; s += n_seqs[i]; }
-  if (hi == n) first_seq[n] = s;
+
+// ---- issue-rate micro-benchmarks (BASELINE.md §2 / SURVEY.md §8d: the roofline denominators of this path are instruction issue
+// and the FP64 pipe, measured on the box, not taken from a datasheet).  Each thread runs `iters` rounds of 8 independent dependent
+// chains; the kernels are launched over every SM at full occupancy and timed with CUDA events by xm_measure_peaks.
+template <int KIND>
+__global__ void __launch_bounds__(256) xm_peak_kernel(int iters, unsigned long long* sink, double seed) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (KIND == 0) {          // INT32 pipe: IMAD chains (the hash mixing / index arithmetic class of instructions)
+    int a0 = tid, a1 = tid + 1, a2 = tid + 2, a3 = tid + 3, a4 = tid + 4, a5 = tid + 5, a6 = tid + 6, a7 = tid + 7;
+    const int m = (int)seed | 1;
+    #pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+      #pragma unroll
+      for (int k = 0; k < 16; k++) { a0 = a0 * m + a1; a1 = a1 * m + a2; a2 = a2 * m + a3; a3 = a3 * m + a4; a4 = a4 * m + a5; a5 = a5 * m + a6; a6 = a6 * m + a7; a7 = a7 * m + a0; }
+    }
+    if ((a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7) == 0x7fffffff) sink[0] = (unsigned long long)a0;
+  } else if (KIND == 1) {   // FP64 pipe: DADD chains (penalty sums / min-add groups of the lattice search)
+    double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+    #pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+      #pragma unroll
+      for (int k = 0; k < 16; k++) { a0 += a1; a1 += a2; a2 += a3; a3 += a4; a4 += a5; a5 += a6; a6 += a7; a7 += a0; }
+    }
+    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 0.123) sink[0] = 1;
+  } else {                  // the issue-slot ceiling: FP32 FFMA and integer LOP3 chains IADD3 chains interleaved (two pipes, one dispatch port per scheduler)
+    unsigned a0 = tid, a1 = tid + 1, a2 = tid + 2, a3 = tid + 3;
+    float f0 = (float)seed, f1 = f0 + 1.0f, f2 = f0 + 2.0f, f3 = f0 + 3.0f;
+    const unsigned m = (unsigned)seed;
+    const float c = (float)seed * 1e-9f;
+    #pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+      #pragma unroll
+      for (int k = 0; k < 16; k++) {
+        a0 = a0 + a1 + m; f0 = __fmaf_rn(f0, c, f1); a1 = a1 + a2 + m; f1 = __fmaf_rn(f1, c, f2);
+        a2 = a2 + a3 + m; f2 = __fmaf_rn(f2, c, f3); a3 = a3 + a0 + m; f3 = __fmaf_rn(f3, c, f0);
+      }
+    }
+    if ((a0 ^ a1 ^ a2 ^ a3) == 0x7fffffffu || f0 + f1 + f2 + f3 == 0.123f) sink[0] = a0;
+  }
 }
 
 // ---- result CSR assembly on the device (include/xmapper_b200.h: xm_results_array) ----
@@ -626,7 +650,7 @@ struct xm_handle {
   int full_warps = XM_FULL_BLOCK / 32, full_blocks_per_sm = XM_FULL_MIN_BLOCKS;  // full kernel: warps per block, blocks per SM
   std::string err;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev5 = nullptr;
   // device mirror of the model
   uint64_t mirrored_generation = ~0ull;
   DevBuf d_words, d_word_off, d_len, d_gstart, d_tables, d_dup_off, d_dup_starts;
@@ -718,7 +742,7 @@ int xm_create(const xm_params* p, int device, xm_handle** out) {
   if (const char* e = getenv("XM_FULL_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) h->full_blocks_per_sm = v; }
   if (const char* e = getenv("XM_FULL_WARPS")) { int v = atoi(e); if (v >= 1 && v <= XM_FULL_BLOCK / 32) h->full_warps = v; }
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
-      cudaEventCreate(&h->ev2) != cudaSuccess || cudaEventCreate(&h->ev3) != cudaSuccess) {
+      cudaEventCreate(&h->ev2) != cudaSuccess || cudaEventCreate(&h->ev3) != cudaSuccess || cudaEventCreate(&h->ev4) != cudaSuccess || cudaEventCreate(&h->ev5) != cudaSuccess) {
     fprintf(stderr, "xmapper_b200: stream/event creation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
     xm_destroy(h); return XM_ERR_CUDA;
   }
@@ -760,7 +784,7 @@ void xm_destroy(xm_handle* h) {
   for (auto& b : h->d_buckets) b.release();
   for (auto& b : h->d_positions) b.release();
   if (h->stream) cudaStreamDestroy(h->stream);
-  for (cudaEvent_t e : {h->ev0, h->ev1, h->ev2, h->ev3}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {h->ev0, h->ev1, h->ev2, h->ev3, h->ev4, h->ev5}) if (e) cudaEventDestroy(e);
   delete h;
 }
 const char* xm_last_error(const xm_handle* h) { return h ? h->err.c_str() : "null handle"; }
@@ -953,10 +977,14 @@ static int var_reserve(xm_handle* h, unsigned long long want) {   // keeps recs[
   h->d_var.p = np; h->d_var.cap = (size_t)ncap * sizeof(VarRec); h->var_cap = ncap;
   return XM_OK;
 }
-static int accumulate_counts(xm_handle* h, const LaunchD& L, int nq, long long n_seqs_total, int& launches) {
+// enqueue: one launch of xm_counts_kernel behind the align kernels; the number of records it wanted to write comes back in *n_after
+// with the caller's next synchronisation.  finish: grows the record buffer and emits the batch's records again if they did not fit.
+struct CountsPending { CountsD C; VarOut V; };
+static int counts_enqueue(xm_handle* h, const LaunchD& L, int nq, long long n_seqs_total, int& launches, CountsPending& P, unsigned long long* n_after) {
   cudaStream_t st = h->stream;
-  CountsD C; C.planes = (int32_t*)h->d_planes.p; C.contig_off = (const int64_t*)h->d_contig_off.p; C.end_fraction = h->end_fraction;
-  VarOut V; V.order = nullptr;
+  CountsD& C = P.C; VarOut& V = P.V;
+  C.planes = (int32_t*)h->d_planes.p; C.contig_off = (const int64_t*)h->d_contig_off.p; C.end_fraction = h->end_fraction;
+  V.order = nullptr;
   V.first_gid = h->have_batch_info ? h->info_first_gid : h->next_gid;
   if (h->have_batch_info && !h->info_order.empty()) {
     if ((long long)h->info_order.size() != n_seqs_total) { h->err = "xm_counts_batch_info: order keys do not match the number of sequences of the batch"; return XM_ERR_ARG; }
@@ -968,29 +996,38 @@ static int accumulate_counts(xm_handle* h, const LaunchD& L, int nq, long long n
   int rc = var_reserve(h, h->var_n + (unsigned long long)n_seqs_total * 4 + 4096);   // ~1.6 records per 150 bp read at 1 % differences
   if (rc != XM_OK) return rc;
   if (!h->d_var_n.ensure(16)) { h->err = "out of device memory"; return XM_ERR_CUDA; }
-  bool planes = true;
-  while (true) {
-    V.recs = (VarRec*)h->d_var.p; V.n = (unsigned long long*)h->d_var_n.p; V.cap = h->var_cap;
+  V.recs = (VarRec*)h->d_var.p; V.n = (unsigned long long*)h->d_var_n.p; V.cap = h->var_cap;
+  CK(cudaMemcpyAsync(h->d_var_n.p, &h->var_n, 8, cudaMemcpyHostToDevice, st));
+  xm_counts_kernel<true><<<(nq + 127) / 128, 128, 0, st>>>(h->ref, L.batch, L.out, C, V, nq);
+  launches++;
+  CK(cudaMemcpyAsync(n_after, h->d_var_n.p, 8, cudaMemcpyDeviceToHost, st));
+  return XM_OK;
+}
+static int counts_finish(xm_handle* h, const LaunchD& L, int nq, int& launches, CountsPending& P, unsigned long long n_after) {
+  cudaStream_t st = h->stream;
+  while (n_after > h->var_cap) {
+    // more records than room: grow and emit the batch's records again (the planes were already updated)
+    int rc = var_reserve(h, n_after);
+    if (rc != XM_OK) return rc;
+    P.V.recs = (VarRec*)h->d_var.p; P.V.cap = h->var_cap;
     CK(cudaMemcpyAsync(h->d_var_n.p, &h->var_n, 8, cudaMemcpyHostToDevice, st));
-    if (planes) xm_counts_kernel<true><<<(nq + 127) / 128, 128, 0, st>>>(h->ref, L.batch, L.out, C, V, nq);
-    else xm_counts_kernel<false><<<(nq + 127) / 128, 128, 0, st>>>(h->ref, L.batch, L.out, C, V, nq);
+    xm_counts_kernel<false><<<(nq + 127) / 128, 128, 0, st>>>(h->ref, L.batch, L.out, P.C, P.V, nq);
     launches++;
-    unsigned long long n_after = 0;
     CK(cudaMemcpyAsync(&n_after, h->d_var_n.p, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    if (n_after <= h->var_cap) { h->var_n = n_after; break; }
-    // more records than room: grow and emit the batch's records again (the planes were already updated)
-    rc = var_reserve(h, n_after);
-    if (rc != XM_OK) return rc;
-    planes = false;
   }
+  h->var_n = n_after;
   if (h->var_n - h->var_reduced_n > (1ull << 24) && h->var_n - h->var_reduced_n > h->var_reduced_n / 2) return var_reduce_now(h);
   return XM_OK;
 }
 
-int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, int64_t n_words, const int64_t* d_seq_word_off, const int32_t* d_seq_len,
-                          const uint8_t* d_n_seqs, const double* d_expected, const double* d_per, int32_t max_seq_len, xm_results** out) {
+struct NSeqsAt {   // n_seqs_per_query[i] as int64, 0 past the end
+  const uint8_t* p; int n;
+  __host__ __device__ long long operator()(int i) const { return i < n ? (long long)p[i] : 0LL; }
+};
+static int align_batch_impl(xm_handle* h, int32_t nq, const uint16_t* d_packed, int64_t n_words, const int64_t* d_seq_word_off, const int32_t* d_seq_len,
+                            const uint8_t* d_n_seqs, const double* d_expected, const double* d_per, int32_t max_seq_len, long long n_seqs_total_hint, xm_results** out) {
   if (out) *out = nullptr;
   if (!h || nq < 0 || !out) return XM_ERR_ARG;
   CK(cudaSetDevice(h->device));
@@ -1007,35 +1044,38 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
   xm_results* R = R_owner.get();
   R->r.stats.assign(XM_STAT_COUNT, 0);
   if (nq == 0) { R->r.assemble(0, nullptr, nullptr, nullptr, nullptr); R->serial = h->batch_serial; R->nq = 0; *out = R_owner.release(); return XM_OK; }
-  // first_seq = exclusive scan of n_seqs
-  const int chunk = 4096;
-  int n_chunks = (nq + chunk - 1) / chunk;
-  if (!h->d_first_seq.ensure(((size_t)nq + 1) * 8) || !h->d_chunk.ensure((size_t)n_chunks * 8)) { h->err = "out of device memory"; return XM_ERR_CUDA; }
+  // first_seq = exclusive scan of n_seqs (cub, on the device: nq + 1 items, the last one reads as 0 so that first_seq[nq] is the total)
+  size_t scan0_tmp = 0;
+  {
+    cub::TransformInputIterator<long long, NSeqsAt, cub::CountingInputIterator<int>> it(cub::CountingInputIterator<int>(0), NSeqsAt{d_n_seqs, nq});
+    cub::DeviceScan::ExclusiveSum(nullptr, scan0_tmp, it, (long long*)nullptr, nq + 1, st);
+  }
+  if (!h->d_first_seq.ensure(((size_t)nq + 1) * 8) || !h->d_chunk.ensure(scan0_tmp + 16)) { h->err = "out of device memory"; return XM_ERR_CUDA; }
   CK(cudaEventRecord(h->ev0, st));
-  xm_chunk_sums_kernel<<<(n_chunks + 127) / 128, 128, 0, st>>>(d_n_seqs, nq, chunk, (long long*)h->d_chunk.p);
-  std::vector<long long> sums((size_t)n_chunks);
-  CK(cudaMemcpyAsync(sums.data(), h->d_chunk.p, (size_t)n_chunks * 8, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  long long acc = 0;
-  for (int i = 0; i < n_chunks; i++) { long long v = sums[(size_t)i]; sums[(size_t)i] = acc; acc += v; }
-  long long n_seqs_total = acc;
-  CK(cudaMemcpyAsync(h->d_chunk.p, sums.data(), (size_t)n_chunks * 8, cudaMemcpyHostToDevice, st));
-  xm_chunk_scan_kernel<<<(n_chunks + 127) / 128, 128, 0, st>>>(d_n_seqs, nq, chunk, (const long long*)h->d_chunk.p, (int64_t*)h->d_first_seq.p);
-  int launches = 2;
+  {
+    cub::TransformInputIterator<long long, NSeqsAt, cub::CountingInputIterator<int>> it(cub::CountingInputIterator<int>(0), NSeqsAt{d_n_seqs, nq});
+    size_t tb = scan0_tmp;
+    CK(cub::DeviceScan::ExclusiveSum(h->d_chunk.p, tb, it, (long long*)h->d_first_seq.p, nq + 1, st));
+  }
+  // sizes the result arena: exact when the caller counted the sequences (xm_align_batch), else the bound of two per query
+  const long long n_seqs_total = n_seqs_total_hint >= 0 ? n_seqs_total_hint : 2LL * nq;
+  int launches = 0;
 
   // result arena
   long long want_c = (long long)nq * 2 + 4096, want_s = n_seqs_total * 2 + 4096, want_b = n_seqs_total * 6 + 16384;
   if (h->cap_choices < want_c) { if (!h->d_choices.ensure((size_t)want_c * sizeof(OutChoice))) { h->err = "out of device memory"; return XM_ERR_CUDA; } h->cap_choices = want_c; }
   if (h->cap_sas < want_s) { if (!h->d_sas.ensure((size_t)want_s * sizeof(OutSA))) { h->err = "out of device memory"; return XM_ERR_CUDA; } h->cap_sas = want_s; }
   if (h->cap_blocks < want_b) { if (!h->d_blocks.ensure((size_t)want_b * 16)) { h->err = "out of device memory"; return XM_ERR_CUDA; } h->cap_blocks = want_b; }
-  if (!h->d_q.ensure((size_t)nq * sizeof(OutQuery)) || !h->d_misc.ensure(256) || !h->d_ids_a.ensure((size_t)nq * 4) || !h->d_ids_b.ensure((size_t)nq * 4) || !h->d_ids_full.ensure((size_t)nq * 4)) {
+  if (!h->d_q.ensure((size_t)nq * sizeof(OutQuery)) || !h->d_misc.ensure(512) || !h->d_ids_a.ensure((size_t)nq * 4) || !h->d_ids_b.ensure((size_t)nq * 4) || !h->d_ids_full.ensure((size_t)nq * 4)) {
     h->err = "out of device memory"; return XM_ERR_CUDA;
   }
-  // misc: [0..2] used (u64) [3..16] stats (u64) then ints: ticket, n_need_more, n_out_full
-  CK(cudaMemsetAsync(h->d_misc.p, 0, 256, st));
+  // misc: [0..2] used (u64) [3..16] stats (u64) [20..27] ints: 0 ticket, 1 n_need_more, 2 n_out_full, 4 ticket of tier 0, 5 n_need_more of tier 0;
+  // [32..38] the stats as they stood after the first pass
+  CK(cudaMemsetAsync(h->d_misc.p, 0, 512, st));
   unsigned long long* d_used = (unsigned long long*)h->d_misc.p;
   unsigned long long* d_stats = d_used + 3;
   int* d_ints = (int*)(d_used + 20);
+  unsigned long long* d_easy_stats = d_used + 32;
 
   LaunchD L;
   L.ref = h->ref; L.ix = h->ix; L.dup = h->dup; L.prm = h->m.prm;
@@ -1046,94 +1086,129 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
   L.out.used = d_used; L.out.stats = d_stats;
   L.ticket = d_ints; L.n_need_more = d_ints + 1; L.n_out_full = d_ints + 2;
   L.out_full = (int32_t*)h->d_ids_full.p;
-  L.q_cycles = nullptr;
+  L.q_cycles = nullptr; L.n_ids_ptr = nullptr;
   if (h->probe_cycles) { if (!h->d_qcycles.ensure((size_t)nq * 8)) { h->err = "out of device memory"; return XM_ERR_CUDA; } L.q_cycles = (long long*)h->d_qcycles.p; }
 
   const int block = XM_BLOCK, warps_per_block = XM_BLOCK / 32;
-  const int32_t* ids = nullptr;
-  int n_ids = nq;
-  int32_t* next_ids = (int32_t*)h->d_ids_a.p;
   float align_ms_tier0 = 0, easy_ms = 0, tier_ms[XM_NUM_TIERS] = {0};
   unsigned long long easy_stats[7] = {0, 0, 0, 0, 0, 0, 0};
-  for (int round = 0; round < 4; round++) {  // extra rounds only after growing the result arena
-    for (int tier = (round == 0 ? -1 : 0); tier < XM_NUM_TIERS && n_ids > 0; tier++) {  // tier -1: the first-pass kernel
-      // tier < 0: first pass, blocks of 4 warps.  tier >= 0: one block per SM of `cpb` warps
-      int cpb = warps_per_block, blocks = 1;
-      long long arena = 0;
-      if (tier < 0) {
-        arena = easy_arena_bytes(max_seq_len, 2);
-        long long max_warps = (long long)(h->ws_budget / (size_t)arena);
-        long long warps = (long long)h->sm_count * h->blocks_per_sm * warps_per_block;  // one resident wave: the kernel is persistent (ticket loop)
-        if (warps > max_warps) warps = max_warps;
-        if (warps > n_ids) warps = n_ids;
-        blocks = (int)((warps + warps_per_block - 1) / warps_per_block);
-        if (blocks < 1) blocks = 1;
-        if ((long long)blocks * warps_per_block * arena > (long long)h->ws_budget && blocks > 1) blocks = (int)(h->ws_budget / (size_t)(arena * warps_per_block));
-      } else {
-        cpb = h->full_warps;
-        const int slots = h->sm_count * h->full_blocks_per_sm;   // resident blocks of the full kernel
-        long long resident = (long long)slots * cpb;
-        arena = tier_arena_bytes(tier, max_seq_len, 2, (long long)h->ws_budget, resident);
-        long long clients = resident, max_warps = (long long)(h->ws_budget / (size_t)arena);
-        if (clients > max_warps) clients = max_warps;
-        if (clients > n_ids) clients = n_ids;
-        if (clients < 1) { h->err = "workspace budget too small for one query"; return XM_ERR_CUDA; }
-        if (clients < (long long)slots * cpb) cpb = (int)(clients / slots);
-        if (cpb < 1) cpb = 1;
-        blocks = (int)(clients / cpb);
-        if (blocks > slots) blocks = slots;
+  // One launch of the align kernel.  tier < 0: the first pass (blocks of 4 warps); tier >= 0: the full aligner (one resident wave of
+  // blocks of `cpb` warps).  n_ids_dev != nullptr: the query count is on the device (n_ids is its bound) - nothing comes back to the host.
+  auto launch_tier = [&](int tier, const int32_t* ids, int n_ids, const int* n_ids_dev, int32_t* need_more_out, int* ticket, int* n_need_more,
+                         cudaEvent_t e0, cudaEvent_t e1) -> int {
+    int cpb = warps_per_block, blocks = 1;
+    long long arena = 0;
+    if (tier < 0) {
+      arena = easy_arena_bytes(max_seq_len, 2);
+      long long max_warps = (long long)(h->ws_budget / (size_t)arena);
+      long long warps = (long long)h->sm_count * h->blocks_per_sm * warps_per_block;  // one resident wave: the kernel is persistent (ticket loop)
+      if (warps > max_warps) warps = max_warps;
+      if (warps > n_ids) warps = n_ids;
+      blocks = (int)((warps + warps_per_block - 1) / warps_per_block);
+      if (blocks < 1) blocks = 1;
+      if ((long long)blocks * warps_per_block * arena > (long long)h->ws_budget && blocks > 1) blocks = (int)(h->ws_budget / (size_t)(arena * warps_per_block));
+    } else {
+      cpb = h->full_warps;
+      const int slots = h->sm_count * h->full_blocks_per_sm;   // resident blocks of the full kernel
+      long long resident = (long long)slots * cpb;
+      arena = tier_arena_bytes(tier, max_seq_len, 2, (long long)h->ws_budget, resident);
+      long long clients = resident, max_warps = (long long)(h->ws_budget / (size_t)arena);
+      if (clients > max_warps) clients = max_warps;
+      if (clients > n_ids) clients = n_ids;
+      if (clients < 1) { h->err = "workspace budget too small for one query"; return XM_ERR_CUDA; }
+      if (clients < (long long)slots * cpb) cpb = (int)(clients / slots);
+      if (cpb < 1) cpb = 1;
+      blocks = (int)(clients / cpb);
+      if (blocks > slots) blocks = slots;
+    }
+    if (blocks < 1) { h->err = "workspace budget too small for one block"; return XM_ERR_CUDA; }
+    if (!h->d_ws.ensure((size_t)blocks * cpb * (size_t)arena)) { h->err = "out of device memory (workspace)"; return XM_ERR_CUDA; }
+    CK(cudaMemsetAsync(ticket, 0, 4, st));
+    CK(cudaMemsetAsync(n_need_more, 0, 4, st));
+    L.ticket = ticket; L.n_need_more = n_need_more;
+    L.ids = ids; L.n_ids = n_ids; L.n_ids_ptr = n_ids_dev; L.need_more = need_more_out; L.arenas = (char*)h->d_ws.p; L.arena_bytes = arena; L.last_tier = (tier == XM_NUM_TIERS - 1);
+    L.need_more_key = nullptr;
+    L.big_arenas = nullptr; L.big_arena_bytes = 0; L.n_big = 0; L.big_busy = nullptr;
+    if (tier >= 0 && tier + 1 < XM_NUM_TIERS && h->big_pool > 0) {
+      // a small pool of next-tier arenas inside this launch: the rare queries that outgrow their arena do not wait for a launch of their own
+      const long long big = tier_arena_bytes(tier + 1, max_seq_len, 2, (long long)h->ws_budget, (long long)h->sm_count * h->full_blocks_per_sm * h->full_warps);
+      int n_big = h->big_pool;
+      while (n_big > 0 && (long long)n_big * big > (long long)h->ws_budget / 4) n_big /= 2;
+      if (n_big > 0 && big > arena && h->d_big.ensure((size_t)n_big * (size_t)big) && h->d_big_busy.ensure((size_t)n_big * 4)) {
+        CK(cudaMemsetAsync(h->d_big_busy.p, 0, (size_t)n_big * 4, st));
+        L.big_arenas = (char*)h->d_big.p; L.big_arena_bytes = big; L.n_big = n_big; L.big_busy = (int*)h->d_big_busy.p;
       }
-      if (blocks < 1) { h->err = "workspace budget too small for one block"; return XM_ERR_CUDA; }
-      if (!h->d_ws.ensure((size_t)blocks * cpb * (size_t)arena)) { h->err = "out of device memory (workspace)"; return XM_ERR_CUDA; }
-      CK(cudaMemsetAsync(d_ints, 0, 8, st));  // ticket, n_need_more
-      L.ids = ids; L.n_ids = n_ids; L.need_more = next_ids; L.arenas = (char*)h->d_ws.p; L.arena_bytes = arena; L.last_tier = (tier == XM_NUM_TIERS - 1);
-      L.need_more_key = nullptr;
-      L.big_arenas = nullptr; L.big_arena_bytes = 0; L.n_big = 0; L.big_busy = nullptr;
-      if (tier >= 0 && tier + 1 < XM_NUM_TIERS && h->big_pool > 0) {
-        // a small pool of next-tier arenas inside this launch: the rare queries that outgrow their arena do not wait for a launch of their own
-        const long long big = tier_arena_bytes(tier + 1, max_seq_len, 2, (long long)h->ws_budget, (long long)h->sm_count * h->full_blocks_per_sm * h->full_warps);
-        int n_big = h->big_pool;
-        while (n_big > 0 && (long long)n_big * big > (long long)h->ws_budget / 4) n_big /= 2;
-        if (n_big > 0 && big > arena && h->d_big.ensure((size_t)n_big * (size_t)big) && h->d_big_busy.ensure((size_t)n_big * 4)) {
-          CK(cudaMemsetAsync(h->d_big_busy.p, 0, (size_t)n_big * 4, st));
-          L.big_arenas = (char*)h->d_big.p; L.big_arena_bytes = big; L.n_big = n_big; L.big_busy = (int*)h->d_big_busy.p;
-        }
-      }
-      if (tier < 0 && h->sort_hard) { if (!h->d_keys_a.ensure((size_t)n_ids * 4) || !h->d_keys_b.ensure((size_t)n_ids * 4)) { h->err = "out of device memory"; return XM_ERR_CUDA; } L.need_more_key = (int32_t*)h->d_keys_a.p; }
-      L.exp_dup = 0;
-      L.exp_groups = 1;
-      if (tier >= 0) { if (const char* e = getenv("XM_EXP_DUP")) L.exp_dup = atoi(e); if (const char* e = getenv("XM_EXP_GROUPS")) L.exp_groups = atoi(e) > 0 ? atoi(e) : 1; }
-      bool time_it = (round == 0 && tier == -1);
-      CK(cudaEventRecord(h->ev2, st));
-      if (tier < 0) xm_align_kernel<true><<<blocks, block, 0, st>>>(L);
-      else xm_align_kernel<false><<<blocks, 32 * cpb, 0, st>>>(L);
-      CK(cudaEventRecord(h->ev3, st));
-      launches++;
-      CK(cudaGetLastError());
-      if (tier < 0) R->r.stats[XM_STAT_EASY_QUERIES] += n_ids; else R->r.stats[XM_STAT_TIER0_QUERIES + tier] += n_ids;
+    }
+    if (tier < 0 && h->sort_hard) {
+      if (!h->d_keys_a.ensure((size_t)n_ids * 4) || !h->d_keys_b.ensure((size_t)n_ids * 4)) { h->err = "out of device memory"; return XM_ERR_CUDA; }
+      CK(cudaMemsetAsync(h->d_keys_a.p, 0x80, (size_t)n_ids * 4, st));   // slots the kernel leaves unused sort last (key 0x80808080 < 0)
+      L.need_more_key = (int32_t*)h->d_keys_a.p;
+    }
+    L.exp_dup = 0;
+    L.exp_groups = 1;
+    if (tier >= 0) { if (const char* e = getenv("XM_EXP_DUP")) L.exp_dup = atoi(e); if (const char* e = getenv("XM_EXP_GROUPS")) L.exp_groups = atoi(e) > 0 ? atoi(e) : 1; }
+    CK(cudaEventRecord(e0, st));
+    if (tier < 0) xm_align_kernel<true><<<blocks, block, 0, st>>>(L);
+    else xm_align_kernel<false><<<blocks, 32 * cpb, 0, st>>>(L);
+    CK(cudaEventRecord(e1, st));
+    launches++;
+    CK(cudaGetLastError());
+    return XM_OK;
+  };
+  // The synchronous tier loop: every launch is followed by a read-back of its counters.  Used for what the fast path below leaves
+  // over - queries that outgrew the tier-0 arenas (rare) and re-runs after growing the result arena (rarer).
+  auto run_tiers_sync = [&](int first_tier, const int32_t* ids, int n_ids, int32_t* next_ids) -> int {
+    for (int tier = first_tier; tier < XM_NUM_TIERS && n_ids > 0; tier++) {
+      int rc3 = launch_tier(tier, ids, n_ids, nullptr, next_ids, d_ints, d_ints + 1, h->ev2, h->ev3);
+      if (rc3 != XM_OK) return rc3;
+      R->r.stats[XM_STAT_TIER0_QUERIES + tier] += n_ids;
       int counts[3];
       CK(cudaMemcpyAsync(counts, d_ints, 12, cudaMemcpyDeviceToHost, st));
-      if (tier < 0) CK(cudaMemcpyAsync(easy_stats, d_stats, sizeof(easy_stats), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
-      { float t = 0; cudaEventElapsedTime(&t, h->ev2, h->ev3); if (tier < 0) easy_ms += t; else tier_ms[tier] += t; if (time_it) align_ms_tier0 = t; }
-      if (tier < 0) R->r.stats[XM_STAT_EASY_DONE] += n_ids - counts[1];
+      { float t = 0; cudaEventElapsedTime(&t, h->ev2, h->ev3); tier_ms[tier] += t; }
       int32_t* other = (next_ids == (int32_t*)h->d_ids_a.p) ? (int32_t*)h->d_ids_b.p : (int32_t*)h->d_ids_a.p;
-      if (tier < 0 && L.need_more_key && counts[1] > 1) {
-        // longest first: the persistent full kernel ends when its slowest query does, so the queries the first pass
-        // scored worst (most likely gapped) start first and the cheap ones fill the tail
-        size_t tb = 0;
-        cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, (const int32_t*)h->d_keys_a.p, (int32_t*)h->d_keys_b.p, (const int32_t*)next_ids, other, counts[1], 0, 32, st);
-        if (!h->d_sort_tmp.ensure(tb + 16)) { h->err = "out of device memory"; return XM_ERR_CUDA; }
-        CK(cub::DeviceRadixSort::SortPairsDescending(h->d_sort_tmp.p, tb, (const int32_t*)h->d_keys_a.p, (int32_t*)h->d_keys_b.p, (const int32_t*)next_ids, other, counts[1], 0, 32, st));
-        int32_t* t = next_ids; next_ids = other; other = t;
-      }
-      ids = next_ids; n_ids = counts[1];
-      next_ids = other;
+      ids = next_ids; n_ids = counts[1]; next_ids = other;
     }
-    int counts[3];
-    CK(cudaMemcpy(counts, d_ints, 12, cudaMemcpyDeviceToHost));
-    if (counts[2] == 0) break;
-    // result arena overflow: grow (keeping what was written) and re-run the affected queries
+    return XM_OK;
+  };
+  // ---- fast path: first pass over every query, class sort of the queries it hands on, tier 0 of the full aligner - three launches
+  // back to back, the count of handed-on queries stays on the device ----
+  int32_t* ids_a = (int32_t*)h->d_ids_a.p; int32_t* ids_b = (int32_t*)h->d_ids_b.p;
+  rc = launch_tier(-1, nullptr, nq, nullptr, ids_a, d_ints, d_ints + 1, h->ev2, h->ev3);
+  if (rc != XM_OK) return rc;
+  R->r.stats[XM_STAT_EASY_QUERIES] += nq;
+  CK(cudaMemcpyAsync(d_easy_stats, d_stats, 7 * 8, cudaMemcpyDeviceToDevice, st));
+  const int32_t* hard_ids = ids_a;
+  if (h->sort_hard && nq > 1) {
+    // longest first: the persistent full kernel ends when its slowest query does, so the queries the first pass scored worst (most
+    // likely gapped) start first and the cheap ones fill the tail; co-resident warps also run the same kind of query, which the
+    // instruction caches reward.  All nq slots are sorted (the unused ones carry the smallest key), so no count is needed here.
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, (const int32_t*)h->d_keys_a.p, (int32_t*)h->d_keys_b.p, (const int32_t*)ids_a, ids_b, nq, 0, 32, st);
+    if (!h->d_sort_tmp.ensure(tb + 16)) { h->err = "out of device memory"; return XM_ERR_CUDA; }
+    CK(cub::DeviceRadixSort::SortPairsDescending(h->d_sort_tmp.p, tb, (const int32_t*)h->d_keys_a.p, (int32_t*)h->d_keys_b.p, (const int32_t*)ids_a, ids_b, nq, 0, 32, st));
+    hard_ids = ids_b;
+  }
+  int32_t* t0_need_more = (hard_ids == ids_a) ? ids_b : ids_a;
+  rc = launch_tier(0, hard_ids, nq, d_ints + 1, t0_need_more, d_ints + 4, d_ints + 5, h->ev4, h->ev5);
+  if (rc != XM_OK) return rc;
+  int fast_counts[8];
+  long long real_seqs_total = 0;
+  CK(cudaMemcpyAsync(&real_seqs_total, (const long long*)h->d_first_seq.p + nq, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(fast_counts, d_ints, 32, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(easy_stats, d_easy_stats, sizeof(easy_stats), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));   // sync 1 of 3 per batch
+  { float t = 0; cudaEventElapsedTime(&t, h->ev2, h->ev3); easy_ms = t; align_ms_tier0 = t; cudaEventElapsedTime(&t, h->ev4, h->ev5); tier_ms[0] += t; }
+  R->r.stats[XM_STAT_EASY_DONE] += nq - fast_counts[1];
+  R->r.stats[XM_STAT_TIER0_QUERIES] += fast_counts[1];
+  if (fast_counts[5] > 0) {   // queries that outgrew the tier-0 arenas (and found no pooled big arena)
+    rc = run_tiers_sync(1, t0_need_more, fast_counts[5], (t0_need_more == ids_a) ? ids_b : ids_a);
+    if (rc != XM_OK) return rc;
+  }
+  for (int round = 0; round < 4; round++) {   // result arena overflow: grow (keeping what was written) and re-run the affected queries
+    int n_full = 0;
+    CK(cudaMemcpy(&n_full, d_ints + 2, 4, cudaMemcpyDeviceToHost));
+    if (n_full == 0) break;
     unsigned long long used[3];
     CK(cudaMemcpy(used, d_used, 24, cudaMemcpyDeviceToHost));
     auto grow = [&](DevBuf& b, long long& cap, unsigned long long& u, size_t elem) -> bool {
@@ -1152,17 +1227,19 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
     L.out.choices = (OutChoice*)h->d_choices.p; L.out.cap_choices = h->cap_choices; L.out.sas = (OutSA*)h->d_sas.p; L.out.cap_sas = h->cap_sas;
     L.out.blocks = (int32_t*)h->d_blocks.p; L.out.cap_blocks = h->cap_blocks;
     // the out_full list becomes the id list of the next round (copy it, the kernel will append to it again)
-    CK(cudaMemcpy(h->d_ids_a.p, h->d_ids_full.p, (size_t)counts[2] * 4, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(ids_a, h->d_ids_full.p, (size_t)n_full * 4, cudaMemcpyDeviceToDevice));
     CK(cudaMemset(d_ints + 2, 0, 4));
-    ids = (const int32_t*)h->d_ids_a.p; n_ids = counts[2]; next_ids = (int32_t*)h->d_ids_b.p;
+    rc = run_tiers_sync(0, ids_a, n_full, ids_b);
+    if (rc != XM_OK) return rc;
   }
+  CountsPending counts_pending; unsigned long long var_n_after = 0;
   if (h->counts_enabled) {
-    int rc2 = accumulate_counts(h, L, nq, n_seqs_total, launches);
+    int rc2 = counts_enqueue(h, L, nq, real_seqs_total, launches, counts_pending, &var_n_after);
     if (rc2 != XM_OK) return rc2;
   }
   // D2H
   unsigned long long misc[20];
-  CK(cudaMemcpyAsync(misc, h->d_misc.p, sizeof(misc), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(misc, h->d_misc.p, sizeof(misc), cudaMemcpyDeviceToHost, st));   // complete at sync 2
   // CSR assembly on the device, then one transfer into a pinned slab
   const bool host_times = getenv("XM_HOST_TIMES") != nullptr;
   const double t_csr0 = now_ms();
@@ -1175,7 +1252,12 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
   for (int k = 0; k < 4; k++) { size_t tb = scan_tmp; CK(cub::DeviceScan::ExclusiveSum(h->d_csr_tmp.p, tb, d_cnt + k * stride, d_base + k * stride, (int)stride, st)); }
   long long totals[4];
   for (int k = 0; k < 4; k++) CK(cudaMemcpyAsync(&totals[k], d_base + k * stride + nq, 8, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  CK(cudaStreamSynchronize(st));   // sync 2 of 3 per batch
+  CK(cudaGetLastError());
+  if (h->counts_enabled) {
+    int rc2 = counts_finish(h, L, nq, launches, counts_pending, var_n_after);
+    if (rc2 != XM_OK) return rc2;
+  }
   const long long n_comp = totals[0], n_ch = totals[1], n_sa = totals[2], n_blk = totals[3];
   {
     int64_t n[11] = {(int64_t)nq + 1, n_comp + 1, n_ch + 1, n_sa + 1, 4 * n_ch, 2 * n_sa, n_ch, n_sa, 4 * n_blk, (int64_t)nq, n_sa};
@@ -1223,6 +1305,11 @@ int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, in
   return XM_OK;
 }
 
+int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, int64_t n_words, const int64_t* d_seq_word_off, const int32_t* d_seq_len,
+                          const uint8_t* d_n_seqs, const double* d_expected, const double* d_per, int32_t max_seq_len, xm_results** out) {
+  return align_batch_impl(h, nq, d_packed, n_words, d_seq_word_off, d_seq_len, d_n_seqs, d_expected, d_per, max_seq_len, -1, out);
+}
+
 int xm_align_batch(xm_handle* h, int32_t nq, const uint16_t* packed4, const int64_t* seq_word_off, const int32_t* seq_len, const uint8_t* n_seqs,
                    const double* expected_inner, const double* per_penalty, xm_results** out) {
   if (out) *out = nullptr;
@@ -1249,11 +1336,10 @@ int xm_align_batch(xm_handle* h, int32_t nq, const uint16_t* packed4, const int6
     CK(cudaMemcpyAsync(h->d_n_seqs.p, n_seqs, (size_t)nq, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_expected.p, expected_inner ? expected_inner : zeros.data(), (size_t)nq * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_per.p, per_penalty ? per_penalty : ones.data(), (size_t)nq * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));
-  }
+  }   // no synchronisation: the kernels are ordered behind the copies on the stream (zeros / ones live until this function returns)
   const double t_h2d = now_ms();
-  int rc = xm_align_batch_device(h, nq, (const uint16_t*)h->d_packed.p, n_words, (const int64_t*)h->d_seq_word_off.p, (const int32_t*)h->d_seq_len.p,
-                                 (const uint8_t*)h->d_n_seqs.p, (const double*)h->d_expected.p, (const double*)h->d_per.p, max_len, out);
+  int rc = align_batch_impl(h, nq, (const uint16_t*)h->d_packed.p, n_words, (const int64_t*)h->d_seq_word_off.p, (const int32_t*)h->d_seq_len.p,
+                            (const uint8_t*)h->d_n_seqs.p, (const double*)h->d_expected.p, (const double*)h->d_per.p, max_len, n_seqs_total, out);
   if (*out) (*out)->r.stats[XM_STAT_H2D_BYTES] = (int64_t)((size_t)n_words * 2 + ((size_t)n_seqs_total + 1) * 8 + (size_t)n_seqs_total * 4 + (size_t)nq * 17);
   if (host_times && *out) fprintf(stderr, "[xm] xm_align_batch: validate+H2D %.1f ms, device call %.1f ms (kernels %.1f ms)\n", t_h2d - t_in, now_ms() - t_h2d, (double)(*out)->r.stats[XM_STAT_KERNEL_NS] / 1e6);
   return rc;
@@ -1322,8 +1408,9 @@ int xm_counts_enable(xm_handle* h, double query_end_fraction) {
   for (int c = 0; c < h->m.n_contigs; c++) off[(size_t)c + 1] = off[(size_t)c] + h->m.len[(size_t)c];
   h->n_plane_ints = off[(size_t)h->m.n_contigs] * 4;
   if (!h->d_planes.ensure((size_t)h->n_plane_ints * 4) || !h->d_contig_off.ensure(off.size() * 8)) { h->err = "out of device memory (count planes)"; return XM_ERR_CUDA; }
-  CK(cudaMemset(h->d_planes.p, 0, (size_t)h->n_plane_ints * 4));
-  CK(cudaMemcpy(h->d_contig_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemsetAsync(h->d_planes.p, 0, (size_t)h->n_plane_ints * 4, h->stream));   // ordered before the next batch's kernels on the handle's stream
+  CK(cudaMemcpyAsync(h->d_contig_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   h->end_fraction = query_end_fraction; h->counts_enabled = true;
   h->var_n = 0; h->var_reduced_n = 0; h->next_gid = 0; h->have_batch_info = false;
   return XM_OK;
@@ -1422,6 +1509,37 @@ int xm_variants_fetch(xm_handle* h, int64_t* n, uint64_t* keys, int32_t* counts,
     if (ex_gid) ex_gid[i] = host[i].ex_gid;
     if (ex_index) ex_index[i] = host[i].ex_index;
   }
+  return XM_OK;
+}
+
+// out[0] INT32 IMAD, out[1] FP64 DADD, out[2] interleaved FP32 FFMA + integer IADD3 (dispatch ceiling): sustained warp-instructions per second over the whole chip (the loop
+// bodies are 128 arithmetic instructions per iteration per warp; loop overhead is below 2 %); out[3] = SM count, out[4] = SM clock in Hz
+// (cudaDevAttrClockRate: the maximum; the achieved clock under load is sampled by the caller).
+int xm_measure_peaks(xm_handle* h, double* out) {
+  if (!h || !out) return XM_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  if (!h->d_misc.ensure(256)) { h->err = "out of device memory"; return XM_ERR_CUDA; }
+  const int blocks = h->sm_count * 8, threads = 256, iters = 2000;
+  const double warp_inst = (double)blocks * (threads / 32) * (double)iters * 128.0;
+  for (int kind = 0; kind < 3; kind++) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+      CK(cudaEventRecord(h->ev2, st));
+      if (kind == 0) xm_peak_kernel<0><<<blocks, threads, 0, st>>>(iters, (unsigned long long*)h->d_misc.p, 3.0);
+      else if (kind == 1) xm_peak_kernel<1><<<blocks, threads, 0, st>>>(iters, (unsigned long long*)h->d_misc.p, 1e-9);
+      else xm_peak_kernel<2><<<blocks, threads, 0, st>>>(iters, (unsigned long long*)h->d_misc.p, 12345.0);
+      CK(cudaEventRecord(h->ev3, st));
+      CK(cudaStreamSynchronize(st));
+      CK(cudaGetLastError());
+      float ms = 0; cudaEventElapsedTime(&ms, h->ev2, h->ev3);
+      if (rep > 0 && ms < best) best = ms;
+    }
+    out[kind] = warp_inst / ((double)best * 1e-3);
+  }
+  int clk_khz = 0;
+  cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, h->device);
+  out[3] = (double)h->sm_count; out[4] = (double)clk_khz * 1e3;
   return XM_OK;
 }
 int xm_counts_device_ptr(xm_handle* h, void** d_ptr, int64_t* n_int32) {
