@@ -391,14 +391,14 @@ def main():
         pk = prof.get(dom_key) or {}
         # The bound that binds is instruction issue (pyramid build and gapped search are issue-bound; the index gathers move
         # < 0.1 % of the HBM roofline).  achieved = warp-instructions of one launch (ncu smsp__inst_executed.sum of the same command) / the
-        # launch duration measured live; peak = the dispatch ceiling measured live by xm_measure_peaks (FFMA + IADD3 chains on every SM).
+        # launch duration measured live; peak = the dispatch ceiling measured live by xm_measure_peaks (FFMA chains on every SM).
         issue_peak = peaks_issue["alu"]
         warp_inst = pk.get("warp_instructions")
         issue_achieved = (warp_inst / (dom_ms / 1e3)) if (warp_inst and dom_ms > 0) else None
         lanes = pk.get("active_lanes_per_instruction")
         roof = dict(bound="issue", kernel=dom_name, achieved=(issue_achieved / 1e9 if issue_achieved else None), peak=issue_peak / 1e9, unit="G warp-instructions/s",
                     frac=(issue_achieved / issue_peak if issue_achieved else None),
-                    peak_source="measured live: xm_measure_peaks (interleaved FFMA + IADD3 chains, all SMs, CUDA events); INT32 IMAD %.0f G/s, FP64 DADD %.0f G/s" % (peaks_issue["int32"] / 1e9, peaks_issue["fp64"] / 1e9),
+                    peak_source="measured live: xm_measure_peaks (independent FFMA chains on every SM = one warp-instruction per scheduler per clock, CUDA events); INT32 IMAD %.0f G/s, FP64 DADD %.0f G/s" % (peaks_issue["int32"] / 1e9, peaks_issue["fp64"] / 1e9),
                     achieved_source=(prof.get("source") if warp_inst else "no ncu capture for this workload: issue rate not quoted"),
                     kernel_ms_per_launch=dom_ms,
                     useful_thread_instruction_fraction=((issue_achieved / issue_peak) * (pk["useful_lanes_per_instruction"] / 32.0) if (issue_achieved and pk.get("useful_lanes_per_instruction")) else None),

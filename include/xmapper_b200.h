@@ -191,8 +191,8 @@ int xm_counts_fetch(xm_handle* h, int32_t contig, int32_t* out /* 4 * contig len
 int xm_variants_fetch(xm_handle* h, int64_t* n, uint64_t* keys, int32_t* counts, int64_t* ex_gid, int32_t* ex_index /* NULL arrays: size query */);
 
 /* Measurement aid (bench.py's roofline): sustained issue rates of this GPU, in warp-instructions per second over the whole chip,
- * from three micro-benchmark kernels timed with CUDA events - out[0] INT32 (IMAD chains), out[1] FP64 (DADD chains), out[2] mixed
- * integer ALU (the issue-slot ceiling); out[3] = number of SMs, out[4] = maximum SM clock in Hz.  SURVEY.md §8(d) takes the relevant
+ * from three micro-benchmark kernels timed with CUDA events - out[0] INT32 (IMAD chains), out[1] FP64 (DADD chains), out[2] FP32
+ * FFMA chains (full-rate pipe: the issue-slot ceiling); out[3] = number of SMs, out[4] = maximum SM clock in Hz.  SURVEY.md §8(d) takes the relevant
  * peaks of this path (instruction issue, FP64 pipe) from such a measurement on the box rather than from a datasheet. */
 int xm_measure_peaks(xm_handle* h, double* out /* 5 doubles */);
 

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(EASY ? XM_BLOCK : XM_FULL_BLOCK, EASY ? XM_MIN
     q.per_penalty = q.n_seqs > 1 ? L.batch.per_penalty[qi] : 1.0;
     OutQuery rec; rec.status = 0; rec.n_comp = 1; rec.n_choice[0] = 0; rec.n_choice[1] = 0; rec.choice_first[0] = 0; rec.choice_first[1] = 0;
     w.hard_hint = 1 << 20;  // anything but Q_HARD (workspace exhausted in the first pass): assume long
-    if (!ws_init(w, arena, L.arena_bytes, &L.ref, &L.ix, &L.dup, L.prm, q)) w.status = Q_NEED_MORE;
+    if (!ws_init(w, arena, L.arena_bytes, &L.ref, &L.ix, &L.dup, L.prm, q, !EASY)) w.status = Q_NEED_MORE;
     else align_query<EASY>(w, L.out, rec);
     __syncwarp();
     int status = w.status;
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(EASY ? XM_BLOCK : XM_FULL_BLOCK, EASY ? XM_MIN
       slot = __shfl_sync(0xffffffffu, slot, 0);
       if (slot >= 0) {
         rec.status = 0; rec.n_comp = 1; rec.n_choice[0] = 0; rec.n_choice[1] = 0; rec.choice_first[0] = 0; rec.choice_first[1] = 0;
-        if (!ws_init(w, L.big_arenas + (long long)slot * L.big_arena_bytes, L.big_arena_bytes, &L.ref, &L.ix, &L.dup, L.prm, q)) w.status = Q_NEED_MORE;
+        if (!ws_init(w, L.big_arenas + (long long)slot * L.big_arena_bytes, L.big_arena_bytes, &L.ref, &L.ix, &L.dup, L.prm, q, true)) w.status = Q_NEED_MORE;
         else align_query<EASY>(w, L.out, rec);
         __syncwarp();
         status = w.status;
@@ -172,20 +172,18 @@ __global__ void __launch_bounds__(256) xm_peak_kernel(int iters, unsigned long l
       for (int k = 0; k < 16; k++) { a0 += a1; a1 += a2; a2 += a3; a3 += a4; a4 += a5; a5 += a6; a6 += a7; a7 += a0; }
     }
     if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 0.123) sink[0] = 1;
-  } else {                  // the issue-slot ceiling: FP32 FFMA and integer LOP3 chains IADD3 chains interleaved (two pipes, one dispatch port per scheduler)
-    unsigned a0 = tid, a1 = tid + 1, a2 = tid + 2, a3 = tid + 3;
-    float f0 = (float)seed, f1 = f0 + 1.0f, f2 = f0 + 2.0f, f3 = f0 + 3.0f;
-    const unsigned m = (unsigned)seed;
+  } else {                  // the issue-slot ceiling: 8 independent FP32 FFMA chains (full-rate pipe: one warp-instruction per scheduler per clock)
+    float f0 = (float)seed, f1 = f0 + 1.0f, f2 = f0 + 2.0f, f3 = f0 + 3.0f, f4 = f0 + 4.0f, f5 = f0 + 5.0f, f6 = f0 + 6.0f, f7 = f0 + 7.0f;
     const float c = (float)seed * 1e-9f;
     #pragma unroll 1
     for (int i = 0; i < iters; i++) {
       #pragma unroll
       for (int k = 0; k < 16; k++) {
-        a0 = a0 + a1 + m; f0 = __fmaf_rn(f0, c, f1); a1 = a1 + a2 + m; f1 = __fmaf_rn(f1, c, f2);
-        a2 = a2 + a3 + m; f2 = __fmaf_rn(f2, c, f3); a3 = a3 + a0 + m; f3 = __fmaf_rn(f3, c, f0);
+        f0 = __fmaf_rn(f0, c, f1); f1 = __fmaf_rn(f1, c, f2); f2 = __fmaf_rn(f2, c, f3); f3 = __fmaf_rn(f3, c, f4);
+        f4 = __fmaf_rn(f4, c, f5); f5 = __fmaf_rn(f5, c, f6); f6 = __fmaf_rn(f6, c, f7); f7 = __fmaf_rn(f7, c, f0);
       }
     }
-    if ((a0 ^ a1 ^ a2 ^ a3) == 0x7fffffffu || f0 + f1 + f2 + f3 == 0.123f) sink[0] = a0;
+    if (f0 + f1 + f2 + f3 + f4 + f5 + f6 + f7 == 0.123f) sink[0] = 1;
   }
 }
 
@@ -1125,6 +1123,8 @@ static int align_batch_impl(xm_handle* h, int32_t nq, const uint16_t* d_packed, 
     if (!h->d_ws.ensure((size_t)blocks * cpb * (size_t)arena)) { h->err = "out of device memory (workspace)"; return XM_ERR_CUDA; }
     CK(cudaMemsetAsync(ticket, 0, 4, st));
     CK(cudaMemsetAsync(n_need_more, 0, 4, st));
+    // generation word of every arena's lattice map: 0 = not used since this launch began (whatever the buffer held before)
+    if (tier >= 0) CK(cudaMemset2DAsync(h->d_ws.p, (size_t)arena, 0, 16, (size_t)blocks * cpb, st));
     L.ticket = ticket; L.n_need_more = n_need_more;
     L.ids = ids; L.n_ids = n_ids; L.n_ids_ptr = n_ids_dev; L.need_more = need_more_out; L.arenas = (char*)h->d_ws.p; L.arena_bytes = arena; L.last_tier = (tier == XM_NUM_TIERS - 1);
     L.need_more_key = nullptr;
@@ -1136,6 +1136,7 @@ static int align_batch_impl(xm_handle* h, int32_t nq, const uint16_t* d_packed, 
       while (n_big > 0 && (long long)n_big * big > (long long)h->ws_budget / 4) n_big /= 2;
       if (n_big > 0 && big > arena && h->d_big.ensure((size_t)n_big * (size_t)big) && h->d_big_busy.ensure((size_t)n_big * 4)) {
         CK(cudaMemsetAsync(h->d_big_busy.p, 0, (size_t)n_big * 4, st));
+        CK(cudaMemset2DAsync(h->d_big.p, (size_t)big, 0, 16, (size_t)n_big, st));
         L.big_arenas = (char*)h->d_big.p; L.big_arena_bytes = big; L.n_big = n_big; L.big_busy = (int*)h->d_big_busy.p;
       }
     }
@@ -1512,7 +1513,7 @@ int xm_variants_fetch(xm_handle* h, int64_t* n, uint64_t* keys, int32_t* counts,
   return XM_OK;
 }
 
-// out[0] INT32 IMAD, out[1] FP64 DADD, out[2] interleaved FP32 FFMA + integer IADD3 (dispatch ceiling): sustained warp-instructions per second over the whole chip (the loop
+// out[0] INT32 IMAD, out[1] FP64 DADD, out[2] FP32 FFMA (full-rate pipe = the dispatch ceiling): sustained warp-instructions per second over the whole chip (the loop
 // bodies are 128 arithmetic instructions per iteration per warp; loop overhead is below 2 %); out[3] = SM count, out[4] = SM clock in Hz
 // (cudaDevAttrClockRate: the maximum; the achieved clock under load is sampled by the caller).
 int xm_measure_peaks(xm_handle* h, double* out) {

@@ -237,6 +237,7 @@ struct WS {
     if (scratch_top + bytes > scratch_size) { fail(Q_NEED_MORE); return nullptr; }
     void* p = scratch + scratch_top; scratch_top += bytes; return p;
   }
+  uint32_t* cell_hdr; uint32_t* cellmap; long long cell_words;  // PathAligner lattice map region of the arena (xm_align.h: PathState::cell)
   uint8_t* qbytes[2][2];  // [mate][reverse-complemented]: one code per byte
   int hard_hint;  // first pass: cost estimate of a query handed to the full kernel (its ungapped penalty), used to start long queries first
   XM_INLINE SeqView query_view(int mate, int rev) const { SeqView v = query.seq[mate]; v.rc = rev; v.bytes = qbytes[mate][rev]; v.b0 = 0; v.bn = v.len; return v; }

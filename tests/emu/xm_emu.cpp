@@ -2,6 +2,7 @@
 // It lets the kernel logic be compared with the oracle on a box without a GPU, one query per loop iteration,
 // with the same workspace tiers the CUDA launcher uses.  It is NOT part of the product: libxmapper_b200.so never
 // contains this file and has no CPU path.
+#include <cstring>
 #include "../../mapper_b200/csrc/xm_align.h"
 #include "../../mapper_b200/csrc/xm_host_model.h"
 #include "../../mapper_b200/csrc/xm_results.h"
@@ -100,7 +101,7 @@ void* xe_align_batch(void* h, int nq, const uint16_t* packed, const int64_t* seq
         OutArena out; out.q = oq.data(); out.choices = choices.data(); out.cap_choices = capc; out.sas = sas.data(); out.cap_sas = caps;
         out.blocks = blocks.data(); out.cap_blocks = capb; out.stats = nullptr;
         OutQuery rec; rec.status = 0; rec.n_comp = 1; rec.n_choice[0] = rec.n_choice[1] = 0; rec.choice_first[0] = rec.choice_first[1] = 0;
-        if (ws_init(w, easy_arena.data(), bytes, &ref, &ix, &dup, M.prm, q)) {
+        if (ws_init(w, easy_arena.data(), bytes, &ref, &ix, &dup, M.prm, q, false)) {
           std::lock_guard<std::mutex> lock(mu);
           out.used = used;
           align_query<true>(w, out, rec);
@@ -112,7 +113,7 @@ void* xe_align_batch(void* h, int nq, const uint16_t* packed, const int64_t* seq
       }
       for (int tier = 0; tier < XM_NUM_TIERS && tier <= max_tier && status == Q_NEED_MORE; tier++) {
         long long bytes = tier_arena_bytes(tier, max_len, 2);
-        if ((long long)arenas[(size_t)tier].size() < bytes) arenas[(size_t)tier].resize((size_t)bytes);
+        if ((long long)arenas[(size_t)tier].size() < bytes) { arenas[(size_t)tier].resize((size_t)bytes); memset(arenas[(size_t)tier].data(), 0, 16); }  // generation word of the lattice map: 0 = clear before use
         WS w;
         OutArena out; out.q = oq.data(); out.choices = choices.data(); out.cap_choices = capc; out.sas = sas.data(); out.cap_sas = caps;
         out.blocks = blocks.data(); out.cap_blocks = capb; out.stats = nullptr;
