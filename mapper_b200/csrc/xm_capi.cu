@@ -19,6 +19,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <mutex>
+#include <condition_variable>
 #include <string>
 #include <vector>
 #include <cstdio>
@@ -600,7 +601,7 @@ struct PinnedPool {
 };
 struct xm_results {
   ResultsHost r;
-  uint64_t serial = 0; int nq = 0;           // which xm_align_batch of the handle produced it
+  uint64_t serial = 0; int nq = 0, slot = -1;   // which batch slot of the handle holds its device copy, and that slot's use counter at the time
   void* sam = nullptr; size_t sam_cap = 0;   // pinned text of the latest xm_format_sam (from the same pool as the slab)
   std::shared_ptr<PinnedPool> pool; void* slab = nullptr; size_t slab_cap = 0;
   ~xm_results() { if (slab && pool) pool->give(slab, slab_cap); if (sam && pool) pool->give(sam, sam_cap); }
@@ -648,18 +649,30 @@ struct xm_handle {
   int full_warps = XM_FULL_BLOCK / 32, full_blocks_per_sm = XM_FULL_MIN_BLOCKS;  // full kernel: warps per block, blocks per SM
   std::string err;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev5 = nullptr;
+  cudaEvent_t ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev5 = nullptr;
   // device mirror of the model
   uint64_t mirrored_generation = ~0ull;
   DevBuf d_words, d_word_off, d_len, d_gstart, d_tables, d_dup_off, d_dup_starts;
   std::vector<DevBuf> d_buckets, d_positions;
   RefD ref{}; IndexD ix{}; DupD dup{};
-  // batch staging + results + workspace
-  DevBuf d_packed, d_seq_word_off, d_seq_len, d_n_seqs, d_expected, d_per, d_first_seq, d_chunk;
+  // Batches in flight.  A call of xm_align_batch owns one slot from its first host->device copy to its last device->host copy: the
+  // slot's staging buffers, its copy stream and its device copy of the result arrays.  The kernels of different calls run one after
+  // the other on `stream` (compute_mu + the order of the events), so the copies of one call overlap the kernels of another:
+  // concurrent callers on one handle (M/Api.java:78, M/Mapper.java:1026-1040: N AlignerWorkers) keep the GPU busy back to back.
+  struct BatchSlot {
+    DevBuf d_packed, d_seq_word_off, d_seq_len, d_n_seqs, d_expected, d_per, d_first_seq, d_csr_slab;
+    cudaStream_t copy = nullptr; cudaEvent_t h2d_done = nullptr, kernels_done = nullptr, ev0 = nullptr, ev1 = nullptr;
+    BatchD batch{}; uint64_t serial = 0, last_use = 0; bool busy = false;
+  };
+  uint64_t use_counter = 0;
+  static const int N_SLOTS = 3;
+  BatchSlot slots[N_SLOTS];
+  std::mutex slot_mu; std::condition_variable slot_cv;
+  std::mutex compute_mu;     // everything that launches kernels on `stream` or touches the shared work buffers below
+  DevBuf d_chunk;
   DevBuf d_q, d_choices, d_sas, d_blocks, d_misc, d_ids_a, d_ids_b, d_ids_full, d_ws, d_qcycles;
-  DevBuf d_csr_cnt, d_csr_base, d_csr_tmp, d_csr_slab, d_keys_a, d_keys_b, d_sort_tmp, d_big, d_big_busy;
+  DevBuf d_csr_cnt, d_csr_base, d_csr_tmp, d_keys_a, d_keys_b, d_sort_tmp, d_big, d_big_busy;
   DevBuf d_sam_len, d_sam_text, d_sam_names, d_sam_name_off, d_sam_cnames, d_sam_cname_off;
-  BatchD last_batch{}; uint64_t batch_serial = 0;   // what xm_format_sam reads: the batch and CSR slab of the latest xm_align_batch
   std::shared_ptr<PinnedPool> pinned = std::make_shared<PinnedPool>();
   bool probe_cycles = false, sort_hard = true;
   int big_pool = 64;  // XM_BIG_POOL: next-tier arenas available inside a full-kernel launch (0 = off)
@@ -679,6 +692,21 @@ struct xm_handle {
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return XM_ERR_CUDA; } } while (0)
+// RAII lease of a batch slot: the least recently used free one, so that the device copies of recent results live as long as possible
+struct SlotLease {
+  xm_handle* h; int i;
+  explicit SlotLease(xm_handle* hh) : h(hh), i(-1) {
+    std::unique_lock<std::mutex> g(h->slot_mu);
+    while (true) {
+      for (int k = 0; k < xm_handle::N_SLOTS; k++) if (!h->slots[k].busy && (i < 0 || h->slots[k].last_use < h->slots[i].last_use)) i = k;
+      if (i >= 0) break;
+      h->slot_cv.wait(g);
+    }
+    h->slots[i].busy = true; h->slots[i].last_use = ++h->use_counter; h->slots[i].serial++;
+  }
+  ~SlotLease() { { std::lock_guard<std::mutex> g(h->slot_mu); h->slots[i].busy = false; } h->slot_cv.notify_one(); }
+  xm_handle::BatchSlot& slot() { return h->slots[i]; }
+};
 
 static int mirror_model(xm_handle* h) {
   HostModel& M = h->m;
@@ -739,10 +767,17 @@ int xm_create(const xm_params* p, int device, xm_handle** out) {
   if (const char* e = getenv("XM_BIG_POOL")) { int v = atoi(e); if (v >= 0 && v <= 1024) h->big_pool = v; }
   if (const char* e = getenv("XM_FULL_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) h->full_blocks_per_sm = v; }
   if (const char* e = getenv("XM_FULL_WARPS")) { int v = atoi(e); if (v >= 1 && v <= XM_FULL_BLOCK / 32) h->full_warps = v; }
-  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&h->ev2) != cudaSuccess || cudaEventCreate(&h->ev3) != cudaSuccess || cudaEventCreate(&h->ev4) != cudaSuccess || cudaEventCreate(&h->ev5) != cudaSuccess) {
     fprintf(stderr, "xmapper_b200: stream/event creation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
     xm_destroy(h); return XM_ERR_CUDA;
+  }
+  for (auto& sl : h->slots) {
+    if (cudaStreamCreateWithFlags(&sl.copy, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&sl.kernels_done, cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&sl.ev0) != cudaSuccess || cudaEventCreate(&sl.ev1) != cudaSuccess) {
+      fprintf(stderr, "xmapper_b200: stream/event creation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+      xm_destroy(h); return XM_ERR_CUDA;
+    }
   }
   size_t stack = 8 * 1024;  // the call graph has no cycle any more: ptxas reports 3.5 KB for the deepest chain; 8 KB leaves margin without reserving 10 GB of local memory
   if (const char* e = getenv("XM_STACK_BYTES")) stack = (size_t)atoll(e);
@@ -774,21 +809,26 @@ void xm_destroy(xm_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->comm && nccl_api().ok) { nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
-  DevBuf* bufs[] = {&h->d_words, &h->d_word_off, &h->d_len, &h->d_gstart, &h->d_tables, &h->d_dup_off, &h->d_dup_starts, &h->d_packed, &h->d_seq_word_off,
-                    &h->d_seq_len, &h->d_n_seqs, &h->d_expected, &h->d_per, &h->d_first_seq, &h->d_chunk, &h->d_q, &h->d_choices, &h->d_sas, &h->d_blocks,
-                    &h->d_misc, &h->d_ids_a, &h->d_ids_b, &h->d_ids_full, &h->d_ws, &h->d_qcycles, &h->d_csr_cnt, &h->d_csr_base, &h->d_csr_tmp, &h->d_csr_slab, &h->d_keys_a, &h->d_keys_b, &h->d_sort_tmp, &h->d_big, &h->d_big_busy, &h->d_sam_len, &h->d_sam_text, &h->d_sam_names, &h->d_sam_name_off, &h->d_sam_cnames, &h->d_sam_cname_off, &h->d_planes, &h->d_contig_off, &h->d_var, &h->d_var_n, &h->d_order, &h->d_var_sizes,
+  for (auto& sl : h->slots) {
+    for (DevBuf* b : {&sl.d_packed, &sl.d_seq_word_off, &sl.d_seq_len, &sl.d_n_seqs, &sl.d_expected, &sl.d_per, &sl.d_first_seq, &sl.d_csr_slab}) b->release();
+    if (sl.copy) cudaStreamDestroy(sl.copy);
+    for (cudaEvent_t e : {sl.h2d_done, sl.kernels_done, sl.ev0, sl.ev1}) if (e) cudaEventDestroy(e);
+  }
+  DevBuf* bufs[] = {&h->d_words, &h->d_word_off, &h->d_len, &h->d_gstart, &h->d_tables, &h->d_dup_off, &h->d_dup_starts, &h->d_chunk, &h->d_q, &h->d_choices, &h->d_sas, &h->d_blocks,
+                    &h->d_misc, &h->d_ids_a, &h->d_ids_b, &h->d_ids_full, &h->d_ws, &h->d_qcycles, &h->d_csr_cnt, &h->d_csr_base, &h->d_csr_tmp, &h->d_keys_a, &h->d_keys_b, &h->d_sort_tmp, &h->d_big, &h->d_big_busy, &h->d_sam_len, &h->d_sam_text, &h->d_sam_names, &h->d_sam_name_off, &h->d_sam_cnames, &h->d_sam_cname_off, &h->d_planes, &h->d_contig_off, &h->d_var, &h->d_var_n, &h->d_order, &h->d_var_sizes,
                     &h->var_scratch.keys_a, &h->var_scratch.keys_b, &h->var_scratch.idx_a, &h->var_scratch.idx_b, &h->var_scratch.gathered, &h->var_scratch.out_keys, &h->var_scratch.n_out, &h->var_scratch.tmp};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : h->d_buckets) b.release();
   for (auto& b : h->d_positions) b.release();
   if (h->stream) cudaStreamDestroy(h->stream);
-  for (cudaEvent_t e : {h->ev0, h->ev1, h->ev2, h->ev3, h->ev4, h->ev5}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {h->ev2, h->ev3, h->ev4, h->ev5}) if (e) cudaEventDestroy(e);
   delete h;
 }
 const char* xm_last_error(const xm_handle* h) { return h ? h->err.c_str() : "null handle"; }
 
 int xm_set_reference(xm_handle* h, int32_t n, const uint16_t* const* packed4, const int32_t* lengths) {
   if (!h || n < 1 || !packed4 || !lengths) return XM_ERR_ARG;
+  std::lock_guard<std::mutex> compute(h->compute_mu);
   long long total = 0;
   for (int i = 0; i < n; i++) { if (lengths[i] < 1) { h->err = "contig of length < 1"; return XM_ERR_ARG; } total += lengths[i]; }
   if (2 * total >= (1LL << 32)) { h->err = "reference too large for 32-bit global positions"; return XM_ERR_ARG; }
@@ -921,6 +961,7 @@ static int build_index_device(xm_handle* h, int max_used) {
 
 int xm_build_index(xm_handle* h, int32_t max_used, int32_t n_threads) {
   if (!h) return XM_ERR_ARG;
+  std::lock_guard<std::mutex> compute(h->compute_mu);
   if (h->m.n_contigs < 1) { h->err = "reference not set"; return XM_ERR_STATE; }
   if (n_threads <= 0) { CK(cudaSetDevice(h->device)); return build_index_device(h, max_used); }  // the device builder; n_threads > 0: the host builder it is checked against
   if (!h->m.build_index(max_used, n_threads, h->err)) return XM_ERR_ARG;
@@ -943,6 +984,7 @@ int xm_set_duplications(xm_handle* h, int32_t window, double granularity, int32_
 }
 int xm_build_duplications(xm_handle* h, int32_t min_len, int32_t max_len, int32_t min_copies, int32_t window) {
   if (!h || window < 1) return XM_ERR_ARG;
+  std::lock_guard<std::mutex> compute(h->compute_mu);
   if (!h->m.index_finished) { h->err = "index not set"; return XM_ERR_STATE; }
   h->m.build_duplications(min_len, max_len, min_copies, window);
   return XM_OK;
@@ -1024,36 +1066,37 @@ struct NSeqsAt {   // n_seqs_per_query[i] as int64, 0 past the end
   const uint8_t* p; int n;
   __host__ __device__ long long operator()(int i) const { return i < n ? (long long)p[i] : 0LL; }
 };
-static int align_batch_impl(xm_handle* h, int32_t nq, const uint16_t* d_packed, int64_t n_words, const int64_t* d_seq_word_off, const int32_t* d_seq_len,
+static int align_batch_impl(xm_handle* h, SlotLease& lease, bool wait_h2d, int32_t nq, const uint16_t* d_packed, int64_t n_words, const int64_t* d_seq_word_off, const int32_t* d_seq_len,
                             const uint8_t* d_n_seqs, const double* d_expected, const double* d_per, int32_t max_seq_len, long long n_seqs_total_hint, xm_results** out) {
+  xm_handle::BatchSlot& slot = lease.slot();
   if (out) *out = nullptr;
   if (!h || nq < 0 || !out) return XM_ERR_ARG;
   CK(cudaSetDevice(h->device));
+  // from here to the CSR fill this call owns the handle's stream and work buffers; the copies before and after run on the slot's stream
+  std::unique_lock<std::mutex> compute(h->compute_mu);
   int rc = mirror_model(h);
   if (rc != XM_OK) return rc;
   (void)n_words;
   cudaStream_t st = h->stream;
-  // the device copy of the previous batch's results (CSR slab, first_seq) is about to be overwritten: results handed out
-  // earlier must not pass xm_format_sam's "latest batch" check any more, whether or not this call succeeds
-  ++h->batch_serial;
+  if (wait_h2d) CK(cudaStreamWaitEvent(st, slot.h2d_done, 0));
   // owned here until the call succeeds (or ends with XM_ERR_QUERY, where the results are still delivered): every early
   // error return frees the results and gives the pinned slab back to the pool
   std::unique_ptr<xm_results> R_owner(new xm_results());
   xm_results* R = R_owner.get();
   R->r.stats.assign(XM_STAT_COUNT, 0);
-  if (nq == 0) { R->r.assemble(0, nullptr, nullptr, nullptr, nullptr); R->serial = h->batch_serial; R->nq = 0; *out = R_owner.release(); return XM_OK; }
+  if (nq == 0) { R->r.assemble(0, nullptr, nullptr, nullptr, nullptr); R->serial = slot.serial; R->slot = lease.i; R->nq = 0; *out = R_owner.release(); return XM_OK; }
   // first_seq = exclusive scan of n_seqs (cub, on the device: nq + 1 items, the last one reads as 0 so that first_seq[nq] is the total)
   size_t scan0_tmp = 0;
   {
     cub::TransformInputIterator<long long, NSeqsAt, cub::CountingInputIterator<int>> it(cub::CountingInputIterator<int>(0), NSeqsAt{d_n_seqs, nq});
     cub::DeviceScan::ExclusiveSum(nullptr, scan0_tmp, it, (long long*)nullptr, nq + 1, st);
   }
-  if (!h->d_first_seq.ensure(((size_t)nq + 1) * 8) || !h->d_chunk.ensure(scan0_tmp + 16)) { h->err = "out of device memory"; return XM_ERR_CUDA; }
-  CK(cudaEventRecord(h->ev0, st));
+  if (!slot.d_first_seq.ensure(((size_t)nq + 1) * 8) || !h->d_chunk.ensure(scan0_tmp + 16)) { h->err = "out of device memory"; return XM_ERR_CUDA; }
+  CK(cudaEventRecord(slot.ev0, st));
   {
     cub::TransformInputIterator<long long, NSeqsAt, cub::CountingInputIterator<int>> it(cub::CountingInputIterator<int>(0), NSeqsAt{d_n_seqs, nq});
     size_t tb = scan0_tmp;
-    CK(cub::DeviceScan::ExclusiveSum(h->d_chunk.p, tb, it, (long long*)h->d_first_seq.p, nq + 1, st));
+    CK(cub::DeviceScan::ExclusiveSum(h->d_chunk.p, tb, it, (long long*)slot.d_first_seq.p, nq + 1, st));
   }
   // sizes the result arena: exact when the caller counted the sequences (xm_align_batch), else the bound of two per query
   const long long n_seqs_total = n_seqs_total_hint >= 0 ? n_seqs_total_hint : 2LL * nq;
@@ -1078,7 +1121,7 @@ static int align_batch_impl(xm_handle* h, int32_t nq, const uint16_t* d_packed, 
   LaunchD L;
   L.ref = h->ref; L.ix = h->ix; L.dup = h->dup; L.prm = h->m.prm;
   L.batch.n_queries = nq; L.batch.packed = d_packed; L.batch.seq_word_off = d_seq_word_off; L.batch.seq_len = d_seq_len;
-  L.batch.first_seq = (const int64_t*)h->d_first_seq.p; L.batch.expected_inner = d_expected; L.batch.per_penalty = d_per;
+  L.batch.first_seq = (const int64_t*)slot.d_first_seq.p; L.batch.expected_inner = d_expected; L.batch.per_penalty = d_per;
   L.out.q = (OutQuery*)h->d_q.p; L.out.choices = (OutChoice*)h->d_choices.p; L.out.cap_choices = h->cap_choices;
   L.out.sas = (OutSA*)h->d_sas.p; L.out.cap_sas = h->cap_sas; L.out.blocks = (int32_t*)h->d_blocks.p; L.out.cap_blocks = h->cap_blocks;
   L.out.used = d_used; L.out.stats = d_stats;
@@ -1195,7 +1238,7 @@ static int align_batch_impl(xm_handle* h, int32_t nq, const uint16_t* d_packed, 
   if (rc != XM_OK) return rc;
   int fast_counts[8];
   long long real_seqs_total = 0;
-  CK(cudaMemcpyAsync(&real_seqs_total, (const long long*)h->d_first_seq.p + nq, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&real_seqs_total, (const long long*)slot.d_first_seq.p + nq, 8, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(fast_counts, d_ints, 32, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(easy_stats, d_easy_stats, sizeof(easy_stats), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));   // sync 1 of 3 per batch
@@ -1266,11 +1309,11 @@ static int align_batch_impl(xm_handle* h, int32_t nq, const uint16_t* d_packed, 
     int64_t off = 0;
     for (int i = 0; i < 11; i++) { R->r.slab_off[i] = off; R->r.slab_n[i] = n[i]; off += (n[i] * elem[i] + 15) & ~(int64_t)15; }
     size_t slab_bytes = (size_t)off + 16;
-    if (!h->d_csr_slab.ensure(slab_bytes)) { h->err = "out of device memory (csr slab)"; return XM_ERR_CUDA; }
+    if (!slot.d_csr_slab.ensure(slab_bytes)) { h->err = "out of device memory (csr slab)"; return XM_ERR_CUDA; }
     R->pool = h->pinned;
     R->slab = h->pinned->take(slab_bytes, R->slab_cap);
     if (!R->slab) { h->err = "out of pinned host memory (results)"; return XM_ERR_CUDA; }
-    char* d = (char*)h->d_csr_slab.p;
+    char* d = (char*)slot.d_csr_slab.p;
     CsrD c;
     c.q_comp_off = (int64_t*)(d + R->r.slab_off[0]); c.comp_choice_off = (int64_t*)(d + R->r.slab_off[1]); c.choice_sa_off = (int64_t*)(d + R->r.slab_off[2]);
     c.sa_block_off = (int64_t*)(d + R->r.slab_off[3]); c.choice_f64 = (double*)(d + R->r.slab_off[4]); c.sa_f64 = (double*)(d + R->r.slab_off[5]);
@@ -1279,23 +1322,26 @@ static int align_batch_impl(xm_handle* h, int32_t nq, const uint16_t* d_packed, 
     xm_csr_fill_kernel<<<(nq + 255) / 256, 256, 0, st>>>(L.out, nq, d_base, c);
     launches += 2;  // xm_csr_count + xm_csr_fill (the cub scans in between are library kernels)
     CK(cudaGetLastError());
-    CK(cudaEventRecord(h->ev1, st));  // device time of a step = every kernel from the scan of n_seqs to the CSR fill
-    CK(cudaMemcpyAsync(R->slab, d, slab_bytes, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(cudaEventRecord(slot.ev1, st));  // device time of a step = every kernel from the scan of n_seqs to the CSR fill
+    CK(cudaEventRecord(slot.kernels_done, st));
+    if (h->probe_cycles) { R->r.q_cycles.resize((size_t)nq); CK(cudaMemcpyAsync(R->r.q_cycles.data(), h->d_qcycles.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); }
+    slot.batch = L.batch; R->serial = slot.serial; R->slot = lease.i; R->nq = nq;
+    compute.unlock();   // the next caller's kernels may follow; this call's results leave on the slot's own stream
+    CK(cudaStreamWaitEvent(slot.copy, slot.kernels_done, 0));
+    CK(cudaMemcpyAsync(R->slab, d, slab_bytes, cudaMemcpyDeviceToHost, slot.copy));
+    CK(cudaStreamSynchronize(slot.copy));   // sync 3 of 3 per batch
     R->r.slab = (const char*)R->slab;
     if (host_times) fprintf(stderr, "[xm]   csr assembly + slab D2H (%.0f MB): %.1f ms\n", (double)slab_bytes / 1e6, now_ms() - t_csr0);
-    h->last_batch = L.batch; R->serial = h->batch_serial; R->nq = nq;
     R->r.stats[XM_STAT_D2H_BYTES] = (int64_t)(slab_bytes + sizeof(misc) + 32);
   }
   float ms = 0;
-  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  cudaEventElapsedTime(&ms, slot.ev0, slot.ev1);
   R->r.stats[XM_STAT_KERNEL_NS] = (int64_t)((double)ms * 1e6);
   R->r.stats[XM_STAT_ALIGN_KERNEL_NS] = (int64_t)((double)align_ms_tier0 * 1e6);
   R->r.stats[XM_STAT_LAUNCHES] = launches;
   for (int t = 0; t < XM_NUM_TIERS && t < 3; t++) R->r.stats[XM_STAT_TIER0_NS + t] = (int64_t)((double)tier_ms[t] * 1e6);
   R->r.stats[XM_STAT_EASY_NS] = (int64_t)((double)easy_ms * 1e6);
   R->r.stats[XM_STAT_EASY_PROBES] = (int64_t)easy_stats[0]; R->r.stats[XM_STAT_EASY_HITS] = (int64_t)easy_stats[2]; R->r.stats[XM_STAT_EASY_STRAIGHT] = (int64_t)easy_stats[3];
-  if (h->probe_cycles) { R->r.q_cycles.resize((size_t)nq); CK(cudaMemcpy(R->r.q_cycles.data(), h->d_qcycles.p, (size_t)nq * 8, cudaMemcpyDeviceToHost)); }
   R->r.stats[XM_STAT_PROBES] = (int64_t)misc[3]; R->r.stats[XM_STAT_SEEDS] = (int64_t)misc[4]; R->r.stats[XM_STAT_HITS] = (int64_t)misc[5];
   R->r.stats[XM_STAT_STRAIGHT] = (int64_t)misc[6]; R->r.stats[XM_STAT_PATH_CALLS] = (int64_t)misc[7]; R->r.stats[XM_STAT_PATH_STEPS] = (int64_t)misc[8];
   R->r.stats[XM_STAT_PATH_CELLS] = (int64_t)misc[9];
@@ -1308,7 +1354,10 @@ static int align_batch_impl(xm_handle* h, int32_t nq, const uint16_t* d_packed, 
 
 int xm_align_batch_device(xm_handle* h, int32_t nq, const uint16_t* d_packed, int64_t n_words, const int64_t* d_seq_word_off, const int32_t* d_seq_len,
                           const uint8_t* d_n_seqs, const double* d_expected, const double* d_per, int32_t max_seq_len, xm_results** out) {
-  return align_batch_impl(h, nq, d_packed, n_words, d_seq_word_off, d_seq_len, d_n_seqs, d_expected, d_per, max_seq_len, -1, out);
+  if (out) *out = nullptr;
+  if (!h || nq < 0 || !out) return XM_ERR_ARG;
+  SlotLease lease(h);
+  return align_batch_impl(h, lease, false, nq, d_packed, n_words, d_seq_word_off, d_seq_len, d_n_seqs, d_expected, d_per, max_seq_len, -1, out);
 }
 
 int xm_align_batch(xm_handle* h, int32_t nq, const uint16_t* packed4, const int64_t* seq_word_off, const int32_t* seq_len, const uint8_t* n_seqs,
@@ -1327,20 +1376,22 @@ int xm_align_batch(xm_handle* h, int32_t nq, const uint16_t* packed4, const int6
   std::vector<double> zeros, ones;
   if (!expected_inner) zeros.assign((size_t)nq + 1, 0.0);
   if (!per_penalty) ones.assign((size_t)nq + 1, 1.0);
-  if (!h->d_packed.ensure((size_t)n_words * 2 + 16) || !h->d_seq_word_off.ensure(((size_t)n_seqs_total + 1) * 8) || !h->d_seq_len.ensure((size_t)n_seqs_total * 4 + 16) ||
-      !h->d_n_seqs.ensure((size_t)nq + 16) || !h->d_expected.ensure((size_t)nq * 8 + 16) || !h->d_per.ensure((size_t)nq * 8 + 16)) { h->err = "out of device memory"; return XM_ERR_CUDA; }
-  cudaStream_t st = h->stream;
-  if (nq > 0) {
-    CK(cudaMemcpyAsync(h->d_packed.p, packed4, (size_t)n_words * 2, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->d_seq_word_off.p, seq_word_off, ((size_t)n_seqs_total + 1) * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->d_seq_len.p, seq_len, (size_t)n_seqs_total * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->d_n_seqs.p, n_seqs, (size_t)nq, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->d_expected.p, expected_inner ? expected_inner : zeros.data(), (size_t)nq * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->d_per.p, per_penalty ? per_penalty : ones.data(), (size_t)nq * 8, cudaMemcpyHostToDevice, st));
-  }   // no synchronisation: the kernels are ordered behind the copies on the stream (zeros / ones live until this function returns)
+  SlotLease lease(h);   // waits while every slot is in flight (N_SLOTS concurrent callers)
+  xm_handle::BatchSlot& sl = lease.slot();
+  if (!sl.d_packed.ensure((size_t)n_words * 2 + 16) || !sl.d_seq_word_off.ensure(((size_t)n_seqs_total + 1) * 8) || !sl.d_seq_len.ensure((size_t)n_seqs_total * 4 + 16) ||
+      !sl.d_n_seqs.ensure((size_t)nq + 16) || !sl.d_expected.ensure((size_t)nq * 8 + 16) || !sl.d_per.ensure((size_t)nq * 8 + 16)) { h->err = "out of device memory"; return XM_ERR_CUDA; }
+  if (nq > 0) {   // on the slot's copy stream: overlaps the kernels of whichever batch holds the compute section right now
+    CK(cudaMemcpyAsync(sl.d_packed.p, packed4, (size_t)n_words * 2, cudaMemcpyHostToDevice, sl.copy));
+    CK(cudaMemcpyAsync(sl.d_seq_word_off.p, seq_word_off, ((size_t)n_seqs_total + 1) * 8, cudaMemcpyHostToDevice, sl.copy));
+    CK(cudaMemcpyAsync(sl.d_seq_len.p, seq_len, (size_t)n_seqs_total * 4, cudaMemcpyHostToDevice, sl.copy));
+    CK(cudaMemcpyAsync(sl.d_n_seqs.p, n_seqs, (size_t)nq, cudaMemcpyHostToDevice, sl.copy));
+    CK(cudaMemcpyAsync(sl.d_expected.p, expected_inner ? expected_inner : zeros.data(), (size_t)nq * 8, cudaMemcpyHostToDevice, sl.copy));
+    CK(cudaMemcpyAsync(sl.d_per.p, per_penalty ? per_penalty : ones.data(), (size_t)nq * 8, cudaMemcpyHostToDevice, sl.copy));
+    CK(cudaEventRecord(sl.h2d_done, sl.copy));
+  }   // no host synchronisation: the kernels wait for h2d_done on the device (zeros / ones live until this function returns)
   const double t_h2d = now_ms();
-  int rc = align_batch_impl(h, nq, (const uint16_t*)h->d_packed.p, n_words, (const int64_t*)h->d_seq_word_off.p, (const int32_t*)h->d_seq_len.p,
-                            (const uint8_t*)h->d_n_seqs.p, (const double*)h->d_expected.p, (const double*)h->d_per.p, max_len, n_seqs_total, out);
+  int rc = align_batch_impl(h, lease, nq > 0, nq, (const uint16_t*)sl.d_packed.p, n_words, (const int64_t*)sl.d_seq_word_off.p, (const int32_t*)sl.d_seq_len.p,
+                            (const uint8_t*)sl.d_n_seqs.p, (const double*)sl.d_expected.p, (const double*)sl.d_per.p, max_len, n_seqs_total, out);
   if (*out) (*out)->r.stats[XM_STAT_H2D_BYTES] = (int64_t)((size_t)n_words * 2 + ((size_t)n_seqs_total + 1) * 8 + (size_t)n_seqs_total * 4 + (size_t)nq * 17);
   if (host_times && *out) fprintf(stderr, "[xm] xm_align_batch: validate+H2D %.1f ms, device call %.1f ms (kernels %.1f ms)\n", t_h2d - t_in, now_ms() - t_h2d, (double)(*out)->r.stats[XM_STAT_KERNEL_NS] / 1e6);
   return rc;
@@ -1352,12 +1403,25 @@ int xm_format_sam(xm_handle* h, xm_results* r, const char* seq_names, const int6
   CK(cudaSetDevice(h->device));
   const int nq = r->nq;
   *text = ""; *n_bytes = 0;
-  if (r->serial != h->batch_serial || (nq > 0 && r->r.slab == nullptr)) { h->err = "xm_format_sam: the results are not those of the handle's latest xm_align_batch (their device copy is gone)"; return XM_ERR_STATE; }
   if (nq == 0) return XM_OK;
+  // the device copy of the results lives in the batch slot that produced them until that slot serves another batch
+  struct Hold {
+    xm_handle* h; int i; bool ok;
+    Hold(xm_handle* hh, int slot, uint64_t serial) : h(hh), i(slot), ok(false) {
+      if (i < 0 || i >= xm_handle::N_SLOTS) return;
+      std::unique_lock<std::mutex> g(h->slot_mu);
+      while (h->slots[i].busy && h->slots[i].serial == serial) h->slot_cv.wait(g);
+      if (h->slots[i].serial == serial) { h->slots[i].busy = true; ok = true; }
+    }
+    ~Hold() { if (ok) { { std::lock_guard<std::mutex> g(h->slot_mu); h->slots[i].busy = false; } h->slot_cv.notify_one(); } }
+  } hold(h, r->slot, r->serial);
+  if (!hold.ok || r->r.slab == nullptr) { h->err = "xm_format_sam: the device copy of these results is gone (their batch slot has served a later xm_align_batch)"; return XM_ERR_STATE; }
+  xm_handle::BatchSlot& slot = h->slots[r->slot];
+  std::lock_guard<std::mutex> compute(h->compute_mu);
   cudaStream_t st = h->stream;
   // number of sequences = first_seq[nq] on the device; the host passes name offsets for all of them
   long long n_seq_total = 0;
-  CK(cudaMemcpy(&n_seq_total, h->last_batch.first_seq + nq, 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&n_seq_total, slot.batch.first_seq + nq, 8, cudaMemcpyDeviceToHost));
   const int n_contigs = h->m.n_contigs;
   const size_t names_bytes = (size_t)seq_name_off[n_seq_total], cnames_bytes = (size_t)contig_name_off[n_contigs];
   if (!h->d_sam_names.ensure(names_bytes + 16) || !h->d_sam_name_off.ensure(((size_t)n_seq_total + 1) * 8) || !h->d_sam_cnames.ensure(cnames_bytes + 16) ||
@@ -1367,7 +1431,7 @@ int xm_format_sam(xm_handle* h, xm_results* r, const char* seq_names, const int6
   CK(cudaMemcpyAsync(h->d_sam_cnames.p, contig_names, cnames_bytes, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(h->d_sam_cname_off.p, contig_name_off, ((size_t)n_contigs + 1) * 8, cudaMemcpyHostToDevice, st));
   SamD S;
-  char* d = (char*)h->d_csr_slab.p;
+  char* d = (char*)slot.d_csr_slab.p;
   const int64_t* off = r->r.slab_off;
   S.c.q_comp_off = (int64_t*)(d + off[0]); S.c.comp_choice_off = (int64_t*)(d + off[1]); S.c.choice_sa_off = (int64_t*)(d + off[2]); S.c.sa_block_off = (int64_t*)(d + off[3]);
   S.c.choice_f64 = (double*)(d + off[4]); S.c.sa_f64 = (double*)(d + off[5]); S.c.choice_inner = (int32_t*)(d + off[6]); S.c.sa_contig = (int32_t*)(d + off[7]);
@@ -1376,7 +1440,7 @@ int xm_format_sam(xm_handle* h, xm_results* r, const char* seq_names, const int6
   S.contig_names = (const char*)h->d_sam_cnames.p; S.contig_name_off = (const int64_t*)h->d_sam_cname_off.p;
   S.q_len = (long long*)h->d_sam_len.p; S.text = nullptr;
   CK(cudaMemsetAsync((char*)h->d_sam_len.p + (size_t)nq * 8, 0, 8, st));
-  xm_sam_kernel<false><<<(nq + 127) / 128, 128, 0, st>>>(S, h->last_batch, nq);
+  xm_sam_kernel<false><<<(nq + 127) / 128, 128, 0, st>>>(S, slot.batch, nq);
   size_t tb = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tb, (const long long*)nullptr, (long long*)nullptr, nq + 1, st);
   if (!h->d_csr_tmp.ensure(tb + 16)) { h->err = "out of device memory (sam)"; return XM_ERR_CUDA; }
@@ -1386,7 +1450,7 @@ int xm_format_sam(xm_handle* h, xm_results* r, const char* seq_names, const int6
   CK(cudaStreamSynchronize(st));
   if (!h->d_sam_text.ensure((size_t)total + 16)) { h->err = "out of device memory (sam text)"; return XM_ERR_CUDA; }
   S.text = (char*)h->d_sam_text.p;
-  xm_sam_kernel<true><<<(nq + 127) / 128, 128, 0, st>>>(S, h->last_batch, nq);
+  xm_sam_kernel<true><<<(nq + 127) / 128, 128, 0, st>>>(S, slot.batch, nq);
   CK(cudaGetLastError());
   if (!r->pool) r->pool = h->pinned;
   if (r->sam && r->sam_cap < (size_t)total + 1) { r->pool->give(r->sam, r->sam_cap); r->sam = nullptr; }
@@ -1404,6 +1468,7 @@ void xm_release_results(xm_results* r) { delete r; }
 
 int xm_counts_enable(xm_handle* h, double query_end_fraction) {
   if (!h || h->m.n_contigs < 1) return XM_ERR_STATE;
+  std::lock_guard<std::mutex> compute(h->compute_mu);
   CK(cudaSetDevice(h->device));
   std::vector<int64_t> off((size_t)h->m.n_contigs + 1, 0);
   for (int c = 0; c < h->m.n_contigs; c++) off[(size_t)c + 1] = off[(size_t)c] + h->m.len[(size_t)c];
@@ -1441,6 +1506,7 @@ int xm_comm_init(xm_handle* h, int32_t n_ranks, int32_t rank, const uint8_t* id1
 int xm_counts_reduce(xm_handle* h) {
   if (!h || !h->counts_enabled) return XM_ERR_STATE;
   if (!h->comm) { h->err = "xm_counts_reduce: xm_comm_init was not called"; return XM_ERR_STATE; }
+  std::lock_guard<std::mutex> compute(h->compute_mu);
   NcclApi& N = nccl_api();
   CK(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
@@ -1497,6 +1563,7 @@ int xm_counts_batch_info(xm_handle* h, int64_t first_sequence_id, const int64_t*
 }
 int xm_variants_fetch(xm_handle* h, int64_t* n, uint64_t* keys, int32_t* counts, int64_t* ex_gid, int32_t* ex_index) {
   if (!h || !h->counts_enabled) return XM_ERR_STATE;
+  std::lock_guard<std::mutex> compute(h->compute_mu);
   CK(cudaSetDevice(h->device));
   int rc = var_reduce_now(h);
   if (rc != XM_OK) return rc;
@@ -1518,6 +1585,7 @@ int xm_variants_fetch(xm_handle* h, int64_t* n, uint64_t* keys, int32_t* counts,
 // (cudaDevAttrClockRate: the maximum; the achieved clock under load is sampled by the caller).
 int xm_measure_peaks(xm_handle* h, double* out) {
   if (!h || !out) return XM_ERR_ARG;
+  std::lock_guard<std::mutex> compute(h->compute_mu);
   CK(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   if (!h->d_misc.ensure(256)) { h->err = "out of device memory"; return XM_ERR_CUDA; }
@@ -1551,6 +1619,7 @@ int xm_counts_device_ptr(xm_handle* h, void** d_ptr, int64_t* n_int32) {
 }
 int xm_counts_fetch(xm_handle* h, int32_t contig, int32_t* out) {
   if (!h || !h->counts_enabled || contig < 0 || contig >= h->m.n_contigs || !out) return XM_ERR_ARG;
+  std::lock_guard<std::mutex> compute(h->compute_mu);
   CK(cudaSetDevice(h->device));
   long long off = 0;
   for (int c = 0; c < contig; c++) off += h->m.len[(size_t)c];

@@ -257,15 +257,55 @@ def test_consecutive_batches_and_result_lifetime():
         kept.append((want, got))
     for want, got in kept:  # every earlier result is still intact
         parity.assert_same_results(want, {k: v for k, v in got.items() if k != "_owner"}, "kept result")
-    # SAM text can only be produced for the latest batch of the handle
+    # SAM text is produced from the device copy of the results, which lives in the batch slot that served the call until that slot
+    # serves another batch (three slots, least recently used first): recent results format fine, old ones are refused loudly
     batch = synth.simulate_reads(contigs, 10, 150, seed=190)
-    r1, r2 = C.c_void_p(), C.c_void_p()
     args = lambda b: (len(b["n_seqs"]), capi._ptr(b["packed"]), capi._ptr(b["seq_word_off"]), capi._ptr(b["seq_len"]), capi._ptr(b["n_seqs"]), capi._ptr(b["expected_inner"]), capi._ptr(b["per_penalty"]))
-    assert g.L.xm_align_batch(g.h, *args(batch), C.byref(r1)) == 0
-    assert g.L.xm_align_batch(g.h, *args(batch), C.byref(r2)) == 0
+    rs = [C.c_void_p() for _ in range(5)]
+    for r in rs:
+        assert g.L.xm_align_batch(g.h, *args(batch), C.byref(r)) == 0
     names = ["r%d" % i for i in range(10)]
     with pytest.raises(capi.XmError):
-        g.format_sam(r1, names, ["c0", "c1"])
-    assert g.format_sam(r2, names, ["c0", "c1"]).count("\n") >= 9
+        g.format_sam(rs[0], names, ["c0", "c1"])
+    with pytest.raises(capi.XmError):
+        g.format_sam(rs[1], names, ["c0", "c1"])
+    texts = [g.format_sam(r, names, ["c0", "c1"]) for r in rs[2:]]
+    assert texts[0].count("\n") >= 9 and texts[0] == texts[1] == texts[2]
+    r1, r2 = rs[0], rs[1]
+    for r in rs[2:]:
+        g.L.xm_release_results(r)
     g.L.xm_release_results(r1); g.L.xm_release_results(r2)
+    g.close()
+
+
+def test_concurrent_callers_on_one_handle():
+    """M/Api.java:78 ("expected to be threadsafe"), M/Mapper.java:1026-1040 (N AlignerWorkers): several host threads call xm_align_batch
+    on ONE handle at the same time; every call gets exactly the results of its own batch (the copies of one call overlap the kernels of
+    another, the kernels themselves run one batch after the other)."""
+    import threading
+    ref = synth.random_reference(300000, seed=171, n_contigs=2, repeat_fraction=0.05, repeat_len=(200, 800))
+    db = xo.Oracle([(n, synth.codes_to_text(s)) for n, s in ref], sort_by_length=True, threads=8, dup=dict(min_copies=2, window=1000))
+    contigs = [db.contig(i) for i in range(db.num_contigs())]
+    g = gpu_from_oracle(db, synth.DEFAULT_PARAMS, 150, 1000, False, False)
+    n_threads, per_thread = 4, 6
+    batches = [[synth.simulate_reads(contigs, 3000 + 500 * t + 100 * k, 150, seed=700 + 10 * t + k, sub_rate=0.015, indel_rate=0.002, paired=(k % 2 == 1))
+                for k in range(per_thread)] for t in range(n_threads)]
+    want = [[db.align_batch(synth.DEFAULT_PARAMS, b, threads=8) for b in bs] for bs in batches]
+    got = [[None] * per_thread for _ in range(n_threads)]
+    errs = []
+
+    def run(t):
+        try:
+            for k in range(per_thread):
+                got[t][k] = g.align_batch(batches[t][k], strict=True)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=run, args=(t,)) for t in range(n_threads)]
+    [x.start() for x in th]
+    [x.join(timeout=300) for x in th]
+    assert not errs, errs
+    for t in range(n_threads):
+        for k in range(per_thread):
+            parity.assert_same_results(want[t][k], got[t][k], "thread %d batch %d" % (t, k))
     g.close()
