@@ -325,7 +325,7 @@ def main():
         reduce_check = dict(plane_checksum_matches=bool(int(want) == int(total)), plane_checksum=int(total), variant_entries=int(hi),
                             same_table_size_on_every_rank=bool(int(lo) == int(hi)), merged_not_smaller_than_any_shard=bool(int(hi) >= int(n_local)))
     # ---- timed: end to end through the C ABI with host buffers (H2D + kernels + D2H + result assembly + the exchange step) ----
-    keep = [step_host() for _ in range(2)]  # untimed warm-up of the host path: staging buffers and BOTH pinned result slabs (a caller holds one result while the next batch runs)
+    keep = [step_host() for _ in range(3)]  # untimed warm-up of the host path: the staging buffers of all three batch slots and the pinned result slabs
     del keep
     barrier()
     t0 = time.time()

@@ -271,11 +271,13 @@ XM_FN int matcher_lookup(WS& w, MatcherD& m, const ACtx& c, int query_index, int
 // is absent and nothing is cleared between searches.  stamp = value of the search's write counter when the node was last written: a
 // neighbour whose stamp is newer than the stamps of all three of its predecessors would be recomputed from unchanged inputs, i.e. to
 // the values it already holds, so its evaluation is skipped (39 % of all evaluations on the 150 bp workload).
-struct alignas(16) PNode { double pen, ins_x, ins_y; uint32_t stamp; uint32_t meta; };  // meta = generation << 8 | flags (2 reachedMain, 4 reachedOther)
+struct alignas(16) PNode { double pen, ins_x, ins_y; uint32_t stamp; uint32_t meta; };
+struct alignas(8) PMeta { uint32_t stamp, meta; };   // the last 8 bytes of a node, read with one 64-bit load  // meta = generation << 8 | flags (2 reachedMain, 4 reachedOther)
 // One queued node: packed (x, y) and the next entry of the same priority (-1 = last).
 struct PEnt { uint32_t xy; int32_t next; };
 struct PathState {
-  Params prm; ACtx ctx; Analysis* an;
+  Params prm; ACtx ctx;
+  int an_confident; double an_max_ins, an_max_del;   // the AlignmentAnalysis in force, by value (the search may run on another SM)
   int start_a, end_a, start_b, end_b, A, B, W, H;
   int diagonal, step, reverse, may_extend;
   int start_x, start_y, goal_x, goal_y;
@@ -452,29 +454,41 @@ struct PaQueue {
 };
 
 XM_INLINE int pa_signed_dist(const PathState& s, int x, int y) { return x - y - s.diagonal; }
+XM_INLINE PNode pa_node(const PathState& s, int idx) {   // a node as the traceback reads it: past L1, the search may have run on another SM
+#if defined(__CUDA_ARCH__)
+  const double2 a = __ldcg((const double2*)&s.nodes[idx]);
+  const double2 b = __ldcg((const double2*)&s.nodes[idx] + 1);
+  PNode n; n.pen = a.x; n.ins_x = a.y; n.ins_y = b.x;
+  const unsigned long long m = (unsigned long long)__double_as_longlong(b.y);
+  n.stamp = (uint32_t)m; n.meta = (uint32_t)(m >> 32);
+  return n;
+#else
+  return s.nodes[idx];
+#endif
+}
 XM_INLINE bool pa_get(const PathState& s, int x, int y, int& idx) {
   if (x < 0 || x >= s.W || y < 0 || y >= s.H) return false;
   idx = x * s.H + y;
-  return (s.nodes[idx].meta >> 8) == s.gen;
+  return (pa_node(s, idx).meta >> 8) == s.gen;
 }
 XM_HD inline double pa_estimate(const PathState& s, int x, int y, const PNode& n, int fl) {  // estimateOverallPenalty :475-521
-  if (!s.an->confident) return n.pen;
+  if (!s.an_confident) return n.pen;
   int sd = pa_signed_dist(s, x, y);
   const Params& p = s.prm;
   if (fl & 2) {
-    if (sd * s.step > 0) { double ie = fabs(sd * p.ins_ext); if (ie > s.an->max_ins) return XM_DISALLOWED; }
-    else { double de = fabs(sd * p.del_ext); if (de > s.an->max_del) return XM_DISALLOWED; }
+    if (sd * s.step > 0) { double ie = fabs(sd * p.ins_ext); if (ie > s.an_max_ins) return XM_DISALLOWED; }
+    else { double de = fabs(sd * p.del_ext); if (de > s.an_max_del) return XM_DISALLOWED; }
     if (fl & 4) return n.pen;
     return n.pen + dmin(p.ins_start + p.ins_ext, p.del_start + p.del_ext);
   }
   if (sd * s.step < 0) {
     double ie = fabs(sd * p.ins_ext);
-    if (ie > s.an->max_ins) return XM_DISALLOWED;
+    if (ie > s.an_max_ins) return XM_DISALLOWED;
     double is = dmin(p.ins_start, n.ins_x - n.pen);
     return n.pen + is + ie;
   } else {
     double de = fabs(sd * p.del_ext);
-    if (de > s.an->max_del) return XM_DISALLOWED;
+    if (de > s.an_max_del) return XM_DISALLOWED;
     double ds = dmin(p.del_start, n.ins_y - n.pen);
     return n.pen + ds + de;
   }
@@ -486,9 +500,9 @@ XM_HD inline double pa_estimate(const PathState& s, int x, int y, const PNode& n
 // their time.  Returns 0 goal reached (last_x/last_y), 1 over budget (null), 2 failed (w.status set).
 XM_FN int pa_search(WS& w, PathState& S, PaOverflow* ovf, int cap_ovf, int& last_x, int& last_y) {
   const int A = S.A, B = S.B, H = S.H, step = S.step, goal_x = S.goal_x, goal_y = S.goal_y, diag = S.diagonal;
-  const bool may_extend = S.may_extend != 0, confident = S.an->confident != 0;
+  const bool may_extend = S.may_extend != 0, confident = S.an_confident != 0;
   const double ins_start = S.prm.ins_start, ins_ext = S.prm.ins_ext, del_start = S.prm.del_start, del_ext = S.prm.del_ext, unaligned = S.prm.unaligned;
-  const double max_ins = S.an->max_ins, max_del = S.an->max_del, budget = S.max_interesting + 0.000001;
+  const double max_ins = S.an_max_ins, max_del = S.an_max_del, budget = S.max_interesting + 0.000001;
   const double min_indel = dmin(ins_start + ins_ext, del_start + del_ext);
   const double* pen_tab = S.prm.pen_tab; const uint8_t* cls_tab = S.prm.cls_tab;
   PNode* nodes = S.nodes; const uint8_t* qa = S.qa; const uint8_t* rb = S.rb;
@@ -505,7 +519,7 @@ XM_FN int pa_search(WS& w, PathState& S, PaOverflow* ovf, int cap_ovf, int& last
     double sisp = XM_DISALLOWED;
     if (along_y && may_extend) sisp = S.prm.starting_ins_start();
     const int cnt1 = (along_y ? imax(0, B - A) : imax(0, A - B)) + 1;
-    const int cnt2 = may_extend ? imax(0, j2i(S.an->max_ins / del_ext) - 1) : 0;
+    const int cnt2 = may_extend ? imax(0, j2i(S.an_max_ins / del_ext) - 1) : 0;
     XM_NOUNROLL
     for (int i = 0; i < cnt1 + cnt2 && qrc == 0; i++) {
       PNode n; int x, y;
@@ -541,43 +555,33 @@ XM_FN int pa_search(WS& w, PathState& S, PaOverflow* ovf, int cap_ovf, int& last
       if (x <= 0 || x > A || y <= 0 || y > B) continue;
       const int ie = x * H + y, il = ie - step * H, iu = ie - step, id = il - step;
       // stamp (low word) and meta (high word) of the node and of its three predecessors: four independent 8-byte loads
-      const unsigned long long me = *(const unsigned long long*)&nodes[ie].stamp, ml = *(const unsigned long long*)&nodes[il].stamp;
-      const unsigned long long mu = *(const unsigned long long*)&nodes[iu].stamp, md = *(const unsigned long long*)&nodes[id].stamp;
-      const bool he = (uint32_t)(me >> 40) == gen, hl = (uint32_t)(ml >> 40) == gen, hu = (uint32_t)(mu >> 40) == gen, hd = (uint32_t)(md >> 40) == gen;
+      const PMeta me = *(const PMeta*)&nodes[ie].stamp, ml = *(const PMeta*)&nodes[il].stamp, mu = *(const PMeta*)&nodes[iu].stamp, md = *(const PMeta*)&nodes[id].stamp;
+      const bool he = (me.meta >> 8) == gen, hl = (ml.meta >> 8) == gen, hu = (mu.meta >> 8) == gen, hd = (md.meta >> 8) == gen;
       if (he) {
         // every predecessor was last written before this node was: recomputing it would reproduce the values it holds (no improvement)
         uint32_t newest = 0;
-        if (hl && (uint32_t)ml > newest) newest = (uint32_t)ml;
-        if (hu && (uint32_t)mu > newest) newest = (uint32_t)mu;
-        if (hd && (uint32_t)md > newest) newest = (uint32_t)md;
-        if ((uint32_t)me > newest) continue;
+        if (hl && ml.stamp > newest) newest = ml.stamp;
+        if (hu && mu.stamp > newest) newest = mu.stamp;
+        if (hd && md.stamp > newest) newest = md.stamp;
+        if (me.stamp > newest) continue;
       }
-      const uint32_t fl_ = hl ? (1u | ((uint32_t)(ml >> 32) & 6u)) : 0u, fu = hu ? (1u | ((uint32_t)(mu >> 32) & 6u)) : 0u, fd = hd ? (1u | ((uint32_t)(md >> 32) & 6u)) : 0u;
+      const uint32_t fl_ = hl ? (1u | (ml.meta & 6u)) : 0u, fu = hu ? (1u | (mu.meta & 6u)) : 0u, fd = hd ? (1u | (md.meta & 6u)) : 0u;
       double ins_x = XM_DISALLOWED, ins_y = XM_DISALLOWED, overlay = XM_DISALLOWED;
       if (hd) overlay = nodes[id].pen + pen_tab[((int)qa[x - 1] << 4) | (int)rb[y - 1]];
       if (hl) {
         const double lp = nodes[il].pen;
         if (y == goal_y && may_extend) ins_x = lp + unaligned;
         else {
-          bool allowed = true;
-          const int pa = x - 1 - step, pb = y - 1;
-          if (pa >= 0 && pa < A && pb >= 0 && pb < B) allowed = (cls_tab[((int)qa[pa] << 4) | (int)rb[pb]] & 1) != 0;
-          if (allowed) {
-            const int na = x - 1, nbb = y - 1 + step;
-            if (na >= 0 && na < A && nbb >= 0 && nbb < B) allowed = (cls_tab[((int)qa[na] << 4) | (int)rb[nbb]] & 6) == 0;
-          }
+          // qa / rb are padded with the sentinel code on both sides: an index off the section leaves the move allowed, as in the reference
+          bool allowed = (cls_tab[((int)qa[x - 1 - step] << 5) | (int)rb[y - 1]] & 1) != 0;
+          if (allowed) allowed = (cls_tab[((int)qa[x - 1] << 5) | (int)rb[y - 1 + step]] & 6) == 0;
           const double nw = allowed ? lp + ins_start + ins_ext : XM_DISALLOWED;
           ins_x = dmin(nodes[il].ins_x + ins_ext, nw);
         }
       }
       if (hu) {
-        bool allowed = true;
-        const int pa = x - 1, pb = y - 1 - step;
-        if (pa >= 0 && pa < A && pb >= 0 && pb < B) allowed = (cls_tab[((int)qa[pa] << 4) | (int)rb[pb]] & 1) != 0;
-        if (allowed) {
-          const int na = x - 1 + step, nbb = y - 1;
-          if (na >= 0 && na < A && nbb >= 0 && nbb < B) allowed = (cls_tab[((int)qa[na] << 4) | (int)rb[nbb]] & 6) == 0;
-        }
+        bool allowed = (cls_tab[((int)qa[x - 1] << 5) | (int)rb[y - 1 - step]] & 1) != 0;
+        if (allowed) allowed = (cls_tab[((int)qa[x - 1 + step] << 5) | (int)rb[y - 1]] & 6) == 0;
         const double nw = allowed ? nodes[iu].pen + del_start + del_ext : XM_DISALLOWED;
         ins_y = dmin(nodes[iu].ins_y + del_ext, nw);
       }
@@ -619,20 +623,60 @@ XM_FN int pa_search(WS& w, PathState& S, PaOverflow* ovf, int cap_ovf, int& last
   w.st_path_steps += steps;
   return rc;
 }
+
+// ---- PathAligner search service ----
+// The per-query code is ~480 KB of SASS and the kernel is bound by instruction delivery (ncu: SM instruction-cache hit rate 55 %, the GPC
+// instruction cache at 50-80 % of its request rate, stall_no_instruction 52 of 77 cycles per issued instruction, same run time at 24, 32
+// or 64 warps per SM).  Half of all instructions are the lattice search (pa_search + PaQueue, ~30 KB of code).  So some SMs run NOTHING
+// but that loop: a warp that reaches a search hands it to them through a ring in global memory and sleeps until the answer is back.
+// The search runs on the client's own arena (PathState, lattice nodes, queue entries); only the two sections are copied into the
+// server's shared memory.  Data that crosses SMs is read past L1 (__ldcg / volatile); the lattice nodes may stay L1-cached on the
+// server because a stale line can only hold an older generation, i.e. an absent node, which is what it is until this search writes it.
+struct PaReq { int state; int rc; int last_x, last_y; int status; int pad; unsigned long long steps; PathState* S; PaOverflow* ovf; int cap_ovf; int pad2; };
+typedef PaServiceRef PaService;
+static const int XM_SVC_SEQ_CAP = 1024;   // bytes of shared memory per server warp for the two padded sections
+XM_INLINE int ld_volatile_i(const int* p) { return *(const volatile int*)p; }
+#if defined(__CUDA_ARCH__)
+// client side: post the request, sleep, take the answer.  Returns pa_search's code.
+__device__ __noinline__ int pa_search_remote(WS& w, PathState& S, PaOverflow* ovf, int cap_ovf, int& last_x, int& last_y) {
+  const int lane = (int)(threadIdx.x & 31);
+  PaReq* rq = w.svc.reqs + w.svc_slot;
+  __threadfence();   // every lane's writes to the arena (PathState, sections) are ordered before lane 0 publishes the request
+  __syncwarp();
+  if (lane == 0) {
+    rq->S = &S; rq->ovf = ovf; rq->cap_ovf = cap_ovf; rq->state = 1;
+    __threadfence();   // PathState, sections and the request are in L2 before the ring entry is
+    const unsigned int pos = atomicAdd(w.svc.tail, 1u);
+    *(volatile int*)&w.svc.ring[pos & w.svc.ring_mask] = w.svc_slot + 1;
+    while (ld_volatile_i(&rq->state) != 2) __nanosleep(400);
+    __threadfence();
+  }
+  __syncwarp();
+  const int rc = __ldcg(&rq->rc);
+  last_x = __ldcg(&rq->last_x); last_y = __ldcg(&rq->last_y);
+  const int st = __ldcg(&rq->status);
+  w.st_path_steps += __ldcg(&rq->steps);
+  if (st != 0) w.fail(st);
+  return rc;
+}
+#endif
 XM_FN DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Params& p, Analysis& an) {  // PathAligner.align :55-293
   PhaseClock pc_(&w.st_cyc[3]);
   long long mark = w.scratch_top;
   PathState* sp = (PathState*)w.salloc(sizeof(PathState));
   if (!sp) return aln_null();
   PathState& s = *sp;
-  s.prm = p; s.ctx = c; s.an = &an;
+  s.prm = p; s.ctx = c; s.an_confident = an.confident; s.an_max_ins = an.max_ins; s.an_max_del = an.max_del;
   s.max_interesting = q.length() * p.max_error_rate;
   s.start_a = q.start; s.end_a = q.end; s.start_b = r.start; s.end_b = r.end;
   s.A = q.length(); s.B = r.length(); s.W = s.A + 2; s.H = s.B + 2;
   s.diagonal = s.start_b - (s.start_a + an.predicted);
   {  // unpack both sections once (lanes split the bases on the device)
-    uint8_t* qa = (uint8_t*)w.salloc(s.A + 1); uint8_t* rb = (uint8_t*)w.salloc(s.B + 1);
+    uint8_t* qa = (uint8_t*)w.salloc(s.A + 5); uint8_t* rb = (uint8_t*)w.salloc(s.B + 5);
     if (w.status != 0) { w.scratch_top = mark; return aln_null(); }
+    qa += 2; rb += 2;   // two sentinel codes (16) on either side: the search reads one position past both ends (xm_types.h: Params::cls_tab)
+    XM_NOUNROLL
+    for (int k = 0; k < 2; k++) { qa[-1 - k] = 16; qa[s.A + k] = 16; rb[-1 - k] = 16; rb[s.B + k] = 16; }
 #if defined(__CUDA_ARCH__)
     for (int k = (int)(threadIdx.x & 31); k < s.A; k += 32) qa[k] = c.a.at(s.start_a + k);
     for (int k = (int)(threadIdx.x & 31); k < s.B; k += 32) rb[k] = c.b.at(s.start_b + k);
@@ -711,10 +755,18 @@ XM_FN DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Pa
   s.ent = (PEnt*)w.salloc(ent_cap * (long long)sizeof(PEnt));
   if (w.status != 0 || s.ent_cap < 8) { w.fail(Q_NEED_MORE); w.scratch_top = mark; return aln_null(); }
   int last_x = -1, last_y = -1;
+  bool remote = false;
   {
-    int rc = pa_search(w, s, ovf, cap_ovf, last_x, last_y);
+    int rc;
+#if defined(__CUDA_ARCH__)
+    remote = w.svc.reqs != nullptr && s.A + s.B + 16 <= XM_SVC_SEQ_CAP;
+    if (remote) rc = pa_search_remote(w, s, ovf, cap_ovf, last_x, last_y);
+    else
+#endif
+      rc = pa_search(w, s, ovf, cap_ovf, last_x, last_y);
     if (rc == 1 && w.status == 0) { w.scratch_top = mark; return aln_null(); }
   }
+  (void)remote;
   if (w.status != 0) { w.scratch_top = mark; return aln_null(); }
   // traceback :193-269. Blocks are collected in a temporary array placed after the heap.
   int max_blocks = s.A + s.B + 4;
@@ -725,7 +777,7 @@ XM_FN DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Pa
   XM_NOUNROLL
   while (i != s.start_x && j != s.start_y) {
     if (!pa_get(s, i, j, idx)) { w.fail(Q_INTERNAL); break; }
-    PNode node = s.nodes[idx];
+    PNode node = pa_node(s, idx);
     Blk k;
     if (node.pen == node.ins_x) {
       int old_i = i;
@@ -733,7 +785,7 @@ XM_FN DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Pa
       XM_NOUNROLL
       while (i != s.start_x) {
         if (!pa_get(s, i, j, idx)) { w.fail(Q_INTERNAL); break; }
-        const PNode& o = s.nodes[idx];
+        const PNode o = pa_node(s, idx);
         if (o.pen + p.ins_start + p.ins_ext < o.ins_x + p.ins_ext) break;
         i -= s.step;
       }
@@ -745,7 +797,7 @@ XM_FN DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Pa
       XM_NOUNROLL
       while (j != s.start_y) {
         if (!pa_get(s, i, j, idx)) { w.fail(Q_INTERNAL); break; }
-        const PNode& o = s.nodes[idx];
+        const PNode o = pa_node(s, idx);
         if (o.pen + p.del_start + p.del_ext < o.ins_y + p.del_ext) break;
         j -= s.step;
       }
@@ -757,7 +809,7 @@ XM_FN DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Pa
       XM_NOUNROLL
       while (i != s.start_x && j != s.start_y) {
         if (!pa_get(s, i, j, idx)) { w.fail(Q_INTERNAL); break; }
-        const PNode& o = s.nodes[idx];
+        const PNode o = pa_node(s, idx);
         if (o.pen == o.ins_x || o.pen == o.ins_y) break;
         i -= s.step; j -= s.step;
       }
@@ -1813,12 +1865,13 @@ XM_HD inline void align_query(WS& w, OutArena& out, OutQuery& oq) {
 
 // Carves the per-thread workspace out of a flat arena and resets all per-query state.
 // fills the 256-entry pair-penalty table (Params::pen_tab) with the reference's formula
-XM_HD inline void fill_pen_tab(const Params& prm, double* tab, uint8_t* cls, int first, int step) {
-  for (int i = first; i < 256; i += step) {
-    uint8_t q = (uint8_t)(i >> 4), r = (uint8_t)(i & 15);
-    double v = prm.base_penalty_formula(q, r);
-    tab[i] = v;
-    cls[i] = (uint8_t)((bp_can_match(q, r) ? 1 : 0) | (v == 0 ? 2 : 0) | ((bp_is_fully_ambiguous(q) || bp_is_fully_ambiguous(r)) ? 4 : 0));
+XM_HD inline void fill_pen_tab(const Params& prm, double* tab, uint8_t* cls, int first, int step) {  // tab: 256 doubles, cls: 1024 bytes
+  for (int i = first; i < 256; i += step) tab[i] = prm.base_penalty_formula((uint8_t)(i >> 4), (uint8_t)(i & 15));
+  for (int i = first; i < 1024; i += step) {
+    const int q = i >> 5, r = i & 31;
+    if (q >= 16 || r >= 16) { cls[i] = 1; continue; }   // a sentinel: the reference skips both checks when an index is off the section
+    const double v = prm.base_penalty_formula((uint8_t)q, (uint8_t)r);
+    cls[i] = (uint8_t)((bp_can_match((uint8_t)q, (uint8_t)r) ? 1 : 0) | (v == 0 ? 2 : 0) | ((bp_is_fully_ambiguous((uint8_t)q) || bp_is_fully_ambiguous((uint8_t)r)) ? 4 : 0));
   }
 }
 // with_lattice: the arena begins with the PathAligner lattice (3/8 of the arena, behind a 16-byte header: [0] generation, 0 = the

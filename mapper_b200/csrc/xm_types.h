@@ -85,7 +85,9 @@ struct Params {
   int max_num_matches;
   int start_free;  // StartingInsertionStartFree
   const double* pen_tab;  // 256 entries [q << 4 | r] of the formula below, filled once per kernel launch (device: shared memory)
-  const uint8_t* cls_tab; // 256 entries [q << 4 | r]: bit 0 canMatch, bit 1 penalty == 0, bit 2 either base fully ambiguous
+  // 1024 entries [q << 5 | r] over 5-bit codes: bit 0 canMatch, bit 1 penalty == 0, bit 2 either base fully ambiguous; code 16 is the
+  // sentinel the PathAligner pads its two sections with ("off the section": canMatch, nothing else), so the search needs no bounds checks
+  const uint8_t* cls_tab;
   XM_INLINE double starting_ins_start() const { return start_free ? 0.0 : ins_start; }
   XM_INLINE double min_possible_nonzero() const {
     double r = mutation;

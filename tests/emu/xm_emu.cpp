@@ -13,7 +13,7 @@ using namespace xm;
 
 namespace {
 struct CParams { double mutation, ins_start, ins_ext, del_start, del_ext, max_error_rate, unaligned, ambiguity, span; int32_t max_num_matches, enable_gapmers; };
-struct Emu { HostModel m; std::string err; double pen[256]; uint8_t cls[256]; };
+struct Emu { HostModel m; std::string err; double pen[256]; uint8_t cls[1024]; };
 }
 
 extern "C" {
