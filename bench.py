@@ -237,6 +237,7 @@ def main():
     nq = len(batch["n_seqs"])
     n_words = int(batch["seq_word_off"][-1])
     reduce_every_step = a.counts and a.workload == "c3"
+    nccl_ms = [0.0, 0.0, 0]   # sums over the steps: device ms of the plane all-reduce, ms of the variant-table exchange, calls
     plane_ptr, plane_ints = g.counts_device_ptr() if a.counts else (0, 0)
 
     def planes_tensor():
@@ -260,6 +261,8 @@ def main():
         t = time.time()
         if world > 1:
             g.counts_reduce()
+            pm, vm = g.counts_reduce_times()
+            nccl_ms[0] += pm; nccl_ms[1] += vm; nccl_ms[2] += 1
         else:
             g.variants_count()     # one rank: the local sort + reduce-by-key of the variant records is all that is left of the exchange
         return time.time() - t
@@ -438,8 +441,10 @@ def main():
                                    ms=[float(stats[S["tier%d_ns" % t]]) / 1e6 for t in range(3)]),
                     wall_ms_per_step_device_api=1000.0 * t_wall_dev / a.steps,
                     exchange=(dict(collective="xm_counts_reduce: ncclAllReduce(int32 sum) of the count planes + all-gather / reduce-by-key of the variant table, in the library (libnccl loaded at run time)",
-                                   comm_nranks=comm_nranks, plane_bytes_per_gpu=plane_ints * 4, allreduce_ms=1000.0 * t_reduce / a.steps,
-                                   bus_gbs=((plane_ints * 4) * 2.0 * (world - 1) / world / (t_reduce / a.steps) / 1e9) if (world > 1 and t_reduce > 0) else None,
+                                   comm_nranks=comm_nranks, plane_bytes_per_gpu=plane_ints * 4, exchange_ms_per_step=1000.0 * t_reduce / a.steps,
+                                   plane_allreduce_ms=(nccl_ms[0] / nccl_ms[2]) if nccl_ms[2] else None, variant_exchange_ms=(nccl_ms[1] / nccl_ms[2]) if nccl_ms[2] else None,
+                                   plane_allreduce_bus_gbs=((plane_ints * 4) * 2.0 * (world - 1) / world / (nccl_ms[0] / nccl_ms[2] / 1e3) / 1e9) if (nccl_ms[2] and nccl_ms[0] > 0) else None,
+                                   note="exchange_ms_per_step = reset of the planes + ncclAllReduce of the planes (device time: plane_allreduce_ms, rank 0) + exchange and merge of the variant table (variant_exchange_ms), wall clock, max over ranks",
                                    align_ms_per_step_max_rank=1000.0 * t_align / a.steps, align_ms_per_step_min_rank=1000.0 * float(tmin[4]) / a.steps, check=reduce_check)
                               if reduce_every_step else None),
                     allreduce_ms=(1000.0 * t_reduce / a.steps) if reduce_every_step else None)

@@ -206,6 +206,9 @@ int xm_measure_peaks(xm_handle* h, double* out /* 5 doubles */);
 int xm_comm_unique_id(uint8_t* id128);
 int xm_comm_init(xm_handle* h, int32_t n_ranks, int32_t rank, const uint8_t* id128);
 int xm_counts_reduce(xm_handle* h);
+/* Measurement aid: of the latest xm_counts_reduce, the device time of the ncclAllReduce of the planes (CUDA events) and the time the
+ * exchange + merge of the variant table took after it. */
+int xm_counts_reduce_times(xm_handle* h, double* planes_allreduce_ms, double* variants_ms);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ EXPORTS = ["xm_create", "xm_destroy", "xm_last_error", "xm_set_reference", "xm_s
            "xm_build_index", "xm_get_index_length", "xm_index_info", "xm_set_duplications", "xm_build_duplications",
            "xm_get_duplications", "xm_align_batch", "xm_align_batch_device", "xm_results_array", "xm_release_results",
            "xm_counts_enable", "xm_counts_device_ptr", "xm_counts_fetch", "xm_format_sam",
-           "xm_comm_unique_id", "xm_comm_init", "xm_counts_reduce", "xm_counts_batch_info", "xm_variants_fetch", "xm_measure_peaks"]
+           "xm_comm_unique_id", "xm_comm_init", "xm_counts_reduce", "xm_counts_batch_info", "xm_variants_fetch", "xm_measure_peaks", "xm_counts_reduce_times"]
 
 RESULT_ARRAYS = [("q_comp_off", np.int64), ("comp_choice_off", np.int64), ("choice_sa_off", np.int64), ("sa_block_off", np.int64),
                  ("choice_f64", np.float64), ("sa_f64", np.float64), ("choice_inner", np.int32), ("sa_contig", np.int32),
@@ -293,6 +293,11 @@ class XMapper:
 
     def counts_reduce(self):
         self._ok(self.L.xm_counts_reduce(self.h))
+
+    def counts_reduce_times(self):
+        a, b = C.c_double(), C.c_double()
+        self._ok(self.L.xm_counts_reduce_times(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def counts_fetch(self, contig):
         out = np.zeros(4 * self.contig_lengths[contig], dtype=np.int32)

@@ -769,7 +769,8 @@ struct xm_handle {
   unsigned long long var_n = 0, var_cap = 0, var_reduced_n = 0;
   long long next_gid = 0;                       // global id of the first sequence of the next batch (xm_counts_batch_info overrides it)
   bool have_batch_info = false; long long info_first_gid = 0; std::vector<int64_t> info_order;
-  ncclComm_t comm = nullptr; int comm_ranks = 0, comm_rank = 0;   // xm_comm_init: the communicator xm_counts_reduce uses
+  ncclComm_t comm = nullptr; int comm_ranks = 0, comm_rank = 0;
+  double last_planes_ms = 0, last_variants_ms = 0;   // xm_counts_reduce: device time of the plane all-reduce, wall time of the variant-table exchange   // xm_comm_init: the communicator xm_counts_reduce uses
 };
 
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -1614,8 +1615,11 @@ int xm_counts_reduce(xm_handle* h) {
   CK(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   // int32 sums are exact and order-free: every rank ends with the planes of the whole run (QV/DirectionalAlignments.java:20-28)
+  CK(cudaEventRecord(h->ev2, st));
   ncclResult_t r = N.AllReduce(h->d_planes.p, h->d_planes.p, (size_t)h->n_plane_ints, ncclInt32, ncclSum, h->comm, st);
   if (r != ncclSuccess) { h->err = std::string("ncclAllReduce: ") + N.GetErrorString(r); return XM_ERR_CUDA; }
+  CK(cudaEventRecord(h->ev3, st));
+  const double t_var0 = now_ms();
   // the sparse variant tables: every rank reduces its own, all-gathers the sizes, receives every other rank's entries behind its own
   // (one broadcast per rank, grouped) and reduces the concatenation - (sum, best example) is associative and commutative, so every
   // rank ends with the table of the whole run
@@ -1655,6 +1659,13 @@ int xm_counts_reduce(xm_handle* h) {
     if (rc != XM_OK) return rc;
   }
   CK(cudaStreamSynchronize(st));
+  { float ms = 0; cudaEventElapsedTime(&ms, h->ev2, h->ev3); h->last_planes_ms = ms; h->last_variants_ms = now_ms() - t_var0 - ms; if (h->last_variants_ms < 0) h->last_variants_ms = 0; }
+  return XM_OK;
+}
+int xm_counts_reduce_times(xm_handle* h, double* planes_ms, double* variants_ms) {
+  if (!h) return XM_ERR_ARG;
+  if (planes_ms) *planes_ms = h->last_planes_ms;
+  if (variants_ms) *variants_ms = h->last_variants_ms;
   return XM_OK;
 }
 int xm_counts_batch_info(xm_handle* h, int64_t first_sequence_id, const int64_t* seq_order_key, int64_t n_sequences) {
