@@ -287,6 +287,27 @@ def main():
     for _ in range(a.warmup):
         r, _ = step_device()
     bad = int((r["q_status"] != 0).sum())
+    # the same step on ONE GPU of this box while the others idle (rank 0 alone, no collective): what the N-GPU number is to be held against,
+    # since the driver's N=1 run measures configs[1] and this run configs[3]
+    solo = None
+    if world > 1 and reduce_every_step:
+        barrier()
+        if rank == 0:
+            ns = 0
+            ex = 0.0
+            k = min(a.steps, 3)
+            for _ in range(k):
+                tb = begin_step()
+                rs = g.align_batch_device(nq, dev["packed"].data_ptr(), n_words, dev["seq_word_off"].data_ptr(), dev["seq_len"].data_ptr(), dev["n_seqs"].data_ptr(),
+                                          dev["expected_inner"].data_ptr(), dev["per_penalty"].data_ptr(), a.read_len)
+                torch.cuda.synchronize()
+                t = time.time()
+                g.variants_count()
+                ex += tb + time.time() - t
+                ns += int(rs["stats"][capi.STAT["kernel_ns"]])
+            solo = dict(value=nq * k / (ns / 1e9 + ex), unit=UNIT, ms_per_step=1000.0 * (ns / 1e9 + ex) / k, steps=k,
+                        note="rank 0 alone on the same workload, the other GPUs idle, no collective (local reduce of the variant records only)")
+        barrier()
     # ---- timed: kernel leg (inputs resident in HBM), device time from CUDA events inside the library + the exchange step ----
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -447,6 +468,7 @@ def main():
                                    note="exchange_ms_per_step = reset of the planes + ncclAllReduce of the planes (device time: plane_allreduce_ms, rank 0) + exchange and merge of the variant table (variant_exchange_ms), wall clock, max over ranks",
                                    align_ms_per_step_max_rank=1000.0 * t_align / a.steps, align_ms_per_step_min_rank=1000.0 * float(tmin[4]) / a.steps, check=reduce_check)
                               if reduce_every_step else None),
+                    single_gpu_same_workload=solo,
                     allreduce_ms=(1000.0 * t_reduce / a.steps) if reduce_every_step else None)
         if not a.no_cpu_baseline and world == 1:
             n_sample = min(a.reads, a.cpu_sample)
