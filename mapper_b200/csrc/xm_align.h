@@ -1252,6 +1252,55 @@ XM_HD inline DAln cascade_t(WS& w, const ACtx& c, const Sec& q, const Sec& r, co
   else return path_align(w, c, q, r, p, an);
 }
 
+
+// ---- reference windows through TMA (cp.async.bulk) into shared memory ----
+// Layout of a warp's staging area (XM_STAGE_BYTES): [0,8) mbarrier; [16, 16 + XM_STAGE_PACKED) the packed window as the bulk copy
+// delivers it (16-byte aligned source, whole 16-byte units); then XM_STAGE_WINDOW bytes: the window, one code per byte.
+static const int XM_STAGE_PACKED = 176, XM_STAGE_WINDOW = 320, XM_STAGE_BYTES = 16 + XM_STAGE_PACKED + XM_STAGE_WINDOW;
+static_assert(XM_STAGE_BYTES <= XM_SVC_SEQ_CAP, "the staging area lives in the per-warp dynamic shared memory slice");
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void stage_init(unsigned char* stage) {   // lane 0, once per warp
+  const unsigned int mbar = (unsigned int)__cvta_generic_to_shared(stage);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// Fetches bases [start, end) of the forward strand `ref` into the staging area and unpacks them; returns the byte window or nullptr
+// when the window does not fit (the caller then unpacks from global memory).  One elected lane issues the bulk copy; the warp waits on
+// the mbarrier (phase bit in WS) and the 32 lanes unpack from shared memory.
+__device__ __noinline__ const uint8_t* stage_window(WS& w, const SeqView& ref, int start, int end) {
+  const int wn = end - start;
+  if (w.stage == nullptr || ref.rc || wn < 1 || wn > XM_STAGE_WINDOW) return nullptr;
+  const char* first = (const char*)ref.w + ((start >> 2) << 1);                 // the 16-bit word that holds base `start`
+  const char* src = (const char*)((unsigned long long)first & ~15ull);
+  const int lead = (int)(first - src);
+  const int bytes = (lead + (((end + 3) >> 2) << 1) - ((start >> 2) << 1) + 15) & ~15;
+  if (bytes > XM_STAGE_PACKED) return nullptr;
+  const int lane = (int)(threadIdx.x & 31);
+  unsigned char* packed = w.stage + 16;
+  uint8_t* out = w.stage + 16 + XM_STAGE_PACKED;
+  const unsigned int mbar = (unsigned int)__cvta_generic_to_shared(w.stage);
+  const unsigned int phase = w.stage_phase;
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");              // earlier generic-proxy reads of the area are done
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"((unsigned int)__cvta_generic_to_shared(packed)), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+  }
+  unsigned int done = 0;
+  while (!done) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }" : "=r"(done) : "r"(mbar), "r"(phase) : "memory");
+  }
+  const unsigned short* words = (const unsigned short*)(packed + lead);
+  const int w0 = start >> 2;
+  for (int k = lane; k < wn; k += 32) { const int b = start + k; out[k] = (uint8_t)((words[(b >> 2) - w0] >> ((b & 3) << 2)) & 15); }
+  __syncwarp();
+  if (lane == 0) w.stage_phase = phase ^ 1u;
+  __syncwarp();
+  return out;
+}
+#endif
+
 // ---------------- QueryMatch_Aligner ----------------
 struct SAStore { int contig, ref_reversed, a_mate, a_rev, n_blk, pad; double penalty, aligned; Blk* blk; };
 struct QAStore { double spacing, multiplier, bonus, total; int inner, n_sa; SAStore sa[2]; };
@@ -1298,8 +1347,15 @@ XM_FN DAln qma_align_match(WS& w, const ACtx& c, const SM& sm, const Params& p, 
   an.predicted = best_offset; an.confident = sm.from_hash ? 1 : 0;
   if (EASY) return straight_align_t<true, ST_STRAIGHT1>(w, c, q, r, p, an);
 #if defined(__CUDA_ARCH__)
-  {  // every stage of the cascade reads the reference through this window: unpack it once (lanes split the bases)
+  {  // every stage of the cascade reads the reference through this window: fetch it once - by TMA into shared memory when it fits the
+     // warp's staging area, else unpacked from global memory into the arena (lanes split the bases)
     const int wn = r.end - r.start;
+    const uint8_t* sw = stage_window(w, c.b, r.start, r.end);
+    if (sw != nullptr) {
+      ACtx cw = c;
+      cw.b.bytes = sw; cw.b.b0 = r.start; cw.b.bn = wn;
+      return cascade_t<ST_STRAIGHT1>(w, cw, q, r, p, an);
+    }
     if (wn > 0 && w.scratch_top + wn + 64 <= w.scratch_size) {
       uint8_t* wb = (uint8_t*)w.salloc(wn);
       XM_NOUNROLL

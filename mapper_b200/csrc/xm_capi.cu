@@ -42,9 +42,9 @@ using namespace xm;
 #define XM_FULL_BLOCK 1024
 #endif
 #ifndef XM_FULL_MIN_BLOCKS
-#define XM_FULL_MIN_BLOCKS 1
+#define XM_FULL_MIN_BLOCKS 2
 #endif
-#define XM_SVC_BYTES_PER_WARP (((sizeof(PathState) + 15) & ~(size_t)15) + XM_SVC_SEQ_CAP)
+#define XM_SVC_BYTES_PER_WARP (((sizeof(PathState) + 15) & ~(size_t)15) + XM_SVC_SEQ_CAP)   // dynamic shared memory per warp of the full kernel: a server's PathState + sections, or a client's TMA staging area (XM_STAGE_BYTES, smaller)
 struct BatchD {
   int n_queries;
   const uint16_t* packed; const int64_t* seq_word_off; const int32_t* seq_len; const int64_t* first_seq;  // first_seq: n_queries+1
@@ -65,6 +65,8 @@ struct LaunchD {
   int last_tier;
   int exp_groups;                         // experiment: distinct query streams per block (XM_EXP_GROUPS, default 1)
   int exp_dup;                            // experiment (XM_EXP_DUP=n): every warp of a block aligns the same n queries, results discarded by overwrite
+  int dyn_stride;                         // bytes of dynamic shared memory per warp (XM_SVC_BYTES_PER_WARP with the search service on, else XM_STAGE_BYTES)
+  int use_tma;                            // full kernel: reference windows are fetched with cp.async.bulk into the warp's staging area in shared memory
   PaServiceRef svc; int n_server_sms;     // PathAligner search service: the blocks that land on the first n_server_sms SMs to ask run nothing but pa_search for the others (xm_align.h)
   long long* q_cycles;                    // optional per-query cost probe (XM_QCYCLES=1): clock64 ticks of the tier that finished it
 };
@@ -117,8 +119,8 @@ __global__ void __launch_bounds__(EASY ? XM_BLOCK : XM_FULL_BLOCK, EASY ? XM_MIN
     if (is_server) {
       // ---- search server: this SM runs only the lattice search, for whichever client asks next ----
       extern __shared__ __align__(16) unsigned char xm_dyn_smem[];   // per warp: a PathState + the two padded sections (XM_SVC_BYTES_PER_WARP)
-      PathState& S = *(PathState*)(xm_dyn_smem + (size_t)warp_in_block * XM_SVC_BYTES_PER_WARP);
-      uint8_t* seq = xm_dyn_smem + (size_t)warp_in_block * XM_SVC_BYTES_PER_WARP + ((sizeof(PathState) + 15) & ~(size_t)15);
+      PathState& S = *(PathState*)(xm_dyn_smem + (size_t)warp_in_block * L.dyn_stride);
+      uint8_t* seq = xm_dyn_smem + (size_t)warp_in_block * L.dyn_stride + ((sizeof(PathState) + 15) & ~(size_t)15);
       while (true) {
         unsigned int pos = 0; int slot1 = 0;
         if (lane == 0) {
@@ -161,6 +163,14 @@ __global__ void __launch_bounds__(EASY ? XM_BLOCK : XM_FULL_BLOCK, EASY ? XM_MIN
     }
     w.svc = L.svc; w.svc_slot = (int)warp;
     if (n_srv == 0) w.svc.reqs = nullptr;
+    {
+      extern __shared__ __align__(16) unsigned char xm_dyn_smem[];
+      unsigned char* stage = L.use_tma ? xm_dyn_smem + (size_t)warp_in_block * L.dyn_stride : nullptr;
+#if defined(__CUDA_ARCH__)
+      if (lane == 0) { w.stage = stage; w.stage_phase = 0; if (stage) stage_init(stage); }
+#endif
+      __syncwarp();
+    }
   }
   unsigned long long st[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (L.n_ids_ptr) L.n_ids = *L.n_ids_ptr;
@@ -188,7 +198,7 @@ __global__ void __launch_bounds__(EASY ? XM_BLOCK : XM_FULL_BLOCK, EASY ? XM_MIN
     q.per_penalty = q.n_seqs > 1 ? L.batch.per_penalty[qi] : 1.0;
     OutQuery rec; rec.status = 0; rec.n_comp = 1; rec.n_choice[0] = 0; rec.n_choice[1] = 0; rec.choice_first[0] = 0; rec.choice_first[1] = 0;
     w.hard_hint = 1 << 20;  // anything but Q_HARD (workspace exhausted in the first pass): assume long
-    if (EASY) w.svc.reqs = nullptr;
+    if (EASY) { w.svc.reqs = nullptr; w.stage = nullptr; }
     if (!ws_init(w, arena, L.arena_bytes, &L.ref, &L.ix, &L.dup, L.prm, q, !EASY)) w.status = Q_NEED_MORE;
     else align_query<EASY>(w, L.out, rec);
     __syncwarp();
@@ -756,7 +766,8 @@ struct xm_handle {
   DevBuf d_sam_len, d_sam_text, d_sam_names, d_sam_name_off, d_sam_cnames, d_sam_cname_off;
   std::shared_ptr<PinnedPool> pinned = std::make_shared<PinnedPool>();
   bool probe_cycles = false, sort_hard = true;
-  int path_servers = 40;  // XM_PATH_SERVERS: SMs of the full kernel's launch that run only the PathAligner search service (0 = every warp searches for itself)
+  bool use_tma = true;    // XM_TMA=0: reference windows are unpacked from global memory (the round-1 path)
+  int path_servers = 0;   // XM_PATH_SERVERS: SMs of the full kernel's launch that run only the PathAligner search service (0 = every warp searches for itself)
   DevBuf d_svc;
   int big_pool = 64;  // XM_BIG_POOL: next-tier arenas available inside a full-kernel launch (0 = off)
   long long cap_choices = 0, cap_sas = 0, cap_blocks = 0;
@@ -848,6 +859,7 @@ int xm_create(const xm_params* p, int device, xm_handle** out) {
   { int nb = 0; if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, xm_align_kernel<true>, XM_BLOCK, 0) == cudaSuccess && nb > 0) h->blocks_per_sm = nb; }
   if (const char* e = getenv("XM_BLOCKS_PER_SM")) { int v = atoi(e); if (v > 0) h->blocks_per_sm = v; }
   if (const char* e = getenv("XM_SORT_HARD")) h->sort_hard = atoi(e) != 0;
+  if (const char* e = getenv("XM_TMA")) h->use_tma = atoi(e) != 0;
   if (const char* e = getenv("XM_PATH_SERVERS")) { int v = atoi(e); if (v >= 0 && v < h->sm_count) h->path_servers = v; }
   if (const char* e = getenv("XM_BIG_POOL")) { int v = atoi(e); if (v >= 0 && v <= 1024) h->big_pool = v; }
   if (const char* e = getenv("XM_FULL_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) h->full_blocks_per_sm = v; }
@@ -857,7 +869,7 @@ int xm_create(const xm_params* p, int device, xm_handle** out) {
     fprintf(stderr, "xmapper_b200: stream/event creation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
     xm_destroy(h); return XM_ERR_CUDA;
   }
-  if (cudaFuncSetAttribute(xm_align_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((XM_FULL_BLOCK / 32) * XM_SVC_BYTES_PER_WARP)) != cudaSuccess) { cudaGetLastError(); h->path_servers = 0; }
+  if (cudaFuncSetAttribute(xm_align_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((XM_FULL_BLOCK / 32) * XM_SVC_BYTES_PER_WARP)) != cudaSuccess) { cudaGetLastError(); h->path_servers = 0; h->use_tma = false; }
   for (auto& sl : h->slots) {
     if (cudaStreamCreateWithFlags(&sl.copy, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&sl.kernels_done, cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&sl.ev0) != cudaSuccess || cudaEventCreate(&sl.ev1) != cudaSuccess) {
@@ -1251,7 +1263,7 @@ static int align_batch_impl(xm_handle* h, SlotLease& lease, bool wait_h2d, int32
     if (blocks < 1) { h->err = "workspace budget too small for one block"; return XM_ERR_CUDA; }
     // search service: the first n_srv blocks of a full-size launch run only pa_search (they own no arena); small launches keep every block a client
     int n_srv = 0;
-    L.svc.reqs = nullptr; L.n_server_sms = 0;
+    L.svc.reqs = nullptr; L.n_server_sms = 0; L.use_tma = (tier >= 0 && h->use_tma) ? 1 : 0;
     if (tier >= 0 && h->path_servers > 0 && blocks == h->sm_count * h->full_blocks_per_sm && cpb == h->full_warps && h->sm_count > 2 * h->path_servers) {
       n_srv = h->path_servers;
       const int client_warps = blocks * cpb;   // upper bound: the ring and the request slots are sized for every warp of the launch
@@ -1296,8 +1308,9 @@ static int align_batch_impl(xm_handle* h, SlotLease& lease, bool wait_h2d, int32
     L.exp_groups = 1;
     if (tier >= 0) { if (const char* e = getenv("XM_EXP_DUP")) L.exp_dup = atoi(e); if (const char* e = getenv("XM_EXP_GROUPS")) L.exp_groups = atoi(e) > 0 ? atoi(e) : 1; }
     CK(cudaEventRecord(e0, st));
+    L.dyn_stride = n_srv > 0 ? (int)XM_SVC_BYTES_PER_WARP : (L.use_tma ? XM_STAGE_BYTES : 0);
     if (tier < 0) xm_align_kernel<true><<<blocks, block, 0, st>>>(L);
-    else xm_align_kernel<false><<<blocks, 32 * cpb, n_srv > 0 ? (size_t)cpb * XM_SVC_BYTES_PER_WARP : 0, st>>>(L);
+    else xm_align_kernel<false><<<blocks, 32 * cpb, (size_t)cpb * (size_t)L.dyn_stride, st>>>(L);
     CK(cudaEventRecord(e1, st));
     launches++;
     CK(cudaGetLastError());

@@ -240,6 +240,10 @@ struct WS {
     if (scratch_top + bytes > scratch_size) { fail(Q_NEED_MORE); return nullptr; }
     void* p = scratch + scratch_top; scratch_top += bytes; return p;
   }
+  // TMA staging area of this warp in shared memory (device, full kernel): an mbarrier, the packed reference window as cp.async.bulk
+  // delivers it, and the window unpacked to one code per byte (what every stage of the cascade reads).  nullptr: windows are unpacked
+  // from global memory into the arena.
+  unsigned char* stage; unsigned int stage_phase;
   PaServiceRef svc; int svc_slot;   // PathAligner search service (xm_align.h): reqs == nullptr = searches run on this warp
   uint32_t* cell_hdr; uint32_t* cellmap; long long cell_words;  // PathAligner lattice map region of the arena (xm_align.h: PathState::cell)
   uint8_t* qbytes[2][2];  // [mate][reverse-complemented]: one code per byte
