@@ -79,7 +79,9 @@ int xm_finish_index(xm_handle* h, int32_t min_interesting_size, int32_t max_buil
  * reference inside the library (HashBlock_Database.hashSequenceThroughSize/addHashblocks, :490-618).
  * n_threads == 0: built on the device (pyramid + gapmer kernel over reference slices, radix sorts, PackedMap fill kernel);
  * n_threads > 0: the library's host builder with that many threads (bit-identical tables; kept as the cross-check).
- * Unambiguous references only in this round (returns XM_ERR_ARG otherwise). */
+ * IUPAC-ambiguous ("-anc") references: both builders expand the reference's MultiHashBlocks (M/HashBlock_ParentRow.java:97-191)
+ * and apply PackedMap.add(preventDuplicates) :117-131; the device builder gives every ambiguous 8 kbp slice a workspace of
+ * XM_INDEX_AMB_ARENA_MB (default 64) MiB and returns XM_ERR_ARG, never a partial index, if an expansion outgrows it. */
 int xm_build_index(xm_handle* h, int32_t max_used, int32_t n_threads);
 /* Reads back a table (for parity tests against the host's PackedMaps). Pass NULL arrays to query sizes. */
 int xm_get_index_length(xm_handle* h, int32_t n_used, int32_t* capacity, int32_t* max_count, int64_t* n_positions,

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
+#include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_run_length_encode.cuh>
@@ -359,8 +360,9 @@ struct IndexBuildD {
   const int* cap;                      // hi + 1 capacities
   char* arenas; long long arena_bytes; // per warp: two level buffers
   unsigned long long* keys; uint32_t* vals; unsigned long long cap_entries;
-  unsigned long long* n_entries; int* ticket;
+  unsigned long long* n_entries; int* ticket; int* fail;
 };
+static const unsigned long long XM_IX_MULTI = 1ull << 63;   // key bit of a MultiHashBlock possibility: above the sorted bits, dropped by the de-duplication
 __device__ __forceinline__ int32_t ext_hash_lane(const SeqView& seq, int from, int n, int dir, bool complement) {  // one block per LANE
   int32_t h = 0;
   for (int k = 0; k < n; k++) {
@@ -465,6 +467,106 @@ __global__ void __launch_bounds__(128) xm_index_emit_kernel(IndexBuildD B) {
     }
   }
 }
+
+// Slices of an IUPAC-ambiguous reference (an "-anc" reference, M/AncestryDetector.java:323-327): one warp per slice builds the
+// MultiHashBlock pyramid of the slice's window with the query path's own builder (pyr_build -> pyr_build_ambiguous,
+// M/HashBlock_ParentRow.java:69-191) in a per-warp arena, then lanes take a row's entries and walk their possibilities; an entry
+// of a multi-block carries XM_IX_MULTI so that xm_index_dedupe_kernel can apply PackedMap.add(preventDuplicates) :117-131.
+__global__ void __launch_bounds__(32) xm_index_emit_amb_kernel(IndexBuildD B) {
+  __shared__ WS w;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  char* arena = B.arenas + (long long)blockIdx.x * B.arena_bytes;
+  while (true) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(B.ticket, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= B.n_slices) break;
+    const int contig = B.slice_contig[t], s = B.slice_start[t];
+    const SeqView full = B.ref.contig(contig, 0);
+    const int e = min(full.len, s + B.slice_len);
+    const int wlen = min(full.len, e + 4 * B.hi + 256) - s;   // the host builder's halo (xm_host_model.h: ambiguous_window_blocks)
+    const long long g_fwd = B.ref.gstart[2 * contig], g_rev = B.ref.gstart[2 * contig + 1];
+    __syncwarp();
+    for (int k = lane; k < (int)(sizeof(WS) / 4); k += 32) ((uint32_t*)&w)[k] = 0;
+    __syncwarp();
+    MatePath& m = w.mp[0];
+    Pyr& P = m.pyr;
+    {
+      SeqView v; v.w = full.w + (s >> 2); v.len = wlen; v.rc = 0; v.bytes = nullptr; v.b0 = 0; v.bn = 0;   // s is a multiple of 4
+      m.q = v;
+      const long long cap = 10LL * wlen + 256;
+      const long long lev_bytes = ((long long)(wlen + 3) * 4 + 15) & ~15LL;
+      char* p = arena;
+      P.cap_levels = wlen + 2; P.cap_blocks = (int)cap;
+      P.level_off = (int32_t*)p; p += lev_bytes;
+      P.blk = (HB16*)p; p += cap * 16; P.child = (int16_t*)p; p += cap * 2; P.up = (int16_t*)p; p += cap * 2;
+      p += (16 - ((uintptr_t)p & 15)) & 15;
+      w.scratch = p; w.scratch_size = (long long)(arena + B.arena_bytes - p) & ~15LL; w.scratch_top = 0;
+    }
+    __syncwarp();
+    const bool built = pyr_build(w, m) && w.status == 0;
+    __syncwarp();
+    if (!built) { if (lane == 0) atomicExch(B.fail, w.status ? w.status : Q_NEED_MORE); continue; }
+    for (int level = 0; level < P.n_levels; level++) {
+      const int n = pyr_level_size(P, level);
+      const HB16* row = P.blk + P.level_off[level];
+      bool any_short = false;
+      for (int base = 0; base < n; base += 32) {
+        const int idx = base + lane;
+        HB16 c; bool valid = false; int k_n = 0;
+        if (idx < n) { c = row[idx]; valid = (s + (int)c.start) < e; if (valid) k_n = pyr_num_opts(c); }
+        if (__ballot_sync(0xffffffffu, valid) == 0) break;   // starts ascend within a row
+        const int k_max = __reduce_max_sync(0xffffffffu, k_n);
+        const unsigned long long multi = (valid && (c.flags & HB_MULTI)) ? XM_IX_MULTI : 0ull;
+        for (int k = 0; k < k_max; k++) {
+          bool prim = false, sec = false; HB g;
+          if (k < k_n) {
+            HB16 o16; bool has = true;
+            if (c.flags & HB_MULTI) { const POpt* o = P.opt + c.fwd + k; has = o->has != 0; o16 = o->hb; } else o16 = c;
+            if (has) {
+              if ((int)o16.len <= B.hi) any_short = true;
+              HB b; b.start = s + o16.start; b.len = o16.len; b.used = o16.len; b.fwd = o16.fwd; b.rev = o16.rev; b.gap_dir = o16.gap_dir; b.flags = o16.flags; b.extra = o16.extra; b.ident = 0;
+              bool ok = true;
+              if (B.gapmers) ok = gapmer_lane(b, full, g); else g = b;
+              if (ok && g.used >= B.min_interesting && g.used <= B.hi) {
+                const bool rml = g.rml(), rmr = g.rmr();
+                prim = (rml != rmr) ? rml : (g.fwd >= g.rev);
+                sec = (rml != rmr) ? rmr : (g.fwd <= g.rev);
+              }
+            }
+          }
+          const unsigned pm = __ballot_sync(0xffffffffu, prim), sm = __ballot_sync(0xffffffffu, sec);
+          const int total = __popc(pm) + __popc(sm);
+          if (total) {
+            unsigned long long at = 0;
+            if (lane == 0) at = atomicAdd(B.n_entries, (unsigned long long)total);
+            at = __shfl_sync(0xffffffffu, at, 0);
+            if (B.keys != nullptr && at + total <= B.cap_entries) {
+              const int cp = B.cap[(prim || sec) ? g.used : 0];
+              if (prim) { int r = g.fwd % cp; if (r < 0) r += cp; const unsigned long long o = at + __popc(pm & lt_mask); B.keys[o] = multi | ((unsigned long long)g.used << 32) | (unsigned)r; B.vals[o] = (uint32_t)(g_fwd + g.start); }
+              if (sec) { int r = g.rev % cp; if (r < 0) r += cp; const unsigned long long o = at + __popc(pm) + __popc(sm & lt_mask); B.keys[o] = multi | ((unsigned long long)g.used << 32) | (unsigned)r; B.vals[o] = (uint32_t)(g_rev + (full.len - g.end())); }
+            }
+          }
+        }
+      }
+      if (!__any_sync(0xffffffffu, any_short)) break;
+    }
+  }
+}
+// PackedMap.add(preventDuplicates) on the sorted entries: a multi-block possibility is dropped when the same (length, bucket,
+// position) was already added - by a plain block (which are never de-duplicated among themselves) or by another possibility.
+__global__ void xm_index_dedupe_kernel(const unsigned long long* keys, const uint32_t* vals, int n, unsigned char* keep) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long k = keys[i];
+  if (!(k & XM_IX_MULTI)) { keep[i] = 1; return; }
+  const unsigned long long km = k & ~XM_IX_MULTI; const uint32_t p = vals[i];
+  bool drop = i > 0 && (keys[i - 1] & ~XM_IX_MULTI) == km && vals[i - 1] == p;
+  for (int j = i + 1; !drop && j < n && (keys[j] & ~XM_IX_MULTI) == km && vals[j] == p; j++) drop = !(keys[j] & XM_IX_MULTI);
+  keep[i] = drop ? 0 : 1;
+}
+struct IxUnmulti { __host__ __device__ unsigned long long operator()(unsigned long long k) const { return k & ~XM_IX_MULTI; } };
 // per run r of equal (used, bucket): kept[r] = count unless the bucket is overfull
 __global__ void xm_index_runs_kernel(const unsigned long long* run_key, const int* run_cnt, int n_runs, long long* kept) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -968,11 +1070,22 @@ static int build_index_device(xm_handle* h, int max_used) {
   B.ref.n_contigs = M.n_contigs; B.ref.words = (const uint16_t*)h->d_words.p; B.ref.word_off = (const int64_t*)h->d_word_off.p;
   B.ref.len = (const int32_t*)h->d_len.p; B.ref.gstart = (const int64_t*)h->d_gstart.p; B.ref.total_fr = M.total_fr;
   const int slice_len = 8192;
-  std::vector<int> sc, ss;
-  for (int c = 0; c < M.n_contigs; c++) for (int s0 = 0; s0 < M.len[(size_t)c]; s0 += slice_len) { sc.push_back(c); ss.push_back(s0); }
+  std::vector<int> sc, ss, amb_sc, amb_ss;   // plain slices; slices whose window holds an IUPAC-ambiguous base (the host builder's test)
+  for (int c = 0; c < M.n_contigs; c++) for (int s0 = 0; s0 < M.len[(size_t)c]; s0 += slice_len) {
+    bool amb = false;
+    if (M.ref_ambiguous) {
+      SeqView seq = M.contig_view(c, 0);
+      const int scan_end = std::min(seq.len, std::min(seq.len, s0 + slice_len) + 4 * hi + 256);
+      for (int i = s0; i < scan_end && !amb; i++) amb = bp_is_ambiguous(seq.at(i));
+    }
+    if (amb) { amb_sc.push_back(c); amb_ss.push_back(s0); } else { sc.push_back(c); ss.push_back(s0); }
+  }
+  const int n_amb = (int)amb_sc.size();
+  if (n_amb && slice_len + 4 * hi + 256 > 32000) { h->err = "xm_build_index: hash lengths this long are not supported on IUPAC-ambiguous references (16-bit window coordinates)"; return XM_ERR_ARG; }
+  DevBuf d_amb_sc, d_amb_ss, d_amb_arena, d_keep;
   DevBuf d_sc, d_ss, d_cap, d_cnt, d_keys_a, d_keys_b, d_vals_a, d_vals_b, d_tmp, d_run_key, d_run_cnt, d_nruns, d_cnt64, d_kept, d_first, d_bbase, d_buckets, d_pos;
   struct Free { std::vector<DevBuf*> v; ~Free() { for (DevBuf* b : v) b->release(); } } fr;
-  fr.v = {&d_sc, &d_ss, &d_cap, &d_cnt, &d_keys_a, &d_keys_b, &d_vals_a, &d_vals_b, &d_tmp, &d_run_key, &d_run_cnt, &d_nruns, &d_cnt64, &d_kept, &d_first, &d_bbase, &d_buckets, &d_pos};
+  fr.v = {&d_amb_sc, &d_amb_ss, &d_amb_arena, &d_keep, &d_sc, &d_ss, &d_cap, &d_cnt, &d_keys_a, &d_keys_b, &d_vals_a, &d_vals_b, &d_tmp, &d_run_key, &d_run_cnt, &d_nruns, &d_cnt64, &d_kept, &d_first, &d_bbase, &d_buckets, &d_pos};
   if (!up(d_sc, sc.data(), sc.size() * 4) || !up(d_ss, ss.data(), ss.size() * 4) || !up(d_cap, cap.data(), cap.size() * 4) || !d_cnt.ensure(64)) { h->err = "out of device memory (index build)"; return XM_ERR_CUDA; }
   B.slice_contig = (const int*)d_sc.p; B.slice_start = (const int*)d_ss.p; B.n_slices = (int)sc.size(); B.slice_len = slice_len;
   B.hi = hi; B.min_interesting = M.min_interesting; B.gapmers = M.gapmers; B.cap = (const int*)d_cap.p;
@@ -980,38 +1093,74 @@ static int build_index_device(xm_handle* h, int max_used) {
   B.arena_bytes = (((long long)(slice_len + hi + 2 + 32) * 2 * (long long)sizeof(HB16)) + 255) & ~255LL;
   if (!h->d_ws.ensure((size_t)warps * (size_t)B.arena_bytes)) { h->err = "out of device memory (index build workspace)"; return XM_ERR_CUDA; }
   B.arenas = (char*)h->d_ws.p;
-  B.n_entries = (unsigned long long*)d_cnt.p; B.ticket = (int*)((char*)d_cnt.p + 16);
+  B.n_entries = (unsigned long long*)d_cnt.p; B.ticket = (int*)((char*)d_cnt.p + 16); B.fail = (int*)((char*)d_cnt.p + 32);
+  // ambiguous slices: one warp (one block) each, with an arena for the window's MultiHashBlock pyramid and its possibilities
+  IndexBuildD A = B;
+  int amb_blocks = 0;
+  if (n_amb) {
+    if (!up(d_amb_sc, amb_sc.data(), amb_sc.size() * 4) || !up(d_amb_ss, amb_ss.data(), amb_ss.size() * 4)) { h->err = "out of device memory (index build)"; return XM_ERR_CUDA; }
+    const long long wlen = slice_len + 4LL * hi + 256;
+    long long amb_mb = 64; if (const char* e = getenv("XM_INDEX_AMB_ARENA_MB")) amb_mb = std::max(8, atoi(e));
+    A.arena_bytes = ((((wlen + 3) * 4 + 15) & ~15LL) + (10 * wlen + 256) * 20 + 64 + (amb_mb << 20) + 255) & ~255LL;
+    amb_blocks = std::min(n_amb, h->sm_count * 2);
+    while (amb_blocks > 1 && !d_amb_arena.ensure((size_t)amb_blocks * (size_t)A.arena_bytes)) { cudaGetLastError(); amb_blocks /= 2; }
+    if (!d_amb_arena.ensure((size_t)amb_blocks * (size_t)A.arena_bytes)) { h->err = "out of device memory (ambiguous index workspace)"; return XM_ERR_CUDA; }
+    A.arenas = (char*)d_amb_arena.p;
+    A.slice_contig = (const int*)d_amb_sc.p; A.slice_start = (const int*)d_amb_ss.p; A.n_slices = n_amb;
+  }
+  auto emit = [&](unsigned long long* keys, uint32_t* vals, unsigned long long cap_entries) -> int {
+    B.keys = A.keys = keys; B.vals = A.vals = vals; B.cap_entries = A.cap_entries = cap_entries;
+    CK(cudaMemsetAsync(d_cnt.p, 0, 64, st));
+    if (B.n_slices) xm_index_emit_kernel<<<blocks, 128, 0, st>>>(B);
+    if (n_amb) { CK(cudaMemsetAsync(B.ticket, 0, 4, st)); xm_index_emit_amb_kernel<<<amb_blocks, 32, 0, st>>>(A); }
+    CK(cudaGetLastError());
+    return XM_OK;
+  };
   // pass 1 counts the entries, pass 2 writes them
-  B.keys = nullptr; B.vals = nullptr; B.cap_entries = 0;
-  CK(cudaMemsetAsync(d_cnt.p, 0, 64, st));
-  xm_index_emit_kernel<<<blocks, 128, 0, st>>>(B);
-  unsigned long long E = 0;
-  CK(cudaMemcpyAsync(&E, d_cnt.p, 8, cudaMemcpyDeviceToHost, st));
+  if (int rc = emit(nullptr, nullptr, 0)) return rc;
+  unsigned long long cnt_host[8] = {0};
+  CK(cudaMemcpyAsync(cnt_host, d_cnt.p, 64, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
+  unsigned long long E = cnt_host[0];
+  if (const int fs = (int)(cnt_host[4] & 0xffffffffu)) { h->err = "xm_build_index: MultiHashBlock expansion of the reference ran out of workspace (status " + std::to_string(fs) + "); raise XM_INDEX_AMB_ARENA_MB or use the host builder (n_threads > 0)"; return XM_ERR_ARG; }
   M.tables.assign((size_t)hi + 1, HostTable());
   if (E >= (1ull << 31)) { h->err = "xm_build_index: more than 2^31 index entries"; return XM_ERR_ARG; }
   if (E > 0) {
     if (!d_keys_a.ensure(E * 8) || !d_keys_b.ensure(E * 8) || !d_vals_a.ensure(E * 4) || !d_vals_b.ensure(E * 4)) { h->err = "out of device memory (index entries)"; return XM_ERR_CUDA; }
-    B.keys = (unsigned long long*)d_keys_a.p; B.vals = (uint32_t*)d_vals_a.p; B.cap_entries = E;
-    CK(cudaMemsetAsync(d_cnt.p, 0, 64, st));
-    xm_index_emit_kernel<<<blocks, 128, 0, st>>>(B);
-    CK(cudaGetLastError());
-    const int n = (int)E;
+    if (int rc = emit((unsigned long long*)d_keys_a.p, (uint32_t*)d_vals_a.p, E)) return rc;
+    int n = (int)E;
     // (used, bucket, position) order: sort by position, then a stable sort by (used << 32 | bucket)
     size_t t1 = 0, t2 = 0, t3 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, t1, (const uint32_t*)d_vals_a.p, (uint32_t*)d_vals_b.p, (const unsigned long long*)d_keys_a.p, (unsigned long long*)d_keys_b.p, n, 0, 32, st);
     cub::DeviceRadixSort::SortPairs(nullptr, t2, (const unsigned long long*)d_keys_b.p, (unsigned long long*)d_keys_a.p, (const uint32_t*)d_vals_b.p, (uint32_t*)d_vals_a.p, n, 0, key_bits, st);
     if (!d_run_key.ensure(E * 8) || !d_run_cnt.ensure(E * 4) || !d_nruns.ensure(16)) { h->err = "out of device memory (index runs)"; return XM_ERR_CUDA; }
     cub::DeviceRunLengthEncode::Encode(nullptr, t3, (const unsigned long long*)d_keys_a.p, (unsigned long long*)d_run_key.p, (int*)d_run_cnt.p, (int*)d_nruns.p, n, st);
-    size_t tb = t1 > t2 ? t1 : t2; if (t3 > tb) tb = t3;
+    size_t t4 = 0, t5 = 0;
+    cub::TransformInputIterator<unsigned long long, IxUnmulti, const unsigned long long*> unmulti((const unsigned long long*)d_keys_a.p, IxUnmulti());
+    if (n_amb) {
+      cub::DeviceSelect::Flagged(nullptr, t4, unmulti, (const unsigned char*)nullptr, (unsigned long long*)d_keys_b.p, (int*)d_nruns.p, n, st);
+      cub::DeviceSelect::Flagged(nullptr, t5, (const uint32_t*)d_vals_a.p, (const unsigned char*)nullptr, (uint32_t*)d_vals_b.p, (int*)d_nruns.p, n, st);
+    }
+    size_t tb = t1 > t2 ? t1 : t2; if (t3 > tb) tb = t3; if (t4 > tb) tb = t4; if (t5 > tb) tb = t5;
     if (!d_tmp.ensure(tb + (size_t)E * 8 + 4096)) { h->err = "out of device memory (index sort)"; return XM_ERR_CUDA; }
     size_t q = tb;
     CK(cub::DeviceRadixSort::SortPairs(d_tmp.p, q, (const uint32_t*)d_vals_a.p, (uint32_t*)d_vals_b.p, (const unsigned long long*)d_keys_a.p, (unsigned long long*)d_keys_b.p, n, 0, 32, st));
     q = tb;
     CK(cub::DeviceRadixSort::SortPairs(d_tmp.p, q, (const unsigned long long*)d_keys_b.p, (unsigned long long*)d_keys_a.p, (const uint32_t*)d_vals_b.p, (uint32_t*)d_vals_a.p, n, 0, key_bits, st));
+    const unsigned long long* skeys = (const unsigned long long*)d_keys_a.p; const uint32_t* svals = (const uint32_t*)d_vals_a.p;
+    if (n_amb) {   // PackedMap.add(preventDuplicates): drop the repeated possibilities of multi-blocks, clear the flag bit
+      if (!d_keep.ensure((size_t)n + 16)) { h->err = "out of device memory (index de-duplication)"; return XM_ERR_CUDA; }
+      xm_index_dedupe_kernel<<<(n + 255) / 256, 256, 0, st>>>(skeys, svals, n, (unsigned char*)d_keep.p);
+      q = tb; CK(cub::DeviceSelect::Flagged(d_tmp.p, q, unmulti, (const unsigned char*)d_keep.p, (unsigned long long*)d_keys_b.p, (int*)d_nruns.p, n, st));
+      q = tb; CK(cub::DeviceSelect::Flagged(d_tmp.p, q, svals, (const unsigned char*)d_keep.p, (uint32_t*)d_vals_b.p, (int*)d_nruns.p, n, st));
+      int kept_n = 0;
+      CK(cudaMemcpyAsync(&kept_n, d_nruns.p, 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      n = kept_n; skeys = (const unsigned long long*)d_keys_b.p; svals = (const uint32_t*)d_vals_b.p;
+    }
     q = tb;
-    CK(cub::DeviceRunLengthEncode::Encode(d_tmp.p, q, (const unsigned long long*)d_keys_a.p, (unsigned long long*)d_run_key.p, (int*)d_run_cnt.p, (int*)d_nruns.p, n, st));
+    CK(cub::DeviceRunLengthEncode::Encode(d_tmp.p, q, skeys, (unsigned long long*)d_run_key.p, (int*)d_run_cnt.p, (int*)d_nruns.p, n, st));
     int n_runs = 0;
     CK(cudaMemcpyAsync(&n_runs, d_nruns.p, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -1038,7 +1187,7 @@ static int build_index_device(xm_handle* h, int max_used) {
     IndexFillD F;
     F.run_key = (const unsigned long long*)d_run_key.p; F.run_cnt = (const int*)d_run_cnt.p; F.run_start = run_start; F.kept_off = kept_off; F.n_runs = n_runs;
     F.first_run = (const int*)d_first.p; F.cap = (const int*)d_cap.p; F.bucket_base = (const long long*)d_bbase.p;
-    F.sorted_pos = (const uint32_t*)d_vals_a.p; F.buckets = (unsigned long long*)d_buckets.p; F.positions = (uint32_t*)d_pos.p;
+    F.sorted_pos = svals; F.buckets = (unsigned long long*)d_buckets.p; F.positions = (uint32_t*)d_pos.p;
     xm_index_fill_kernel<<<(n_runs + 255) / 256, 256, 0, st>>>(F);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));

@@ -113,7 +113,6 @@ struct HostModel {
 
   // what both index builders start from: minInterestingSize :51-55, the longest length built and the capacity per length
   bool index_plan(int max_used, int& hi, std::vector<int>& cap, std::string& err) {
-    if (ref_ambiguous) { err = "xm_build_index: the reference contains IUPAC-ambiguous bases; the device builder handles unambiguous references - call xm_build_index with n_threads > 0 (the library's host builder expands MultiHashBlocks) or upload the tables with xm_set_index_length"; return false; }
     min_interesting = j2i(std::max((std::log((double)(total_forward + 1)) / std::log(4.0)) - 2, 1.0));
     hi = std::max(max_used, 2 * choose_min_dup_len());
     cap.assign((size_t)hi + 1, 1);

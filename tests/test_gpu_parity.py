@@ -117,20 +117,20 @@ def test_long_reads_1kbp_split_shape():
     g.close()
 
 
-def test_iupac_ambiguous_reference():
+@pytest.mark.parametrize("threads", [0, 8], ids=["device", "host"])
+def test_iupac_ambiguous_reference(threads):
     """An "-anc" reference (--infer-ancestors writes IUPAC unions into the reference, M/AncestryDetector.java:323-327) produced by the
     oracle's AncestryDetector from a reference with 3-6-copy repeat families; the LIBRARY builds the index (MultiHashBlock fan-out of the
     reference, M/HashBlock_ParentRow.java:97-191 + PackedMap.add(preventDuplicates)) and the duplication table; tables and alignments
-    equal the oracle's, single and paired; the ambiguity penalty decides."""
+    equal the oracle's, single and paired; the ambiguity penalty decides.  threads=0: the device builder (one warp per ambiguous
+    slice runs the query path's MultiHashBlock pyramid, xm_index_emit_amb_kernel + xm_index_dedupe_kernel); threads>0: the host builder."""
     ref = synth.random_reference(600000, seed=91, n_contigs=4, repeat_fraction=0.1, repeat_copies=(3, 6), repeat_len=(300, 2500))
     db, changed = parity.inferred_ancestor_oracle(ref, synth.DEFAULT_PARAMS, threads=8)
     assert changed > 200
     contigs = [(n, s) for n, s in (db.contig(i) for i in range(db.num_contigs()))]
     clean = {n: s for n, s in ref}
     sample_from = [(n, clean[n[:-4]]) for n, _ in contigs]   # reads come from the ORIGINAL reference (names: contigN-anc)
-    g = gpu_from_oracle(db, synth.DEFAULT_PARAMS, 150, 1000, False, False, threads=8)
-    with pytest.raises(capi.XmError):
-        g.build_index(150, threads=0)   # the device builder refuses ambiguous references loudly (no silent fallback)
+    g = gpu_from_oracle(db, synth.DEFAULT_PARAMS, 150, 1000, False, False, threads=threads)
     built = db.build_through(150)
     for n in range(1, built + 1):
         t0, t1 = db.table(n), g.get_index_length(n)
