@@ -92,8 +92,13 @@ int xm_index_info(xm_handle* h, int32_t* min_interesting_size, int32_t* max_buil
  * keys of forward contig `contig`; window = DuplicationDetector.windowSize, granularity = getDetectionGranularity()
  * (DuplicationDetector.java:67-77). */
 int xm_set_duplications(xm_handle* h, int32_t window, double granularity, int32_t contig, int32_t n, const int32_t* starts);
-/* Or build it inside the library from the index (DuplicationDetector.process, :129-214). */
+/* Or build it inside the library from the index (DuplicationDetector.process, :129-214; min_len / max_len < 0: the reference's
+ * defaults, :59-65).  The bucket scan - lookupByForwardHash :41-52 for every bucket with >= min_copies positions, grouping by text -
+ * runs on the device (xm_dup_scan_kernel, block lengths <= 64); saveDuplications' order-dependent containment rule (:332-436) is
+ * applied to the blocks it finds on the host, in the reference's order. */
 int xm_build_duplications(xm_handle* h, int32_t min_len, int32_t max_len, int32_t min_copies, int32_t window);
+/* The same table computed entirely on host threads (any block length); kept as the cross-check of the device scan. */
+int xm_build_duplications_host(xm_handle* h, int32_t min_len, int32_t max_len, int32_t min_copies, int32_t window);
 int xm_get_duplications(xm_handle* h, int32_t contig, int32_t* n, int32_t* starts);
 
 /* AlignerWorker.process(): aligns n_queries queries. Query q owns n_seqs_per_query[q] (1 or 2) consecutive

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("XM_LIB_PATH") or os.path.join(HERE, "libxmapper_b200.so")  # XM_LIB_PATH: build-variant experiments
 
 EXPORTS = ["xm_create", "xm_destroy", "xm_last_error", "xm_set_reference", "xm_set_index_length", "xm_finish_index",
-           "xm_build_index", "xm_get_index_length", "xm_index_info", "xm_set_duplications", "xm_build_duplications",
+           "xm_build_index", "xm_get_index_length", "xm_index_info", "xm_set_duplications", "xm_build_duplications", "xm_build_duplications_host",
            "xm_get_duplications", "xm_align_batch", "xm_align_batch_device", "xm_results_array", "xm_release_results",
            "xm_counts_enable", "xm_counts_device_ptr", "xm_counts_fetch", "xm_format_sam",
            "xm_comm_unique_id", "xm_comm_init", "xm_counts_reduce", "xm_counts_batch_info", "xm_variants_fetch", "xm_measure_peaks", "xm_counts_reduce_times"]
@@ -166,8 +166,10 @@ class XMapper:
             s = np.zeros(1, dtype=np.int32)
         self._ok(self.L.xm_set_duplications(self.h, int(window), C.c_double(granularity), int(contig), n, _ptr(s)))
 
-    def build_duplications(self, min_len=-1, max_len=-1, min_copies=2, window=1000):
-        self._ok(self.L.xm_build_duplications(self.h, min_len, max_len, min_copies, window))
+    def build_duplications(self, min_len=-1, max_len=-1, min_copies=2, window=1000, host=False):
+        """host=False: bucket scan on the device; host=True: the library's host-thread detector (its cross-check)."""
+        f = self.L.xm_build_duplications_host if host else self.L.xm_build_duplications
+        self._ok(f(self.h, min_len, max_len, min_copies, window))
 
     def get_duplications(self, contig):
         n = C.c_int32()

@@ -844,9 +844,11 @@ struct xm_handle {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev5 = nullptr;
   // device mirror of the model
-  uint64_t mirrored_generation = ~0ull;
+  uint64_t mirrored_generation = ~0ull, mirrored_dup_generation = ~0ull;
   DevBuf d_words, d_word_off, d_len, d_gstart, d_tables, d_dup_off, d_dup_starts;
   std::vector<DevBuf> d_buckets, d_positions;
+  std::vector<TableD> tables_host;   // host copy of the device table descriptors
+  DevBuf d_ix_buckets, d_ix_pos;     // tables the device index builder left in place (every length in one allocation)
   RefD ref{}; IndexD ix{}; DupD dup{};
   // Batches in flight.  A call of xm_align_batch owns one slot from its first host->device copy to its last device->host copy: the
   // slot's staging buffers, its copy stream and its device copy of the result arrays.  The kernels of different calls run one after
@@ -907,7 +909,7 @@ struct SlotLease {
 
 static int mirror_model(xm_handle* h) {
   HostModel& M = h->m;
-  if (h->mirrored_generation == M.generation) return XM_OK;
+  if (h->mirrored_generation == M.generation && h->mirrored_dup_generation == M.dup_generation) return XM_OK;
   if (M.n_contigs < 1) { h->err = "reference not set"; return XM_ERR_STATE; }
   if (!M.index_finished) { h->err = "index not set (xm_set_index_length + xm_finish_index, or xm_build_index)"; return XM_ERR_STATE; }
   auto up = [&](DevBuf& b, const void* src, size_t bytes) -> bool {
@@ -915,31 +917,156 @@ static int mirror_model(xm_handle* h) {
     if (bytes && cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return false;
     return true;
   };
-  bool ok = up(h->d_words, M.words.data(), M.words.size() * 2) && up(h->d_word_off, M.word_off.data(), M.word_off.size() * 8) &&
-            up(h->d_len, M.len.data(), M.len.size() * 4) && up(h->d_gstart, M.gstart.data(), M.gstart.size() * 8);
-  size_t nt = (size_t)M.max_built + 1;
-  if (M.tables.size() < nt) M.tables.resize(nt);
-  h->d_buckets.resize(nt); h->d_positions.resize(nt);
-  std::vector<TableD> tabs(nt);
-  for (size_t i = 0; ok && i < nt; i++) {
-    const HostTable& T = M.tables[i];
-    tabs[i].capacity = T.capacity; tabs[i].max_count = T.max_count; tabs[i].buckets = nullptr; tabs[i].positions = nullptr;
-    if (!T.buckets.empty()) {
-      ok = up(h->d_buckets[i], T.buckets.data(), T.buckets.size() * 8) && up(h->d_positions[i], T.positions.data(), T.positions.size() * 4);
-      tabs[i].buckets = (const uint64_t*)h->d_buckets[i].p; tabs[i].positions = (const uint32_t*)h->d_positions[i].p;
+  bool ok = true;
+  if (h->mirrored_generation != M.generation) {   // reference + index tables
+    ok = up(h->d_words, M.words.data(), M.words.size() * 2) && up(h->d_word_off, M.word_off.data(), M.word_off.size() * 8) &&
+         up(h->d_len, M.len.data(), M.len.size() * 4) && up(h->d_gstart, M.gstart.data(), M.gstart.size() * 8);
+    size_t nt = (size_t)M.max_built + 1;
+    if (M.tables.size() < nt) M.tables.resize(nt);
+    h->d_ix_buckets.release(); h->d_ix_pos.release();
+    h->d_buckets.resize(nt); h->d_positions.resize(nt);
+    std::vector<TableD> tabs(nt);
+    for (size_t i = 0; ok && i < nt; i++) {
+      const HostTable& T = M.tables[i];
+      tabs[i].capacity = T.capacity; tabs[i].max_count = T.max_count; tabs[i].buckets = nullptr; tabs[i].positions = nullptr;
+      if (!T.buckets.empty()) {
+        ok = up(h->d_buckets[i], T.buckets.data(), T.buckets.size() * 8) && up(h->d_positions[i], T.positions.data(), T.positions.size() * 4);
+        tabs[i].buckets = (const uint64_t*)h->d_buckets[i].p; tabs[i].positions = (const uint32_t*)h->d_positions[i].p;
+      }
     }
+    ok = ok && up(h->d_tables, tabs.data(), nt * sizeof(TableD));
+    h->tables_host = tabs;
   }
-  ok = ok && up(h->d_tables, tabs.data(), nt * sizeof(TableD));
-  std::vector<int64_t> doff((size_t)M.n_contigs + 1, 0); std::vector<int32_t> dst;
-  for (int c = 0; c < M.n_contigs; c++) { if ((size_t)c < M.dup_starts.size()) dst.insert(dst.end(), M.dup_starts[(size_t)c].begin(), M.dup_starts[(size_t)c].end()); doff[(size_t)c + 1] = (int64_t)dst.size(); }
-  dst.push_back(0);
-  ok = ok && up(h->d_dup_off, doff.data(), doff.size() * 8) && up(h->d_dup_starts, dst.data(), dst.size() * 4);
+  if (ok) {   // the duplication table (small; re-uploaded on its own when only it changed)
+    std::vector<int64_t> doff((size_t)M.n_contigs + 1, 0); std::vector<int32_t> dst;
+    for (int c = 0; c < M.n_contigs; c++) { if ((size_t)c < M.dup_starts.size()) dst.insert(dst.end(), M.dup_starts[(size_t)c].begin(), M.dup_starts[(size_t)c].end()); doff[(size_t)c + 1] = (int64_t)dst.size(); }
+    dst.push_back(0);
+    ok = up(h->d_dup_off, doff.data(), doff.size() * 8) && up(h->d_dup_starts, dst.data(), dst.size() * 4);
+  }
   if (!ok) { h->err = std::string("device upload failed: ") + cudaGetErrorString(cudaGetLastError()); return XM_ERR_CUDA; }
   h->ref.n_contigs = M.n_contigs; h->ref.words = (const uint16_t*)h->d_words.p; h->ref.word_off = (const int64_t*)h->d_word_off.p;
   h->ref.len = (const int32_t*)h->d_len.p; h->ref.gstart = (const int64_t*)h->d_gstart.p; h->ref.total_fr = M.total_fr;
   h->ix.min_interesting = M.min_interesting; h->ix.max_built = M.max_built; h->ix.gapmers = M.gapmers; h->ix.tables = (const TableD*)h->d_tables.p;
   h->dup.window = M.dup_window; h->dup.granularity = M.dup_granularity; h->dup.off = (const int64_t*)h->d_dup_off.p; h->dup.starts = (const int32_t*)h->d_dup_starts.p;
-  h->mirrored_generation = M.generation;
+  h->mirrored_generation = M.generation; h->mirrored_dup_generation = M.dup_generation;
+  return XM_OK;
+}
+
+// ---- duplication detector, first half on the device (M/DuplicationDetector.java:129-214) ----
+// xm_dup_scan_kernel walks the buckets of one table: lanes test 32 bucket words at a time, and every bucket that holds at least
+// min_copies positions (and is not overfull) is then grouped by the whole warp - lookupByForwardHash :41-52 lists every stored
+// position plus its reverse complement, the blocks are grouped by their text (first and last ceil(length / 4) bases, blocks with an
+// ambiguous base dropped), and every block of a group of >= min_copies distinct (sequence, start) pairs is a duplication.  The
+// forward-strand ones are appended to `recs`; HostModel::merge_duplications applies saveDuplications' order-dependent containment
+// rule to them (a std::map walk per block, the part that stays on the host).
+struct DupItem { unsigned long long klo, khi; int32_t sid, st; };   // sid < 0: not a member (ambiguous text, or an image that repeats a stored position)
+struct DupScanD {
+  RefD ref; TableD t; int bl, min_copies, prefix;
+  char* scratch; long long scratch_stride;   // per warp: 2 * max_count items
+  HostModel::DupRecH* recs; unsigned long long cap; unsigned long long* n_recs;
+};
+__global__ void __launch_bounds__(128) xm_dup_scan_kernel(DupScanD D) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  DupItem* items = (DupItem*)(D.scratch + warp * D.scratch_stride);
+  for (long long base = warp * 32; base < D.t.capacity; base += n_warps * 32) {
+    const long long my = base + lane;
+    unsigned long long word = 0;
+    if (my < D.t.capacity) word = D.t.buckets[my];
+    const bool want = !((word >> 16) & 1) && (int)(word & 0xFFFF) >= D.min_copies;
+    unsigned todo = __ballot_sync(0xffffffffu, want);
+    while (todo) {
+      const int src = __ffs(todo) - 1; todo &= todo - 1;
+      const unsigned long long wd = __shfl_sync(0xffffffffu, word, src);
+      const int c = (int)(wd & 0xFFFF), n = 2 * c;
+      const uint32_t* pos = D.t.positions + (wd >> 24);
+      for (int k = lane; k < n; k += 32) {
+        const long long g = pos[k % c];
+        int sid, st; D.ref.decode(g, sid, st);
+        bool out = false;
+        if (k >= c) {   // the reverse complement of a stored block; a set: dropped when that block is itself stored in this bucket
+          sid ^= 1; st = D.ref.len[sid >> 1] - st - D.bl;
+          const long long gi = D.ref.gstart[sid] + st;
+          for (int x = 0; x < c && !out; x++) out = (long long)pos[x] == gi;
+        }
+        const SeqView v = D.ref.contig(sid >> 1, sid & 1);
+        unsigned long long klo = 0, khi = 0;
+        for (int i = 0; i < D.prefix; i++) {
+          const unsigned a = v.at(st + i), b = v.at(st + D.bl - D.prefix + i);
+          out |= bp_is_ambiguous((uint8_t)a) || bp_is_ambiguous((uint8_t)b);
+          klo = (klo << 4) | a; khi = (khi << 4) | b;
+        }
+        DupItem it; it.klo = klo; it.khi = khi; it.sid = out ? -1 : sid; it.st = st;
+        items[k] = it;
+      }
+      __syncwarp();
+      for (int ib = 0; ib < n; ib += 32) {
+        const int i = ib + lane;
+        DupItem me; me.sid = -1; me.klo = 0; me.khi = 0; me.st = 0;
+        if (i < n) me = items[i];
+        int count = 0;
+        for (int j = 0; j < n; j++) { const DupItem o = items[j]; count += (o.sid >= 0 && o.klo == me.klo && o.khi == me.khi) ? 1 : 0; }
+        const bool emit = me.sid >= 0 && !(me.sid & 1) && count >= D.min_copies;
+        const unsigned em = __ballot_sync(0xffffffffu, emit);
+        if (em) {
+          unsigned long long at = 0;
+          if (lane == 0) at = atomicAdd(D.n_recs, (unsigned long long)__popc(em));
+          at = __shfl_sync(0xffffffffu, at, 0) + __popc(em & lt_mask);
+          if (emit && at < D.cap) { HostModel::DupRecH r; r.contig = me.sid >> 1; r.st = me.st; r.count_len = count | (D.bl << 24); r.hc = (int32_t)(base + src); D.recs[at] = r; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+static int build_duplications_device(xm_handle* h, int min_len, int max_len, int min_copies, int window) {
+  HostModel& M = h->m;
+  if (min_len < 0) min_len = M.choose_min_dup_len();
+  if (max_len < 0) max_len = 2 * M.choose_min_dup_len();
+  if (max_len > M.max_built) max_len = M.max_built;
+  if (max_len > 64) { h->err = "xm_build_duplications: block lengths above 64 are not supported by the device scan (128-bit text keys); xm_build_duplications_host takes any length"; return XM_ERR_ARG; }
+  if (min_copies < 1) min_copies = 1;
+  const bool trace = getenv("XM_TRACE_SETUP") != nullptr;
+  auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = now();
+  if (int rc = mirror_model(h)) return rc;
+  const double t_mirror = now();
+  cudaStream_t st = h->stream;
+  const int blocks = h->sm_count * 8, warps = blocks * 4;
+  int max_items = 2;
+  for (int bl = std::max(1, min_len); bl <= max_len; bl++) max_items = std::max(max_items, 2 * h->tables_host[(size_t)bl].max_count);
+  DevBuf d_scratch, d_recs, d_n;
+  struct Free { std::vector<DevBuf*> v; ~Free() { for (DevBuf* b : v) b->release(); } } fr;
+  fr.v = {&d_scratch, &d_recs, &d_n};
+  DupScanD D; D.ref = h->ref; D.min_copies = min_copies;
+  D.scratch_stride = (((long long)max_items * (long long)sizeof(DupItem)) + 255) & ~255LL;
+  if (!d_scratch.ensure((size_t)warps * (size_t)D.scratch_stride) || !d_n.ensure(16)) { h->err = "out of device memory (duplication scan)"; return XM_ERR_CUDA; }
+  D.scratch = (char*)d_scratch.p; D.n_recs = (unsigned long long*)d_n.p;
+  unsigned long long cap = 1ull << 20, found = 0;
+  std::vector<HostModel::DupRecH> recs;
+  for (int attempt = 0; attempt < 2; attempt++) {   // second attempt: the buffer sized by the first one's count
+    if (!d_recs.ensure((size_t)cap * sizeof(HostModel::DupRecH))) { h->err = "out of device memory (duplication records)"; return XM_ERR_CUDA; }
+    D.recs = (HostModel::DupRecH*)d_recs.p; D.cap = cap;
+    CK(cudaMemsetAsync(d_n.p, 0, 16, st));
+    for (int bl = std::max(1, min_len); bl <= max_len; bl++) {
+      const TableD& T = h->tables_host[(size_t)bl];
+      if (T.buckets == nullptr) continue;
+      D.t = T; D.bl = bl; D.prefix = (bl + 3) / 4;
+      xm_dup_scan_kernel<<<blocks, 128, 0, st>>>(D);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&found, d_n.p, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (found <= cap) break;
+    cap = found;
+  }
+  const double t_scan = now();
+  recs.resize((size_t)found);
+  if (found) CK(cudaMemcpy(recs.data(), d_recs.p, (size_t)found * sizeof(HostModel::DupRecH), cudaMemcpyDeviceToHost));
+  M.merge_duplications(recs, min_len, window);
+  if (trace) fprintf(stderr, "[xm] duplications: mirror %.3f s, device scan of lengths %d..%d %.3f s (%llu blocks found), merge %.3f s\n", t_mirror - t_begin, min_len, max_len, t_scan - t_mirror, found, now() - t_scan);
   return XM_OK;
 }
 
@@ -1014,7 +1141,7 @@ void xm_destroy(xm_handle* h) {
     if (sl.copy) cudaStreamDestroy(sl.copy);
     for (cudaEvent_t e : {sl.h2d_done, sl.kernels_done, sl.ev0, sl.ev1}) if (e) cudaEventDestroy(e);
   }
-  DevBuf* bufs[] = {&h->d_words, &h->d_word_off, &h->d_len, &h->d_gstart, &h->d_tables, &h->d_dup_off, &h->d_dup_starts, &h->d_chunk, &h->d_q, &h->d_choices, &h->d_sas, &h->d_blocks,
+  DevBuf* bufs[] = {&h->d_ix_buckets, &h->d_ix_pos, &h->d_words, &h->d_word_off, &h->d_len, &h->d_gstart, &h->d_tables, &h->d_dup_off, &h->d_dup_starts, &h->d_chunk, &h->d_q, &h->d_choices, &h->d_sas, &h->d_blocks,
                     &h->d_misc, &h->d_ids_a, &h->d_ids_b, &h->d_ids_full, &h->d_ws, &h->d_qcycles, &h->d_csr_cnt, &h->d_csr_base, &h->d_csr_tmp, &h->d_keys_a, &h->d_keys_b, &h->d_sort_tmp, &h->d_big, &h->d_big_busy, &h->d_sam_len, &h->d_sam_text, &h->d_sam_names, &h->d_sam_name_off, &h->d_sam_cnames, &h->d_sam_cname_off, &h->d_svc, &h->d_planes, &h->d_contig_off, &h->d_var, &h->d_var_n, &h->d_order, &h->d_var_sizes,
                     &h->var_scratch.keys_a, &h->var_scratch.keys_b, &h->var_scratch.idx_a, &h->var_scratch.idx_b, &h->var_scratch.gathered, &h->var_scratch.out_keys, &h->var_scratch.n_out, &h->var_scratch.tmp};
   for (DevBuf* b : bufs) b->release();
@@ -1125,6 +1252,7 @@ static int build_index_device(xm_handle* h, int max_used) {
   unsigned long long E = cnt_host[0];
   if (const int fs = (int)(cnt_host[4] & 0xffffffffu)) { h->err = "xm_build_index: MultiHashBlock expansion of the reference ran out of workspace (status " + std::to_string(fs) + "); raise XM_INDEX_AMB_ARENA_MB or use the host builder (n_threads > 0)"; return XM_ERR_ARG; }
   M.tables.assign((size_t)hi + 1, HostTable());
+  std::vector<long long> tab_bbase((size_t)hi + 2, 0), tab_koff((size_t)hi + 2, 0);
   if (E >= (1ull << 31)) { h->err = "xm_build_index: more than 2^31 index entries"; return XM_ERR_ARG; }
   if (E > 0) {
     if (!d_keys_a.ensure(E * 8) || !d_keys_b.ensure(E * 8) || !d_vals_a.ensure(E * 4) || !d_vals_b.ensure(E * 4)) { h->err = "out of device memory (index entries)"; return XM_ERR_CUDA; }
@@ -1183,6 +1311,7 @@ static int build_index_device(xm_handle* h, int max_used) {
     long long words = 0;
     for (int k = 0; k <= hi; k++) { bbase[(size_t)k] = words; if (first[(size_t)k + 1] > first[(size_t)k]) words += cap[(size_t)k]; }
     const long long n_pos = koff[(size_t)hi + 1];
+    tab_bbase = bbase; tab_koff = koff;
     if (!up(d_bbase, bbase.data(), bbase.size() * 8) || !d_buckets.ensure((size_t)words * 8 + 16) || !d_pos.ensure((size_t)n_pos * 4 + 16)) { h->err = "out of device memory (index tables)"; return XM_ERR_CUDA; }
     IndexFillD F;
     F.run_key = (const unsigned long long*)d_run_key.p; F.run_cnt = (const int*)d_run_cnt.p; F.run_start = run_start; F.kept_off = kept_off; F.n_runs = n_runs;
@@ -1203,6 +1332,20 @@ static int build_index_device(xm_handle* h, int max_used) {
     }
   }
   M.max_built = hi; M.index_finished = true; M.generation++;
+  // the tables stay where the fill kernel wrote them: the device view is current, nothing is uploaded again
+  for (auto& b : h->d_buckets) b.release();
+  for (auto& b : h->d_positions) b.release();
+  h->d_ix_buckets.release(); h->d_ix_pos.release();
+  std::swap(h->d_ix_buckets, d_buckets); std::swap(h->d_ix_pos, d_pos);
+  std::vector<TableD> tabs((size_t)hi + 1);
+  for (int k = 0; k <= hi; k++) {
+    const HostTable& T = M.tables[(size_t)k];
+    tabs[(size_t)k].capacity = T.capacity; tabs[(size_t)k].max_count = T.max_count; tabs[(size_t)k].buckets = nullptr; tabs[(size_t)k].positions = nullptr;
+    if (!T.buckets.empty()) { tabs[(size_t)k].buckets = (const uint64_t*)h->d_ix_buckets.p + tab_bbase[(size_t)k]; tabs[(size_t)k].positions = (const uint32_t*)h->d_ix_pos.p + tab_koff[(size_t)k]; }
+  }
+  if (!up(h->d_tables, tabs.data(), tabs.size() * sizeof(TableD))) { h->err = "device upload failed (index tables)"; return XM_ERR_CUDA; }
+  h->tables_host = tabs;
+  h->mirrored_generation = M.generation; h->mirrored_dup_generation = ~0ull;   // mirror_model still uploads the duplication table and sets the views
   return XM_OK;
 }
 
@@ -1230,6 +1373,13 @@ int xm_set_duplications(xm_handle* h, int32_t window, double granularity, int32_
   return XM_OK;
 }
 int xm_build_duplications(xm_handle* h, int32_t min_len, int32_t max_len, int32_t min_copies, int32_t window) {
+  if (!h || window < 1) return XM_ERR_ARG;
+  std::lock_guard<std::mutex> compute(h->compute_mu);
+  if (!h->m.index_finished) { h->err = "index not set"; return XM_ERR_STATE; }
+  CK(cudaSetDevice(h->device));
+  return build_duplications_device(h, min_len, max_len, min_copies, window);
+}
+int xm_build_duplications_host(xm_handle* h, int32_t min_len, int32_t max_len, int32_t min_copies, int32_t window) {
   if (!h || window < 1) return XM_ERR_ARG;
   std::lock_guard<std::mutex> compute(h->compute_mu);
   if (!h->m.index_finished) { h->err = "index not set"; return XM_ERR_STATE; }

@@ -45,6 +45,7 @@ struct HostModel {
   int dup_window = 1; double dup_granularity = 1;
   std::vector<std::vector<int32_t>> dup_starts;
   bool dup_set = false;
+  uint64_t dup_generation = 0;   // bumped by changes of the duplication table alone (mirror_model re-uploads only that)
   uint64_t generation = 0;  // bumped on every change so the device mirror knows to refresh
 
   SeqView contig_view(int c, int rc) const { SeqView v; v.w = words.data() + word_off[c]; v.len = len[c]; v.rc = rc; v.bytes = nullptr; return v; }
@@ -65,7 +66,7 @@ struct HostModel {
     for (int c = 0; c < n; c++) { gstart[2 * c] = g; g += lengths[c]; gstart[2 * c + 1] = g; g += lengths[c]; }
     gstart[2 * (size_t)n] = g; total_fr = g;
     for (int c = 0; c < n && !ref_ambiguous; c++) { SeqView v = contig_view(c, 0); for (int i = 0; i < v.len; i++) if (bp_is_ambiguous(v.at(i))) { ref_ambiguous = true; break; } }
-    tables.clear(); max_built = 0; index_finished = false; dup_starts.assign(n, {}); dup_set = false;
+    tables.clear(); max_built = 0; index_finished = false; dup_starts.assign(n, {}); dup_set = false; dup_generation++;
     generation++;
   }
 
@@ -308,29 +309,84 @@ struct HostModel {
     if (window > 1) { int cd = d1.count - d2.count; if (cd != 0) return cd; if (s1 != s2) return s1 - s2; }
     return 0;
   }
-  void build_duplications(int min_len, int max_len, int min_copies, int window) {
+  // saveDuplications :332-400 for one block: the map keeps, per window, the blocks that contain no other block
+  static void dup_insert(std::map<int, Dup>& m, int window, int ds, const Dup& nd) {
+    bool insert = true;
+    while (true) {
+      auto it = m.upper_bound(ds);
+      if (it != m.begin()) { --it; int c = compare_dups(window, ds, nd, it->first, it->second); if (c > 0) { insert = false; break; } if (c < 0) { m.erase(it); continue; } }
+      break;
+    }
+    while (true) {
+      auto it = m.lower_bound(ds);
+      if (it != m.end()) { int c = compare_dups(window, ds, nd, it->first, it->second); if (c > 0) { insert = false; break; } if (c < 0) { m.erase(it); continue; } }
+      break;
+    }
+    if (insert) m[ds] = nd;
+  }
+  // The second half of the detector for blocks found by the device scan (xm_capi.cu: xm_dup_scan_kernel): `recs` are the forward-strand
+  // blocks of every length, (length, hashcode, contig, start, count); they are merged in the reference's order - lengths ascending,
+  // saveDuplications once per 10000 hashcodes, sequences and starts ascending within such a chunk, the last hashcode winning when a
+  // chunk names a start twice.  Only forward-strand maps are kept: the table that is handed out (dup_starts) never reads the others.
+  struct DupRecH { int32_t contig, st, count_len, hc; };   // count_len = count | length << 24
+  void merge_duplications(std::vector<DupRecH>& recs, int min_len, int window) {
+    dup_window = window; dup_granularity = gapmers ? (double)(min_len * 5 / 8) : (double)min_len;  // :67-77
+    const int chunk_len = 10000;
+    // Units that cannot interact are merged by different threads: contigs, and - when window > 1, where compareDuplications :406-436
+    // only relates blocks of one window - stretches of whole windows within a contig.
+    const long long seg = window > 1 ? (long long)window * ((1000000 + window - 1) / window) : (1LL << 40);
+    std::vector<long long> unit_base((size_t)n_contigs + 1, 0);
+    for (int c = 0; c < n_contigs; c++) unit_base[(size_t)c + 1] = unit_base[(size_t)c] + ((long long)len[(size_t)c] + seg - 1) / seg + 1;
+    const size_t n_units = (size_t)unit_base[(size_t)n_contigs];
+    auto unit_of = [&](const DupRecH& r) { return (size_t)(unit_base[(size_t)r.contig] + (long long)r.st / seg); };
+    std::vector<size_t> first(n_units + 1, 0);
+    for (const DupRecH& r : recs) first[unit_of(r) + 1]++;
+    for (size_t u = 0; u < n_units; u++) first[u + 1] += first[u];
+    std::vector<DupRecH> by_unit(recs.size());
+    { std::vector<size_t> at(first.begin(), first.end() - 1); for (const DupRecH& r : recs) by_unit[at[unit_of(r)]++] = r; }
+    std::vector<std::vector<int32_t>> unit_starts(n_units);
+    std::atomic<size_t> next(0);
+    auto work = [&]() {
+      while (true) {
+        const size_t u = next.fetch_add(1);
+        if (u >= n_units) break;
+        DupRecH* lo = by_unit.data() + first[u]; DupRecH* hi = by_unit.data() + first[u + 1];
+        if (lo == hi) continue;
+        std::sort(lo, hi, [&](const DupRecH& a, const DupRecH& b) {
+          const int la = a.count_len >> 24, lb = b.count_len >> 24;
+          if (la != lb) return la < lb;
+          const int ca = a.hc / chunk_len, cb = b.hc / chunk_len;
+          if (ca != cb) return ca < cb;
+          if (a.st != b.st) return a.st < b.st;
+          return a.hc < b.hc;
+        });
+        std::map<int, Dup> m;
+        for (DupRecH* r = lo; r < hi; r++) {
+          if (r + 1 < hi) { const DupRecH& x = r[1]; if ((x.count_len >> 24) == (r->count_len >> 24) && x.hc / chunk_len == r->hc / chunk_len && x.st == r->st) continue; }
+          dup_insert(m, window, r->st, Dup{r->count_len >> 24, r->count_len & 0xFFFFFF});
+        }
+        for (auto& e : m) unit_starts[u].push_back(e.first);
+      }
+    };
+    unsigned hw = std::thread::hardware_concurrency();
+    const int n_thr = (int)std::max<size_t>(1, std::min<size_t>(std::min(hw ? hw : 1u, 32u), recs.size() / 4096 + 1));
+    if (n_thr == 1) work();
+    else { std::vector<std::thread> th; for (int t = 0; t < n_thr; t++) th.emplace_back(work); for (auto& x : th) x.join(); }
+    dup_starts.assign((size_t)n_contigs, {});
+    for (int c = 0; c < n_contigs; c++)
+      for (long long u = unit_base[(size_t)c]; u < unit_base[(size_t)c + 1]; u++) dup_starts[(size_t)c].insert(dup_starts[(size_t)c].end(), unit_starts[(size_t)u].begin(), unit_starts[(size_t)u].end());
+    dup_set = true; dup_generation++;
+  }
+  // via_merge: the blocks this scan finds go through merge_duplications (the path the device scan feeds) instead of the maps below -
+  // how the CPU tests check that routine against this one
+  void build_duplications(int min_len, int max_len, int min_copies, int window, bool via_merge = false) {
+    std::vector<DupRecH> merge_recs;
     if (min_len < 0) min_len = choose_min_dup_len();
     if (max_len < 0) max_len = 2 * choose_min_dup_len();
     dup_window = window; dup_granularity = gapmers ? (double)(min_len * 5 / 8) : (double)min_len;  // :67-77
     std::vector<std::map<int, Dup>> all((size_t)2 * n_contigs);  // per sequence id
     auto save = [&](std::map<int, std::map<int, Dup>>& blocks) {
-      for (auto& e : blocks) {
-        auto& m = all[(size_t)e.first];
-        for (auto& pos : e.second) {
-          int ds = pos.first; const Dup& nd = pos.second; bool insert = true;
-          while (true) {
-            auto it = m.upper_bound(ds);
-            if (it != m.begin()) { --it; int c = compare_dups(window, ds, nd, it->first, it->second); if (c > 0) { insert = false; break; } if (c < 0) { m.erase(it); continue; } }
-            break;
-          }
-          while (true) {
-            auto it = m.lower_bound(ds);
-            if (it != m.end()) { int c = compare_dups(window, ds, nd, it->first, it->second); if (c > 0) { insert = false; break; } if (c < 0) { m.erase(it); continue; } }
-            break;
-          }
-          if (insert) m[ds] = nd;
-        }
-      }
+      for (auto& e : blocks) for (auto& pos : e.second) dup_insert(all[(size_t)e.first], window, pos.first, pos.second);
       blocks.clear();
     };
     // The per-bucket grouping (the expensive part) is independent across buckets: threads build the `blocks` of chunks of
@@ -377,17 +433,21 @@ struct HostModel {
         for (int t = 0; t < std::min(n_thr, n_chunks); t++) th.emplace_back([&]() { while (true) { int ci = next_chunk.fetch_add(1); if (ci >= n_chunks) break; scan_chunk(ci); } });
         for (auto& x : th) x.join();
       }
-      for (int ci = 0; ci < n_chunks; ci++) save(chunk_blocks[(size_t)ci]);
+      for (int ci = 0; ci < n_chunks; ci++) {
+        if (via_merge) { for (auto& e : chunk_blocks[(size_t)ci]) if (!(e.first & 1)) for (auto& pos : e.second) merge_recs.push_back({e.first >> 1, pos.first, pos.second.count | (bl << 24), ci * chunk_len}); }
+        else save(chunk_blocks[(size_t)ci]);
+      }
     }
+    if (via_merge) { merge_duplications(merge_recs, min_len, window); return; }
     dup_starts.assign((size_t)n_contigs, {});
     for (int c = 0; c < n_contigs; c++) for (auto& e : all[(size_t)2 * c]) dup_starts[(size_t)c].push_back(e.first);
-    dup_set = true; generation++;
+    dup_set = true; dup_generation++;
   }
   void set_duplications(int window, double granularity, int contig, int n, const int32_t* starts) {
     dup_window = window; dup_granularity = granularity;
     if ((int)dup_starts.size() < n_contigs) dup_starts.resize((size_t)n_contigs);
     dup_starts[(size_t)contig].assign(starts, starts + n);
-    dup_set = true; generation++;
+    dup_set = true; dup_generation++;
   }
 };
 

@@ -46,6 +46,7 @@ int xe_get_index_length(void* h, int n, int* cap, int* maxc, int64_t* npos, int6
 }
 int xe_set_duplications(void* h, int window, double gran, int contig, int n, const int32_t* starts) { ((Emu*)h)->m.set_duplications(window, gran, contig, n, starts); return 0; }
 int xe_build_duplications(void* h, int min_len, int max_len, int min_copies, int window) { ((Emu*)h)->m.build_duplications(min_len, max_len, min_copies, window); return 0; }
+int xe_build_duplications_via_merge(void* h, int min_len, int max_len, int min_copies, int window) { ((Emu*)h)->m.build_duplications(min_len, max_len, min_copies, window, true); return 0; }
 int xe_get_duplications(void* h, int contig, int* n, int32_t* starts) {
   Emu* e = (Emu*)h;
   auto& v = e->m.dup_starts[(size_t)contig];

@@ -73,6 +73,14 @@ def test_library_index_builder_matches_host_tables():
     emu.build_duplications(-1, -1, 2, 1000)
     for c in range(db.num_contigs()):
         assert np.array_equal(db.dup_starts(c), emu.get_duplications(c)), c
+    # the merge the device scan feeds (forward-strand blocks, units merged by different threads) gives the same table
+    for window, lo, hi, copies in ((1000, -1, -1, 2), (1, -1, -1, 2), (100, 12, 30, 3)):
+        emu.build_duplications(lo, hi, copies, window)
+        want = [emu.get_duplications(c).copy() for c in range(db.num_contigs())]
+        emu.build_duplications(lo, hi, copies, window, via_merge=True)
+        for c in range(db.num_contigs()):
+            assert np.array_equal(want[c], emu.get_duplications(c)), (window, c)
+        assert sum(len(w) for w in want) > 0
     emu.close()
 
 

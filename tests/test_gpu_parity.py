@@ -103,6 +103,42 @@ def test_library_index_builder_on_gpu_box(threads):
     g.close()
 
 
+@pytest.mark.parametrize("ambiguous", [False, True], ids=["plain", "anc"])
+def test_duplication_table_device_scan(ambiguous):
+    """xm_build_duplications (bucket scan on the device + the reference-ordered merge) == xm_build_duplications_host == the oracle's
+    DuplicationDetector (M/DuplicationDetector.java:129-214, :332-436), on a reference with 2-6-copy repeat families, for window sizes 1 and 1000 and explicit length ranges."""
+    ref = synth.random_reference(500000, seed=171, n_contigs=4, repeat_fraction=0.15, repeat_copies=(2, 6), repeat_len=(60, 2500))
+    if ambiguous:
+        db, changed = parity.inferred_ancestor_oracle(ref, synth.DEFAULT_PARAMS, threads=8)
+        assert changed > 100
+    else:
+        db = xo.Oracle([(n, synth.codes_to_text(s)) for n, s in ref], sort_by_length=True, threads=8, dup=dict(min_copies=2, window=1000))
+    g = capi.XMapper(synth.DEFAULT_PARAMS, device=0)
+    parity.feed_reference(g, db)
+    g.build_index(150)
+    db.detect_duplications()
+    total = 0
+    for window in (1000, 1):
+        g.build_duplications(-1, -1, 2, window)
+        dev = [g.get_duplications(c).copy() for c in range(db.num_contigs())]
+        g.build_duplications(-1, -1, 2, window, host=True)
+        for c in range(db.num_contigs()):
+            assert np.array_equal(dev[c], g.get_duplications(c)), (window, c)
+            if window == 1000:
+                assert np.array_equal(dev[c], db.dup_starts(c)), c
+            total += len(dev[c])
+    assert total > 200
+    for lo, hi, copies in ((12, 20, 3), (25, 64, 2)):
+        g.build_duplications(lo, hi, copies, 100)
+        dev = [g.get_duplications(c).copy() for c in range(db.num_contigs())]
+        g.build_duplications(lo, hi, copies, 100, host=True)
+        for c in range(db.num_contigs()):
+            assert np.array_equal(dev[c], g.get_duplications(c)), (lo, hi, c)
+    with pytest.raises(capi.XmError):
+        g.build_duplications(60, 80, 2, 100)   # above 64: the device scan says so instead of switching to the host detector
+    g.close()
+
+
 def test_long_reads_1kbp_split_shape():
     """BASELINE.json configs[4] shape: 1 kbp pieces (what --split-queries-past-size 1000 hands the aligner, M/SequenceSplitter.java:9-38)
     with 1 % substitutions + 0.5 % indels on a multi-contig reference with repeat families."""

@@ -106,8 +106,10 @@ class Emu:
             s = np.zeros(1, dtype=np.int32)
         self._ok(self.L.xe_set_duplications(C.c_void_p(self.h), window, C.c_double(granularity), contig, len(starts), s.ctypes.data_as(C.c_void_p)))
 
-    def build_duplications(self, min_len=-1, max_len=-1, min_copies=2, window=1000):
-        self._ok(self.L.xe_build_duplications(C.c_void_p(self.h), min_len, max_len, min_copies, window))
+    def build_duplications(self, min_len=-1, max_len=-1, min_copies=2, window=1000, via_merge=False):
+        """via_merge: the found blocks go through HostModel::merge_duplications, the routine the device scan feeds."""
+        f = self.L.xe_build_duplications_via_merge if via_merge else self.L.xe_build_duplications
+        self._ok(f(C.c_void_p(self.h), min_len, max_len, min_copies, window))
 
     def get_duplications(self, contig):
         n = C.c_int()
