@@ -63,7 +63,10 @@ const char* xm_last_error(const xm_handle* h);
 
 /* SequenceDatabase of the sorted reference (Mapper.sortAndComplementReference, Mapper.java:1151-1172; global
  * position space QV/SequenceDatabase.java:230-238): forward strands only, in database order; the reverse
- * complements are implicit (contig i occupies sequence ids 2i and 2i+1). */
+ * complements are implicit (contig i occupies sequence ids 2i and 2i+1).
+ * Global positions are as wide as the reference needs (QV/SequenceDatabase.java:69-74 sizes them by log2 of the forward + reverse
+ * size; KAT T/PackedMap_Test.testLargeReferenceSize): 32 bits while 2 x total length <= 2^32, otherwise 40 bits, stored on the
+ * device as a uint32 plane plus a uint8 plane so that the common case reads what it always read.  Limit: 2 x total < 2^40. */
 int xm_set_reference(xm_handle* h, int32_t n_contigs, const uint16_t* const* packed4, const int32_t* lengths);
 
 /* One PackedMap (PackedMap.java / QV/ByteKeyStore.java) per numBasepairsUsed, uploaded from the host's
@@ -72,6 +75,9 @@ int xm_set_reference(xm_handle* h, int32_t n_contigs, const uint16_t* const* pac
  * capacity == 1 with no positions is the empty PackedMap(1, 1, ...) of HashBlock_Database.java:383-389. */
 int xm_set_index_length(xm_handle* h, int32_t n_used, int32_t capacity, int32_t max_count, const int64_t* offsets,
                         const uint8_t* overfull, const uint32_t* positions);
+/* The same call for references whose positions need more than 32 bits (required then; accepted for any reference). */
+int xm_set_index_length_wide(xm_handle* h, int32_t n_used, int32_t capacity, int32_t max_count, const int64_t* offsets,
+                             const uint8_t* overfull, const uint64_t* positions);
 /* Declares HashBlock_Database.minInterestingSize (:51-55) and maxFullySetUpSize after all uploads. */
 int xm_finish_index(xm_handle* h, int32_t min_interesting_size, int32_t max_built);
 
@@ -86,6 +92,8 @@ int xm_build_index(xm_handle* h, int32_t max_used, int32_t n_threads);
 /* Reads back a table (for parity tests against the host's PackedMaps). Pass NULL arrays to query sizes. */
 int xm_get_index_length(xm_handle* h, int32_t n_used, int32_t* capacity, int32_t* max_count, int64_t* n_positions,
                         int64_t* offsets, uint8_t* overfull, uint32_t* positions);
+int xm_get_index_length_wide(xm_handle* h, int32_t n_used, int32_t* capacity, int32_t* max_count, int64_t* n_positions,
+                             int64_t* offsets, uint8_t* overfull, uint64_t* positions);
 int xm_index_info(xm_handle* h, int32_t* min_interesting_size, int32_t* max_built);
 
 /* Readable_DuplicationDetector table (Readable_DuplicationDetector.java:28-47): the sorted duplication start

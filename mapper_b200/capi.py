@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("XM_LIB_PATH") or os.path.join(HERE, "libxmapper_b200.so")  # XM_LIB_PATH: build-variant experiments
 
 EXPORTS = ["xm_create", "xm_destroy", "xm_last_error", "xm_set_reference", "xm_set_index_length", "xm_finish_index",
-           "xm_build_index", "xm_get_index_length", "xm_index_info", "xm_set_duplications", "xm_build_duplications", "xm_build_duplications_host",
+           "xm_set_index_length_wide", "xm_build_index", "xm_get_index_length", "xm_get_index_length_wide", "xm_index_info", "xm_set_duplications", "xm_build_duplications", "xm_build_duplications_host",
            "xm_get_duplications", "xm_align_batch", "xm_align_batch_device", "xm_results_array", "xm_release_results",
            "xm_counts_enable", "xm_counts_device_ptr", "xm_counts_fetch", "xm_format_sam",
            "xm_comm_unique_id", "xm_comm_init", "xm_counts_reduce", "xm_counts_batch_info", "xm_variants_fetch", "xm_measure_peaks", "xm_counts_reduce_times"]
@@ -124,13 +124,15 @@ class XMapper:
         self._ok(self.L.xm_set_reference(self.h, n, arr, _ptr(lens)))
         self.contig_lengths = [int(x) for x in lens]
 
-    def set_index_length(self, t):
+    def set_index_length(self, t, wide=False):
+        """wide: positions are uint64 (xm_set_index_length_wide; required when 2 x the reference size exceeds 2^32)."""
         off = np.ascontiguousarray(t["offsets"], dtype=np.int64)
         over = np.ascontiguousarray(t["overfull"], dtype=np.uint8)
-        pos = np.ascontiguousarray(t["positions"], dtype=np.uint32)
+        pos = np.ascontiguousarray(t["positions"], dtype=np.uint64 if wide else np.uint32)
         if len(pos) == 0:
-            pos = np.zeros(1, dtype=np.uint32)
-        self._ok(self.L.xm_set_index_length(self.h, int(t["used"]), int(t["capacity"]), int(t["max_count"]), _ptr(off), _ptr(over), _ptr(pos)))
+            pos = np.zeros(1, dtype=pos.dtype)
+        f = self.L.xm_set_index_length_wide if wide else self.L.xm_set_index_length
+        self._ok(f(self.h, int(t["used"]), int(t["capacity"]), int(t["max_count"]), _ptr(off), _ptr(over), _ptr(pos)))
 
     def finish_index(self, min_interesting, max_built):
         self._ok(self.L.xm_finish_index(self.h, int(min_interesting), int(max_built)))
@@ -144,13 +146,14 @@ class XMapper:
         self._ok(self.L.xm_index_info(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
-    def get_index_length(self, n):
+    def get_index_length(self, n, wide=False):
         cap, mx, npos = C.c_int32(), C.c_int32(), C.c_int64()
         self._ok(self.L.xm_get_index_length(self.h, n, C.byref(cap), C.byref(mx), C.byref(npos), None, None, None))
         off = np.zeros(cap.value + 1, dtype=np.int64)
         over = np.zeros(cap.value, dtype=np.uint8)
-        pos = np.zeros(max(npos.value, 1), dtype=np.uint32)
-        self._ok(self.L.xm_get_index_length(self.h, n, C.byref(cap), C.byref(mx), C.byref(npos), _ptr(off), _ptr(over), _ptr(pos)))
+        pos = np.zeros(max(npos.value, 1), dtype=np.uint64 if wide else np.uint32)
+        f = self.L.xm_get_index_length_wide if wide else self.L.xm_get_index_length
+        self._ok(f(self.h, n, C.byref(cap), C.byref(mx), C.byref(npos), _ptr(off), _ptr(over), _ptr(pos)))
         return dict(used=n, capacity=cap.value, max_count=mx.value, offsets=off, overfull=over, positions=pos[:npos.value])
 
     def index_length_size(self, n):

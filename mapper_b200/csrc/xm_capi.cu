@@ -359,7 +359,8 @@ struct IndexBuildD {
   int hi, min_interesting, gapmers;
   const int* cap;                      // hi + 1 capacities
   char* arenas; long long arena_bytes; // per warp: two level buffers
-  unsigned long long* keys; uint32_t* vals; unsigned long long cap_entries;
+  unsigned long long* keys; void* vals; int wide; unsigned long long cap_entries;   // vals: uint32 global positions, uint64 when the reference needs more than 32 bits (wide)
+  __device__ __forceinline__ void store_pos(unsigned long long o, long long g) const { if (wide) ((unsigned long long*)vals)[o] = (unsigned long long)g; else ((uint32_t*)vals)[o] = (uint32_t)g; }
   unsigned long long* n_entries; int* ticket; int* fail;
 };
 static const unsigned long long XM_IX_MULTI = 1ull << 63;   // key bit of a MultiHashBlock possibility: above the sorted bits, dropped by the de-duplication
@@ -446,8 +447,8 @@ __global__ void __launch_bounds__(128) xm_index_emit_kernel(IndexBuildD B) {
           at = __shfl_sync(0xffffffffu, at, 0);
           if (B.keys != nullptr && at + total <= B.cap_entries) {
             const int c = B.cap[(prim || sec) ? g.used : 0];
-            if (prim) { int r = g.fwd % c; if (r < 0) r += c; const unsigned long long o = at + __popc(pm & lt_mask); B.keys[o] = ((unsigned long long)g.used << 32) | (unsigned)r; B.vals[o] = (uint32_t)(g_fwd + g.start); }
-            if (sec) { int r = g.rev % c; if (r < 0) r += c; const unsigned long long o = at + __popc(pm) + __popc(sm & lt_mask); B.keys[o] = ((unsigned long long)g.used << 32) | (unsigned)r; B.vals[o] = (uint32_t)(g_rev + (seq.len - g.end())); }
+            if (prim) { int r = g.fwd % c; if (r < 0) r += c; const unsigned long long o = at + __popc(pm & lt_mask); B.keys[o] = ((unsigned long long)g.used << 32) | (unsigned)r; B.store_pos(o, g_fwd + g.start); }
+            if (sec) { int r = g.rev % c; if (r < 0) r += c; const unsigned long long o = at + __popc(pm) + __popc(sm & lt_mask); B.keys[o] = ((unsigned long long)g.used << 32) | (unsigned)r; B.store_pos(o, g_rev + (seq.len - g.end())); }
           }
         }
       }
@@ -544,8 +545,8 @@ __global__ void __launch_bounds__(32) xm_index_emit_amb_kernel(IndexBuildD B) {
             at = __shfl_sync(0xffffffffu, at, 0);
             if (B.keys != nullptr && at + total <= B.cap_entries) {
               const int cp = B.cap[(prim || sec) ? g.used : 0];
-              if (prim) { int r = g.fwd % cp; if (r < 0) r += cp; const unsigned long long o = at + __popc(pm & lt_mask); B.keys[o] = multi | ((unsigned long long)g.used << 32) | (unsigned)r; B.vals[o] = (uint32_t)(g_fwd + g.start); }
-              if (sec) { int r = g.rev % cp; if (r < 0) r += cp; const unsigned long long o = at + __popc(pm) + __popc(sm & lt_mask); B.keys[o] = multi | ((unsigned long long)g.used << 32) | (unsigned)r; B.vals[o] = (uint32_t)(g_rev + (full.len - g.end())); }
+              if (prim) { int r = g.fwd % cp; if (r < 0) r += cp; const unsigned long long o = at + __popc(pm & lt_mask); B.keys[o] = multi | ((unsigned long long)g.used << 32) | (unsigned)r; B.store_pos(o, g_fwd + g.start); }
+              if (sec) { int r = g.rev % cp; if (r < 0) r += cp; const unsigned long long o = at + __popc(pm) + __popc(sm & lt_mask); B.keys[o] = multi | ((unsigned long long)g.used << 32) | (unsigned)r; B.store_pos(o, g_rev + (full.len - g.end())); }
             }
           }
         }
@@ -556,12 +557,13 @@ __global__ void __launch_bounds__(32) xm_index_emit_amb_kernel(IndexBuildD B) {
 }
 // PackedMap.add(preventDuplicates) on the sorted entries: a multi-block possibility is dropped when the same (length, bucket,
 // position) was already added - by a plain block (which are never de-duplicated among themselves) or by another possibility.
-__global__ void xm_index_dedupe_kernel(const unsigned long long* keys, const uint32_t* vals, int n, unsigned char* keep) {
+template <typename PosT>
+__global__ void xm_index_dedupe_kernel(const unsigned long long* keys, const PosT* vals, int n, unsigned char* keep) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned long long k = keys[i];
   if (!(k & XM_IX_MULTI)) { keep[i] = 1; return; }
-  const unsigned long long km = k & ~XM_IX_MULTI; const uint32_t p = vals[i];
+  const unsigned long long km = k & ~XM_IX_MULTI; const PosT p = vals[i];
   bool drop = i > 0 && (keys[i - 1] & ~XM_IX_MULTI) == km && vals[i - 1] == p;
   for (int j = i + 1; !drop && j < n && (keys[j] & ~XM_IX_MULTI) == km && vals[j] == p; j++) drop = !(keys[j] & XM_IX_MULTI);
   keep[i] = drop ? 0 : 1;
@@ -584,12 +586,14 @@ __global__ void xm_index_first_run_kernel(const unsigned long long* run_key, int
   while (lo < h) { int mid = (lo + h) >> 1; if ((int)(run_key[mid] >> 32) < n) lo = mid + 1; else h = mid; }
   first_run[n] = lo;
 }
+template <typename PosT>
 struct IndexFillD {
   const unsigned long long* run_key; const int* run_cnt; const long long* run_start; const long long* kept_off; int n_runs;
   const int* first_run; const int* cap; const long long* bucket_base;   // per used: offset of its bucket words in `buckets`
-  const uint32_t* sorted_pos; unsigned long long* buckets; uint32_t* positions;  // positions: all lengths back to back, in kept_off order
+  const PosT* sorted_pos; unsigned long long* buckets; uint32_t* positions; uint8_t* positions_hi;  // positions: all lengths back to back, in kept_off order (low 32 bits; bits 32-39 in positions_hi when PosT is 64 bits wide)
 };
-__global__ void xm_index_fill_kernel(IndexFillD F) {
+template <typename PosT>
+__global__ void xm_index_fill_kernel(IndexFillD<PosT> F) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= F.n_runs) return;
   const int n = (int)(F.run_key[r] >> 32); const unsigned bucket = (unsigned)F.run_key[r];
@@ -607,7 +611,7 @@ __global__ void xm_index_fill_kernel(IndexFillD F) {
     const long long end_off = F.kept_off[r + 1] - base_n;
     for (unsigned b = bucket + 1; b < (unsigned)F.cap[n]; b++) bw[b] = ((unsigned long long)end_off << 24);
   }
-  if (!over) { const long long src = F.run_start[r], dst = F.kept_off[r]; for (int k = 0; k < cnt; k++) F.positions[dst + k] = F.sorted_pos[src + k]; }
+  if (!over) { const long long src = F.run_start[r], dst = F.kept_off[r]; for (int k = 0; k < cnt; k++) { const PosT v = F.sorted_pos[src + k]; F.positions[dst + k] = (uint32_t)v; if (sizeof(PosT) > 4) F.positions_hi[dst + k] = (uint8_t)((unsigned long long)v >> 32); } }
 }
 
 // ---- SAM bodies on the device (QV/SamWriter.java:118-352) ----
@@ -846,9 +850,9 @@ struct xm_handle {
   // device mirror of the model
   uint64_t mirrored_generation = ~0ull, mirrored_dup_generation = ~0ull;
   DevBuf d_words, d_word_off, d_len, d_gstart, d_tables, d_dup_off, d_dup_starts;
-  std::vector<DevBuf> d_buckets, d_positions;
+  std::vector<DevBuf> d_buckets, d_positions, d_positions_hi;
   std::vector<TableD> tables_host;   // host copy of the device table descriptors
-  DevBuf d_ix_buckets, d_ix_pos;     // tables the device index builder left in place (every length in one allocation)
+  DevBuf d_ix_buckets, d_ix_pos, d_ix_pos_hi;   // tables the device index builder left in place (every length in one allocation)
   RefD ref{}; IndexD ix{}; DupD dup{};
   // Batches in flight.  A call of xm_align_batch owns one slot from its first host->device copy to its last device->host copy: the
   // slot's staging buffers, its copy stream and its device copy of the result arrays.  The kernels of different calls run one after
@@ -923,15 +927,16 @@ static int mirror_model(xm_handle* h) {
          up(h->d_len, M.len.data(), M.len.size() * 4) && up(h->d_gstart, M.gstart.data(), M.gstart.size() * 8);
     size_t nt = (size_t)M.max_built + 1;
     if (M.tables.size() < nt) M.tables.resize(nt);
-    h->d_ix_buckets.release(); h->d_ix_pos.release();
-    h->d_buckets.resize(nt); h->d_positions.resize(nt);
+    h->d_ix_buckets.release(); h->d_ix_pos.release(); h->d_ix_pos_hi.release();
+    h->d_buckets.resize(nt); h->d_positions.resize(nt); h->d_positions_hi.resize(nt);
     std::vector<TableD> tabs(nt);
     for (size_t i = 0; ok && i < nt; i++) {
       const HostTable& T = M.tables[i];
-      tabs[i].capacity = T.capacity; tabs[i].max_count = T.max_count; tabs[i].buckets = nullptr; tabs[i].positions = nullptr;
+      tabs[i].capacity = T.capacity; tabs[i].max_count = T.max_count; tabs[i].buckets = nullptr; tabs[i].positions = nullptr; tabs[i].positions_hi = nullptr;
       if (!T.buckets.empty()) {
         ok = up(h->d_buckets[i], T.buckets.data(), T.buckets.size() * 8) && up(h->d_positions[i], T.positions.data(), T.positions.size() * 4);
         tabs[i].buckets = (const uint64_t*)h->d_buckets[i].p; tabs[i].positions = (const uint32_t*)h->d_positions[i].p;
+        if (ok && !T.positions_hi.empty()) { ok = up(h->d_positions_hi[i], T.positions_hi.data(), T.positions_hi.size()); tabs[i].positions_hi = (const uint8_t*)h->d_positions_hi[i].p; }
       }
     }
     ok = ok && up(h->d_tables, tabs.data(), nt * sizeof(TableD));
@@ -981,15 +986,15 @@ __global__ void __launch_bounds__(128) xm_dup_scan_kernel(DupScanD D) {
       const int src = __ffs(todo) - 1; todo &= todo - 1;
       const unsigned long long wd = __shfl_sync(0xffffffffu, word, src);
       const int c = (int)(wd & 0xFFFF), n = 2 * c;
-      const uint32_t* pos = D.t.positions + (wd >> 24);
+      const long long pos0 = (long long)(wd >> 24);
       for (int k = lane; k < n; k += 32) {
-        const long long g = pos[k % c];
+        const long long g = D.t.position(pos0 + k % c);
         int sid, st; D.ref.decode(g, sid, st);
         bool out = false;
         if (k >= c) {   // the reverse complement of a stored block; a set: dropped when that block is itself stored in this bucket
           sid ^= 1; st = D.ref.len[sid >> 1] - st - D.bl;
           const long long gi = D.ref.gstart[sid] + st;
-          for (int x = 0; x < c && !out; x++) out = (long long)pos[x] == gi;
+          for (int x = 0; x < c && !out; x++) out = D.t.position(pos0 + x) == gi;
         }
         const SeqView v = D.ref.contig(sid >> 1, sid & 1);
         unsigned long long klo = 0, khi = 0;
@@ -1141,12 +1146,13 @@ void xm_destroy(xm_handle* h) {
     if (sl.copy) cudaStreamDestroy(sl.copy);
     for (cudaEvent_t e : {sl.h2d_done, sl.kernels_done, sl.ev0, sl.ev1}) if (e) cudaEventDestroy(e);
   }
-  DevBuf* bufs[] = {&h->d_ix_buckets, &h->d_ix_pos, &h->d_words, &h->d_word_off, &h->d_len, &h->d_gstart, &h->d_tables, &h->d_dup_off, &h->d_dup_starts, &h->d_chunk, &h->d_q, &h->d_choices, &h->d_sas, &h->d_blocks,
+  DevBuf* bufs[] = {&h->d_ix_buckets, &h->d_ix_pos, &h->d_ix_pos_hi, &h->d_words, &h->d_word_off, &h->d_len, &h->d_gstart, &h->d_tables, &h->d_dup_off, &h->d_dup_starts, &h->d_chunk, &h->d_q, &h->d_choices, &h->d_sas, &h->d_blocks,
                     &h->d_misc, &h->d_ids_a, &h->d_ids_b, &h->d_ids_full, &h->d_ws, &h->d_qcycles, &h->d_csr_cnt, &h->d_csr_base, &h->d_csr_tmp, &h->d_keys_a, &h->d_keys_b, &h->d_sort_tmp, &h->d_big, &h->d_big_busy, &h->d_sam_len, &h->d_sam_text, &h->d_sam_names, &h->d_sam_name_off, &h->d_sam_cnames, &h->d_sam_cname_off, &h->d_svc, &h->d_planes, &h->d_contig_off, &h->d_var, &h->d_var_n, &h->d_order, &h->d_var_sizes,
                     &h->var_scratch.keys_a, &h->var_scratch.keys_b, &h->var_scratch.idx_a, &h->var_scratch.idx_b, &h->var_scratch.gathered, &h->var_scratch.out_keys, &h->var_scratch.n_out, &h->var_scratch.tmp};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : h->d_buckets) b.release();
   for (auto& b : h->d_positions) b.release();
+  for (auto& b : h->d_positions_hi) b.release();
   if (h->stream) cudaStreamDestroy(h->stream);
   for (cudaEvent_t e : {h->ev2, h->ev3, h->ev4, h->ev5}) if (e) cudaEventDestroy(e);
   delete h;
@@ -1158,7 +1164,11 @@ int xm_set_reference(xm_handle* h, int32_t n, const uint16_t* const* packed4, co
   std::lock_guard<std::mutex> compute(h->compute_mu);
   long long total = 0;
   for (int i = 0; i < n; i++) { if (lengths[i] < 1) { h->err = "contig of length < 1"; return XM_ERR_ARG; } total += lengths[i]; }
-  if (2 * total >= (1LL << 32)) { h->err = "reference too large for 32-bit global positions"; return XM_ERR_ARG; }
+  // XM_POSITION_BIAS (tests): global position of the first contig, as if a reference of that many bases preceded it - moves every
+  // index position past 2^32 without a multi-gigabase reference in memory
+  long long bias = 0; if (const char* e = getenv("XM_POSITION_BIAS")) bias = atoll(e);
+  if (bias < 0 || bias + 2 * total >= (1LL << 40)) { h->err = "reference too large for 40-bit global positions"; return XM_ERR_ARG; }
+  h->m.position_bias = bias;
   h->m.set_reference(n, packed4, lengths);
   h->counts_enabled = false;
   return XM_OK;
@@ -1174,7 +1184,23 @@ int xm_set_index_length(xm_handle* h, int32_t n_used, int32_t capacity, int32_t 
   }
   if (offsets[capacity] >= (1LL << 40)) { h->err = "xm_set_index_length: more than 2^40 positions"; return XM_ERR_ARG; }
   if (offsets[capacity] > 0 && !positions) return XM_ERR_ARG;
+  if (h->m.wide_positions()) { h->err = "xm_set_index_length: the reference needs more than 32 bits per position - use xm_set_index_length_wide"; return XM_ERR_ARG; }
   h->m.set_index_length(n_used, capacity, max_count, offsets, overfull, positions);
+  return XM_OK;
+}
+int xm_set_index_length_wide(xm_handle* h, int32_t n_used, int32_t capacity, int32_t max_count, const int64_t* offsets, const uint8_t* overfull, const uint64_t* positions) {
+  if (!h || n_used < 0 || capacity < 1 || !offsets) return XM_ERR_ARG;
+  if (max_count > 32766) { h->err = "max_count > 32766"; return XM_ERR_ARG; }
+  if (offsets[0] != 0) { h->err = "xm_set_index_length_wide: offsets[0] != 0"; return XM_ERR_ARG; }
+  for (int32_t b = 0; b < capacity; b++) {
+    const int64_t cnt = offsets[b + 1] - offsets[b];
+    if (cnt < 0) { h->err = "xm_set_index_length_wide: offsets are not non-decreasing"; return XM_ERR_ARG; }
+    if (cnt > 65535 || (cnt > max_count && !(overfull && overfull[b]))) { h->err = "xm_set_index_length_wide: a bucket that is not overfull holds more than max_count positions"; return XM_ERR_ARG; }
+  }
+  if (offsets[capacity] >= (1LL << 40)) { h->err = "xm_set_index_length_wide: more than 2^40 positions"; return XM_ERR_ARG; }
+  if (offsets[capacity] > 0 && !positions) return XM_ERR_ARG;
+  for (int64_t i = 0; i < offsets[capacity]; i++) if (positions[i] >= (uint64_t)h->m.position_end) { h->err = "xm_set_index_length_wide: a position lies past the end of the reference"; return XM_ERR_ARG; }
+  h->m.set_index_length(n_used, capacity, max_count, offsets, overfull, positions, true);
   return XM_OK;
 }
 int xm_finish_index(xm_handle* h, int32_t min_interesting, int32_t max_built) {
@@ -1209,10 +1235,10 @@ static int build_index_device(xm_handle* h, int max_used) {
   }
   const int n_amb = (int)amb_sc.size();
   if (n_amb && slice_len + 4 * hi + 256 > 32000) { h->err = "xm_build_index: hash lengths this long are not supported on IUPAC-ambiguous references (16-bit window coordinates)"; return XM_ERR_ARG; }
-  DevBuf d_amb_sc, d_amb_ss, d_amb_arena, d_keep;
+  DevBuf d_amb_sc, d_amb_ss, d_amb_arena, d_keep, d_pos_hi;
   DevBuf d_sc, d_ss, d_cap, d_cnt, d_keys_a, d_keys_b, d_vals_a, d_vals_b, d_tmp, d_run_key, d_run_cnt, d_nruns, d_cnt64, d_kept, d_first, d_bbase, d_buckets, d_pos;
   struct Free { std::vector<DevBuf*> v; ~Free() { for (DevBuf* b : v) b->release(); } } fr;
-  fr.v = {&d_amb_sc, &d_amb_ss, &d_amb_arena, &d_keep, &d_sc, &d_ss, &d_cap, &d_cnt, &d_keys_a, &d_keys_b, &d_vals_a, &d_vals_b, &d_tmp, &d_run_key, &d_run_cnt, &d_nruns, &d_cnt64, &d_kept, &d_first, &d_bbase, &d_buckets, &d_pos};
+  fr.v = {&d_amb_sc, &d_amb_ss, &d_amb_arena, &d_keep, &d_pos_hi, &d_sc, &d_ss, &d_cap, &d_cnt, &d_keys_a, &d_keys_b, &d_vals_a, &d_vals_b, &d_tmp, &d_run_key, &d_run_cnt, &d_nruns, &d_cnt64, &d_kept, &d_first, &d_bbase, &d_buckets, &d_pos};
   if (!up(d_sc, sc.data(), sc.size() * 4) || !up(d_ss, ss.data(), ss.size() * 4) || !up(d_cap, cap.data(), cap.size() * 4) || !d_cnt.ensure(64)) { h->err = "out of device memory (index build)"; return XM_ERR_CUDA; }
   B.slice_contig = (const int*)d_sc.p; B.slice_start = (const int*)d_ss.p; B.n_slices = (int)sc.size(); B.slice_len = slice_len;
   B.hi = hi; B.min_interesting = M.min_interesting; B.gapmers = M.gapmers; B.cap = (const int*)d_cap.p;
@@ -1235,8 +1261,8 @@ static int build_index_device(xm_handle* h, int max_used) {
     A.arenas = (char*)d_amb_arena.p;
     A.slice_contig = (const int*)d_amb_sc.p; A.slice_start = (const int*)d_amb_ss.p; A.n_slices = n_amb;
   }
-  auto emit = [&](unsigned long long* keys, uint32_t* vals, unsigned long long cap_entries) -> int {
-    B.keys = A.keys = keys; B.vals = A.vals = vals; B.cap_entries = A.cap_entries = cap_entries;
+  auto emit = [&](unsigned long long* keys, void* vals, unsigned long long cap_entries) -> int {
+    B.keys = A.keys = keys; B.vals = A.vals = vals; B.wide = A.wide = M.wide_positions() ? 1 : 0; B.cap_entries = A.cap_entries = cap_entries;
     CK(cudaMemsetAsync(d_cnt.p, 0, 64, st));
     if (B.n_slices) xm_index_emit_kernel<<<blocks, 128, 0, st>>>(B);
     if (n_amb) { CK(cudaMemsetAsync(B.ticket, 0, 4, st)); xm_index_emit_amb_kernel<<<amb_blocks, 32, 0, st>>>(A); }
@@ -1254,38 +1280,41 @@ static int build_index_device(xm_handle* h, int max_used) {
   M.tables.assign((size_t)hi + 1, HostTable());
   std::vector<long long> tab_bbase((size_t)hi + 2, 0), tab_koff((size_t)hi + 2, 0);
   if (E >= (1ull << 31)) { h->err = "xm_build_index: more than 2^31 index entries"; return XM_ERR_ARG; }
-  if (E > 0) {
-    if (!d_keys_a.ensure(E * 8) || !d_keys_b.ensure(E * 8) || !d_vals_a.ensure(E * 4) || !d_vals_b.ensure(E * 4)) { h->err = "out of device memory (index entries)"; return XM_ERR_CUDA; }
-    if (int rc = emit((unsigned long long*)d_keys_a.p, (uint32_t*)d_vals_a.p, E)) return rc;
+  const bool wide = M.wide_positions();
+  const int pos_bits = wide ? 40 : 32;
+  auto sort_fill = [&](auto pos_tag) -> int {
+    using PosT = decltype(pos_tag);
+    if (!d_keys_a.ensure(E * 8) || !d_keys_b.ensure(E * 8) || !d_vals_a.ensure(E * sizeof(PosT)) || !d_vals_b.ensure(E * sizeof(PosT))) { h->err = "out of device memory (index entries)"; return XM_ERR_CUDA; }
+    if (int rc = emit((unsigned long long*)d_keys_a.p, d_vals_a.p, E)) return rc;
     int n = (int)E;
     // (used, bucket, position) order: sort by position, then a stable sort by (used << 32 | bucket)
     size_t t1 = 0, t2 = 0, t3 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, t1, (const uint32_t*)d_vals_a.p, (uint32_t*)d_vals_b.p, (const unsigned long long*)d_keys_a.p, (unsigned long long*)d_keys_b.p, n, 0, 32, st);
-    cub::DeviceRadixSort::SortPairs(nullptr, t2, (const unsigned long long*)d_keys_b.p, (unsigned long long*)d_keys_a.p, (const uint32_t*)d_vals_b.p, (uint32_t*)d_vals_a.p, n, 0, key_bits, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, (const PosT*)d_vals_a.p, (PosT*)d_vals_b.p, (const unsigned long long*)d_keys_a.p, (unsigned long long*)d_keys_b.p, n, 0, pos_bits, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, t2, (const unsigned long long*)d_keys_b.p, (unsigned long long*)d_keys_a.p, (const PosT*)d_vals_b.p, (PosT*)d_vals_a.p, n, 0, key_bits, st);
     if (!d_run_key.ensure(E * 8) || !d_run_cnt.ensure(E * 4) || !d_nruns.ensure(16)) { h->err = "out of device memory (index runs)"; return XM_ERR_CUDA; }
     cub::DeviceRunLengthEncode::Encode(nullptr, t3, (const unsigned long long*)d_keys_a.p, (unsigned long long*)d_run_key.p, (int*)d_run_cnt.p, (int*)d_nruns.p, n, st);
     size_t t4 = 0, t5 = 0;
     cub::TransformInputIterator<unsigned long long, IxUnmulti, const unsigned long long*> unmulti((const unsigned long long*)d_keys_a.p, IxUnmulti());
     if (n_amb) {
       cub::DeviceSelect::Flagged(nullptr, t4, unmulti, (const unsigned char*)nullptr, (unsigned long long*)d_keys_b.p, (int*)d_nruns.p, n, st);
-      cub::DeviceSelect::Flagged(nullptr, t5, (const uint32_t*)d_vals_a.p, (const unsigned char*)nullptr, (uint32_t*)d_vals_b.p, (int*)d_nruns.p, n, st);
+      cub::DeviceSelect::Flagged(nullptr, t5, (const PosT*)d_vals_a.p, (const unsigned char*)nullptr, (PosT*)d_vals_b.p, (int*)d_nruns.p, n, st);
     }
     size_t tb = t1 > t2 ? t1 : t2; if (t3 > tb) tb = t3; if (t4 > tb) tb = t4; if (t5 > tb) tb = t5;
     if (!d_tmp.ensure(tb + (size_t)E * 8 + 4096)) { h->err = "out of device memory (index sort)"; return XM_ERR_CUDA; }
     size_t q = tb;
-    CK(cub::DeviceRadixSort::SortPairs(d_tmp.p, q, (const uint32_t*)d_vals_a.p, (uint32_t*)d_vals_b.p, (const unsigned long long*)d_keys_a.p, (unsigned long long*)d_keys_b.p, n, 0, 32, st));
+    CK(cub::DeviceRadixSort::SortPairs(d_tmp.p, q, (const PosT*)d_vals_a.p, (PosT*)d_vals_b.p, (const unsigned long long*)d_keys_a.p, (unsigned long long*)d_keys_b.p, n, 0, pos_bits, st));
     q = tb;
-    CK(cub::DeviceRadixSort::SortPairs(d_tmp.p, q, (const unsigned long long*)d_keys_b.p, (unsigned long long*)d_keys_a.p, (const uint32_t*)d_vals_b.p, (uint32_t*)d_vals_a.p, n, 0, key_bits, st));
-    const unsigned long long* skeys = (const unsigned long long*)d_keys_a.p; const uint32_t* svals = (const uint32_t*)d_vals_a.p;
+    CK(cub::DeviceRadixSort::SortPairs(d_tmp.p, q, (const unsigned long long*)d_keys_b.p, (unsigned long long*)d_keys_a.p, (const PosT*)d_vals_b.p, (PosT*)d_vals_a.p, n, 0, key_bits, st));
+    const unsigned long long* skeys = (const unsigned long long*)d_keys_a.p; const PosT* svals = (const PosT*)d_vals_a.p;
     if (n_amb) {   // PackedMap.add(preventDuplicates): drop the repeated possibilities of multi-blocks, clear the flag bit
       if (!d_keep.ensure((size_t)n + 16)) { h->err = "out of device memory (index de-duplication)"; return XM_ERR_CUDA; }
       xm_index_dedupe_kernel<<<(n + 255) / 256, 256, 0, st>>>(skeys, svals, n, (unsigned char*)d_keep.p);
       q = tb; CK(cub::DeviceSelect::Flagged(d_tmp.p, q, unmulti, (const unsigned char*)d_keep.p, (unsigned long long*)d_keys_b.p, (int*)d_nruns.p, n, st));
-      q = tb; CK(cub::DeviceSelect::Flagged(d_tmp.p, q, svals, (const unsigned char*)d_keep.p, (uint32_t*)d_vals_b.p, (int*)d_nruns.p, n, st));
+      q = tb; CK(cub::DeviceSelect::Flagged(d_tmp.p, q, svals, (const unsigned char*)d_keep.p, (PosT*)d_vals_b.p, (int*)d_nruns.p, n, st));
       int kept_n = 0;
       CK(cudaMemcpyAsync(&kept_n, d_nruns.p, 4, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
-      n = kept_n; skeys = (const unsigned long long*)d_keys_b.p; svals = (const uint32_t*)d_vals_b.p;
+      n = kept_n; skeys = (const unsigned long long*)d_keys_b.p; svals = (const PosT*)d_vals_b.p;
     }
     q = tb;
     CK(cub::DeviceRunLengthEncode::Encode(d_tmp.p, q, skeys, (unsigned long long*)d_run_key.p, (int*)d_run_cnt.p, (int*)d_nruns.p, n, st));
@@ -1312,11 +1341,11 @@ static int build_index_device(xm_handle* h, int max_used) {
     for (int k = 0; k <= hi; k++) { bbase[(size_t)k] = words; if (first[(size_t)k + 1] > first[(size_t)k]) words += cap[(size_t)k]; }
     const long long n_pos = koff[(size_t)hi + 1];
     tab_bbase = bbase; tab_koff = koff;
-    if (!up(d_bbase, bbase.data(), bbase.size() * 8) || !d_buckets.ensure((size_t)words * 8 + 16) || !d_pos.ensure((size_t)n_pos * 4 + 16)) { h->err = "out of device memory (index tables)"; return XM_ERR_CUDA; }
-    IndexFillD F;
+    if (!up(d_bbase, bbase.data(), bbase.size() * 8) || !d_buckets.ensure((size_t)words * 8 + 16) || !d_pos.ensure((size_t)n_pos * 4 + 16) || (wide && !d_pos_hi.ensure((size_t)n_pos + 16))) { h->err = "out of device memory (index tables)"; return XM_ERR_CUDA; }
+    IndexFillD<PosT> F;
     F.run_key = (const unsigned long long*)d_run_key.p; F.run_cnt = (const int*)d_run_cnt.p; F.run_start = run_start; F.kept_off = kept_off; F.n_runs = n_runs;
     F.first_run = (const int*)d_first.p; F.cap = (const int*)d_cap.p; F.bucket_base = (const long long*)d_bbase.p;
-    F.sorted_pos = svals; F.buckets = (unsigned long long*)d_buckets.p; F.positions = (uint32_t*)d_pos.p;
+    F.sorted_pos = svals; F.buckets = (unsigned long long*)d_buckets.p; F.positions = (uint32_t*)d_pos.p; F.positions_hi = wide ? (uint8_t*)d_pos_hi.p : nullptr;
     xm_index_fill_kernel<<<(n_runs + 255) / 256, 256, 0, st>>>(F);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
@@ -1329,19 +1358,26 @@ static int build_index_device(xm_handle* h, int max_used) {
       const long long np = koff[(size_t)k + 1] - koff[(size_t)k];
       T.positions.resize((size_t)np);
       if (np) CK(cudaMemcpy(T.positions.data(), (const uint32_t*)d_pos.p + koff[(size_t)k], (size_t)np * 4, cudaMemcpyDeviceToHost));
+      if (wide) { T.positions_hi.resize((size_t)np); if (np) CK(cudaMemcpy(T.positions_hi.data(), (const uint8_t*)d_pos_hi.p + koff[(size_t)k], (size_t)np, cudaMemcpyDeviceToHost)); }
     }
-  }
+    return XM_OK;
+  };
+  if (E > 0) { if (int rc = wide ? sort_fill((unsigned long long)0) : sort_fill((uint32_t)0)) return rc; }
   M.max_built = hi; M.index_finished = true; M.generation++;
   // the tables stay where the fill kernel wrote them: the device view is current, nothing is uploaded again
   for (auto& b : h->d_buckets) b.release();
   for (auto& b : h->d_positions) b.release();
-  h->d_ix_buckets.release(); h->d_ix_pos.release();
-  std::swap(h->d_ix_buckets, d_buckets); std::swap(h->d_ix_pos, d_pos);
+  for (auto& b : h->d_positions_hi) b.release();
+  h->d_ix_buckets.release(); h->d_ix_pos.release(); h->d_ix_pos_hi.release();
+  std::swap(h->d_ix_buckets, d_buckets); std::swap(h->d_ix_pos, d_pos); std::swap(h->d_ix_pos_hi, d_pos_hi);
   std::vector<TableD> tabs((size_t)hi + 1);
   for (int k = 0; k <= hi; k++) {
     const HostTable& T = M.tables[(size_t)k];
-    tabs[(size_t)k].capacity = T.capacity; tabs[(size_t)k].max_count = T.max_count; tabs[(size_t)k].buckets = nullptr; tabs[(size_t)k].positions = nullptr;
-    if (!T.buckets.empty()) { tabs[(size_t)k].buckets = (const uint64_t*)h->d_ix_buckets.p + tab_bbase[(size_t)k]; tabs[(size_t)k].positions = (const uint32_t*)h->d_ix_pos.p + tab_koff[(size_t)k]; }
+    tabs[(size_t)k].capacity = T.capacity; tabs[(size_t)k].max_count = T.max_count; tabs[(size_t)k].buckets = nullptr; tabs[(size_t)k].positions = nullptr; tabs[(size_t)k].positions_hi = nullptr;
+    if (!T.buckets.empty()) {
+      tabs[(size_t)k].buckets = (const uint64_t*)h->d_ix_buckets.p + tab_bbase[(size_t)k]; tabs[(size_t)k].positions = (const uint32_t*)h->d_ix_pos.p + tab_koff[(size_t)k];
+      if (wide) tabs[(size_t)k].positions_hi = (const uint8_t*)h->d_ix_pos_hi.p + tab_koff[(size_t)k];
+    }
   }
   if (!up(h->d_tables, tabs.data(), tabs.size() * sizeof(TableD))) { h->err = "device upload failed (index tables)"; return XM_ERR_CUDA; }
   h->tables_host = tabs;
@@ -1360,7 +1396,17 @@ int xm_build_index(xm_handle* h, int32_t max_used, int32_t n_threads) {
 int xm_get_index_length(xm_handle* h, int32_t n, int32_t* capacity, int32_t* max_count, int64_t* n_positions, int64_t* offsets, uint8_t* overfull, uint32_t* positions) {
   if (!h || n < 0 || n > h->m.max_built || (size_t)n >= h->m.tables.size()) return XM_ERR_ARG;
   int c, m; int64_t np;
+  if (positions && h->m.wide_positions()) { h->err = "xm_get_index_length: the reference needs more than 32 bits per position - use xm_get_index_length_wide"; return XM_ERR_ARG; }
   h->m.get_index_length(n, c, m, np, offsets, overfull, positions);
+  if (capacity) *capacity = c;
+  if (max_count) *max_count = m;
+  if (n_positions) *n_positions = np;
+  return XM_OK;
+}
+int xm_get_index_length_wide(xm_handle* h, int32_t n, int32_t* capacity, int32_t* max_count, int64_t* n_positions, int64_t* offsets, uint8_t* overfull, uint64_t* positions) {
+  if (!h || n < 0 || n > h->m.max_built || (size_t)n >= h->m.tables.size()) return XM_ERR_ARG;
+  int c, m; int64_t np;
+  h->m.get_index_length(n, c, m, np, offsets, overfull, nullptr, positions);
   if (capacity) *capacity = c;
   if (max_count) *max_count = m;
   if (n_positions) *n_positions = np;

@@ -23,7 +23,9 @@ namespace xm {
 struct HostTable {
   int capacity = 1, max_count = 1;
   std::vector<uint64_t> buckets;   // empty => PackedMap(1,1)
-  std::vector<uint32_t> positions;
+  std::vector<uint32_t> positions;     // low 32 bits
+  std::vector<uint8_t> positions_hi;   // bits 32-39; empty while the reference's forward + reverse size fits 32 bits
+  int64_t position(size_t i) const { return (int64_t)positions[i] | (positions_hi.empty() ? 0 : ((int64_t)positions_hi[i] << 32)); }
 };
 
 struct HostModel {
@@ -36,6 +38,9 @@ struct HostModel {
   std::vector<int32_t> len;
   std::vector<int64_t> gstart;
   int64_t total_forward = 0, total_fr = 0;
+  int64_t position_bias = 0;   // global position of the first contig (0 in production; tests move the reference past 2^32 with it)
+  int64_t position_end = 0;    // one past the last global position (= position_bias + total_fr)
+  bool wide_positions() const { return position_end > (1LL << 32); }
   bool ref_ambiguous = false;
   // index
   std::vector<HostTable> tables;
@@ -62,9 +67,9 @@ struct HostModel {
       total_forward += lengths[c];
     }
     words.resize((words.size() + 15) & ~(size_t)7, 0);
-    int64_t g = 0;
+    int64_t g = position_bias;
     for (int c = 0; c < n; c++) { gstart[2 * c] = g; g += lengths[c]; gstart[2 * c + 1] = g; g += lengths[c]; }
-    gstart[2 * (size_t)n] = g; total_fr = g;
+    gstart[2 * (size_t)n] = g; position_end = g; total_fr = g - position_bias;
     for (int c = 0; c < n && !ref_ambiguous; c++) { SeqView v = contig_view(c, 0); for (int i = 0; i < v.len; i++) if (bp_is_ambiguous(v.at(i))) { ref_ambiguous = true; break; } }
     tables.clear(); max_built = 0; index_finished = false; dup_starts.assign(n, {}); dup_set = false; dup_generation++;
     generation++;
@@ -72,16 +77,23 @@ struct HostModel {
 
   static uint64_t bucket_word(int64_t start, bool overfull, int count) { return ((uint64_t)start << 24) | ((uint64_t)(overfull ? 1 : 0) << 16) | (uint64_t)(count & 0xFFFF); }
 
-  void set_index_length(int n_used, int capacity, int max_count, const int64_t* offsets, const uint8_t* overfull, const uint32_t* positions) {
+  // positions: uint32 (wide64 false) or uint64 (wide64 true) global positions
+  void set_index_length(int n_used, int capacity, int max_count, const int64_t* offsets, const uint8_t* overfull, const void* positions, bool wide64 = false) {
     if ((int)tables.size() <= n_used) tables.resize((size_t)n_used + 1);
     HostTable& T = tables[(size_t)n_used];
     T.capacity = capacity < 1 ? 1 : capacity; T.max_count = max_count;
-    T.buckets.clear(); T.positions.clear();
+    T.buckets.clear(); T.positions.clear(); T.positions_hi.clear();
     int64_t total = offsets ? offsets[capacity] : 0;
     if (offsets) {
       T.buckets.resize((size_t)T.capacity);
       for (int b = 0; b < capacity; b++) T.buckets[(size_t)b] = bucket_word(offsets[b], overfull && overfull[b], (int)(offsets[b + 1] - offsets[b]));
-      T.positions.assign(positions, positions + total);
+      if (!wide64) { const uint32_t* p = (const uint32_t*)positions; T.positions.assign(p, p + total); if (wide_positions()) T.positions_hi.assign((size_t)total, 0); }
+      else {
+        const uint64_t* p = (const uint64_t*)positions;
+        T.positions.resize((size_t)total);
+        if (wide_positions()) T.positions_hi.resize((size_t)total);
+        for (int64_t i = 0; i < total; i++) { T.positions[(size_t)i] = (uint32_t)p[i]; if (wide_positions()) T.positions_hi[(size_t)i] = (uint8_t)(p[i] >> 32); }
+      }
     }
     generation++;
   }
@@ -110,7 +122,7 @@ struct HostModel {
   }
   static int max_count_for(int n, int max_short) { int m = n * n; if (m < max_short) m = max_short; if (m > 32766) m = 32766; if (m < 1) m = 1; return m; }
 
-  struct Entry { uint32_t bucket, pos; };
+  struct Entry { uint32_t bucket; uint64_t pos; };
 
   // what both index builders start from: minInterestingSize :51-55, the longest length built and the capacity per length
   bool index_plan(int max_used, int& hi, std::vector<int>& cap, std::string& err) {
@@ -200,8 +212,8 @@ struct HostModel {
           bool primary = (rml != rmr) ? rml : (g.fwd >= g.rev);
           bool secondary = (rml != rmr) ? rmr : (g.fwd <= g.rev);  // HashBlock.isSecondaryPolarity :339-343
           auto& dst = is_multi ? multi_parts[(size_t)t][(size_t)n] : parts[(size_t)t][(size_t)n];
-          if (primary) { int r = g.fwd % c; if (r < 0) r += c; dst.push_back({(uint32_t)r, (uint32_t)(gstart[2 * sl.contig] + g.start)}); }
-          if (secondary) { int r = g.rev % c; if (r < 0) r += c; dst.push_back({(uint32_t)r, (uint32_t)(gstart[2 * sl.contig + 1] + (seq.len - g.end()))}); }
+          if (primary) { int r = g.fwd % c; if (r < 0) r += c; dst.push_back({(uint32_t)r, (uint64_t)(gstart[2 * sl.contig] + g.start)}); }
+          if (secondary) { int r = g.rev % c; if (r < 0) r += c; dst.push_back({(uint32_t)r, (uint64_t)(gstart[2 * sl.contig + 1] + (seq.len - g.end()))}); }
         };
         if (ref_ambiguous) {
           bool amb = false;
@@ -274,7 +286,7 @@ struct HostModel {
           while (j < all.size() && all[j].bucket == (uint32_t)b) j++;
           int64_t cnt = (int64_t)(j - i);
           if (cnt > T.max_count) T.buckets[(size_t)b] = bucket_word(off, true, 0);
-          else { T.buckets[(size_t)b] = bucket_word(off, false, (int)cnt); for (size_t k = i; k < j; k++) T.positions.push_back(all[k].pos); off += cnt; }
+          else { T.buckets[(size_t)b] = bucket_word(off, false, (int)cnt); for (size_t k = i; k < j; k++) { T.positions.push_back((uint32_t)all[k].pos); if (wide_positions()) T.positions_hi.push_back((uint8_t)(all[k].pos >> 32)); } off += cnt; }
           i = j;
         }
       }
@@ -286,7 +298,7 @@ struct HostModel {
   }
 
   // reads a table back in the xm_set_index_length layout
-  void get_index_length(int n, int& capacity, int& max_count, int64_t& n_pos, int64_t* offsets, uint8_t* overfull, uint32_t* positions) const {
+  void get_index_length(int n, int& capacity, int& max_count, int64_t& n_pos, int64_t* offsets, uint8_t* overfull, uint32_t* positions, uint64_t* positions64 = nullptr) const {
     const HostTable& T = tables[(size_t)n];
     capacity = T.capacity; max_count = T.max_count; n_pos = (int64_t)T.positions.size();
     if (offsets) {
@@ -297,6 +309,7 @@ struct HostModel {
       }
     }
     if (positions && n_pos) memcpy(positions, T.positions.data(), (size_t)n_pos * 4);
+    if (positions64) for (int64_t i = 0; i < n_pos; i++) positions64[i] = (uint64_t)T.position((size_t)i);
   }
 
   // ---- duplication detector (DuplicationDetector.process :129-214, saveDuplications :332-400) ----
@@ -410,7 +423,7 @@ struct HostModel {
           std::map<std::string, std::set<std::pair<int, int>>> by_text;
           int prefix = (bl + 3) / 4;
           for (int k = 0; k < 2 * cnt; k++) {
-            int64_t g = T.positions[(size_t)(word >> 24) + (size_t)(k % cnt)];
+            int64_t g = T.position((size_t)(word >> 24) + (size_t)(k % cnt));
             int sid = (int)(std::upper_bound(gstart.begin(), gstart.end(), g) - gstart.begin()) - 1;
             int st = (int)(g - gstart[(size_t)sid]);
             if (k >= cnt) { sid ^= 1; st = len[(size_t)(sid >> 1)] - st - bl; }

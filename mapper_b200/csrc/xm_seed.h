@@ -759,10 +759,10 @@ XM_HD inline bool counting_next_block(WS& w, MatePath& m, HB& out) {  // getNext
 }
 // One index hit of seed qb at global position pos: decode, flank verification (Counting_HashBlockPath.step :98-153)
 // and the resulting SequenceMatch (:155-166).  mate < 0 = rejected.
-XM_FN SM verify_hit(const WS& w, const MatePath& m, const HB& qb, uint32_t pos, bool invert) {
+XM_FN SM verify_hit(const WS& w, const MatePath& m, const HB& qb, int64_t pos, bool invert) {
   SM full; full.mate = -1; full.rev = 0; full.contig = 0; full.offset = 0; full.from_hash = 1;
   int seq_id, rstart;
-  w.ref->decode((int64_t)pos, seq_id, rstart);
+  w.ref->decode(pos, seq_id, rstart);
   if (invert) { seq_id ^= 1; rstart = w.ref->len[seq_id >> 1] - rstart - qb.len; }
   const int contig = seq_id >> 1, on_rc = seq_id & 1;
   const SeqView cms = w.ref->contig(contig, on_rc);
@@ -824,7 +824,7 @@ XM_FN bool counting_step(WS& w, MatePath& m) {  // step :40-179
   m.history[m.n_hist++] = hh;
   w.st_seeds++; w.st_hits += (unsigned long long)count;
   bool invert = !qb.primary();
-  const uint32_t* pos = (count > 0) ? t->positions + (word >> 24) : nullptr;
+  const int64_t pos0 = (int64_t)(word >> 24);   // first position of the bucket
   // Each hit is verified independently (flank comparison, :98-153); the bins are then updated in bucket order.
   // On the device 32 lanes verify 32 hits at a time and lane results are replayed in order by the whole warp.
 #if defined(__CUDA_ARCH__)
@@ -833,7 +833,7 @@ XM_FN bool counting_step(WS& w, MatePath& m) {  // step :40-179
   for (int base = 0; base < count; base += 32) {
     const int n = imin(32, count - base);
     SM mine; mine.mate = -1; mine.rev = 0; mine.contig = 0; mine.offset = 0; mine.from_hash = 1;
-    if (lane < n) mine = verify_hit(w, m, qb, pos[base + lane], invert);
+    if (lane < n) mine = verify_hit(w, m, qb, t->position(pos0 + base + lane), invert);
     XM_NOUNROLL
     for (int j = 0; j < n; j++) {
       SM full;
@@ -847,7 +847,7 @@ XM_FN bool counting_step(WS& w, MatePath& m) {  // step :40-179
   }
 #else
   for (int k = 0; k < count; k++) {
-    SM full = verify_hit(w, m, qb, pos[k], invert);
+    SM full = verify_hit(w, m, qb, t->position(pos0 + k), invert);
     if (full.mate < 0) continue;
     counting_update_matches(w, m, full, qb, count);
     if (w.status != 0) return false;

@@ -139,7 +139,9 @@ struct TableD {
   int capacity;
   int max_count;
   const uint64_t* buckets;   // capacity entries; nullptr for the empty PackedMap(1,1)
-  const uint32_t* positions;
+  const uint32_t* positions;     // low 32 bits of the global positions
+  const uint8_t* positions_hi;   // bits 32-39, nullptr while the reference's forward + reverse size fits 32 bits (QV/SequenceDatabase.java:69-74 sizes positions the same way)
+  XM_INLINE int64_t position(int64_t i) const { return (int64_t)positions[i] | (positions_hi ? ((int64_t)positions_hi[i] << 32) : 0); }
 };
 struct IndexD {
   int min_interesting;

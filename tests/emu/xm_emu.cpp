@@ -33,6 +33,15 @@ void xe_destroy(void* h) { delete (Emu*)h; }
 const char* xe_last_error(void* h) { return ((Emu*)h)->err.c_str(); }
 int xe_set_reference(void* h, int n, const uint16_t* const* packed, const int32_t* lens) { ((Emu*)h)->m.set_reference(n, packed, lens); return 0; }
 int xe_set_index_length(void* h, int n_used, int cap, int maxc, const int64_t* off, const uint8_t* over, const uint32_t* pos) { ((Emu*)h)->m.set_index_length(n_used, cap, maxc, off, over, pos); return 0; }
+int xe_set_position_bias(void* h, long long bias) { ((Emu*)h)->m.position_bias = bias; return 0; }   // before xe_set_reference
+int xe_set_index_length_wide(void* h, int n_used, int cap, int maxc, const int64_t* off, const uint8_t* over, const uint64_t* pos) { ((Emu*)h)->m.set_index_length(n_used, cap, maxc, off, over, pos, true); return 0; }
+int xe_get_index_positions_wide(void* h, int n, uint64_t* pos) {
+  Emu* e = (Emu*)h;
+  if (n < 0 || n > e->m.max_built) return -1;
+  int c, m; int64_t np;
+  e->m.get_index_length(n, c, m, np, nullptr, nullptr, nullptr, pos);
+  return 0;
+}
 int xe_finish_index(void* h, int mi, int mb) { ((Emu*)h)->m.finish_index(mi, mb); return 0; }
 int xe_build_index(void* h, int max_used, int threads) { Emu* e = (Emu*)h; return e->m.build_index(max_used, threads, e->err) ? 0 : -1; }
 int xe_index_info(void* h, int* mi, int* mb) { *mi = ((Emu*)h)->m.min_interesting; *mb = ((Emu*)h)->m.max_built; return 0; }
@@ -62,7 +71,7 @@ void* xe_align_batch(void* h, int nq, const uint16_t* packed, const int64_t* seq
   // "device" structs over host arrays
   RefD ref; ref.n_contigs = M.n_contigs; ref.words = M.words.data(); ref.word_off = M.word_off.data(); ref.len = M.len.data(); ref.gstart = M.gstart.data(); ref.total_fr = M.total_fr;
   std::vector<TableD> tabs(M.tables.size());
-  for (size_t i = 0; i < M.tables.size(); i++) { tabs[i].capacity = M.tables[i].capacity; tabs[i].max_count = M.tables[i].max_count; tabs[i].buckets = M.tables[i].buckets.empty() ? nullptr : M.tables[i].buckets.data(); tabs[i].positions = M.tables[i].positions.data(); }
+  for (size_t i = 0; i < M.tables.size(); i++) { tabs[i].capacity = M.tables[i].capacity; tabs[i].max_count = M.tables[i].max_count; tabs[i].buckets = M.tables[i].buckets.empty() ? nullptr : M.tables[i].buckets.data(); tabs[i].positions = M.tables[i].positions.data(); tabs[i].positions_hi = M.tables[i].positions_hi.empty() ? nullptr : M.tables[i].positions_hi.data(); }
   IndexD ix; ix.min_interesting = M.min_interesting; ix.max_built = M.max_built; ix.gapmers = M.gapmers; ix.tables = tabs.data();
   std::vector<int64_t> doff((size_t)M.n_contigs + 1, 0); std::vector<int32_t> dst;
   for (int c = 0; c < M.n_contigs; c++) { if ((size_t)c < M.dup_starts.size()) dst.insert(dst.end(), M.dup_starts[(size_t)c].begin(), M.dup_starts[(size_t)c].end()); doff[(size_t)c + 1] = (int64_t)dst.size(); }

@@ -84,6 +84,51 @@ def test_library_index_builder_matches_host_tables():
     emu.close()
 
 
+def test_positions_past_2_32():
+    """Global positions wider than 32 bits (QV/SequenceDatabase.java:69-74 sizes them by the forward + reverse size; KAT
+    T/PackedMap_Test.testLargeReferenceSize): the reference is placed 2^33 + 12345 bases into the position space, as if a reference of
+    that size preceded it.  The host builder's tables are the unbiased ones shifted by the bias, the duplication table is unchanged,
+    uploaded 64-bit tables work, and the alignments are bit-identical to the oracle's."""
+    bias = (1 << 33) + 12345
+    ref = synth.random_reference(120000, seed=211, n_contigs=3, repeat_fraction=0.1, repeat_len=(100, 600))
+    db = xo.Oracle([(n, synth.codes_to_text(s)) for n, s in ref], sort_by_length=True, dup=dict(min_copies=2, window=1000))
+    contigs = [db.contig(i) for i in range(db.num_contigs())]
+    batch = synth.simulate_reads(contigs, 600, 120, seed=212, sub_rate=0.02, indel_rate=0.003, paired=True)
+    want = db.align_batch(synth.DEFAULT_PARAMS, batch, threads=2)
+    plain = xm_emu.Emu(synth.DEFAULT_PARAMS)
+    parity.feed_reference(plain, db)
+    plain.build_index(120, threads=2)
+    plain.build_duplications(-1, -1, 2, 1000)
+    wide = xm_emu.Emu(synth.DEFAULT_PARAMS)
+    wide.set_position_bias(bias)
+    parity.feed_reference(wide, db)
+    wide.build_index(120, threads=2)
+    wide.build_duplications(-1, -1, 2, 1000)
+    mi, mb = wide.index_info()
+    assert (mi, mb) == plain.index_info()
+    tables = []
+    for n in range(1, mb + 1):
+        t0, t1 = plain.get_index_length(n), wide.get_index_length(n, wide=True)
+        assert t0["capacity"] == t1["capacity"] and np.array_equal(t0["offsets"], t1["offsets"]) and np.array_equal(t0["overfull"], t1["overfull"]), n
+        assert np.array_equal(t0["positions"].astype(np.uint64) + np.uint64(bias), t1["positions"]), n
+        tables.append(t1)
+    for c in range(db.num_contigs()):
+        assert np.array_equal(plain.get_duplications(c), wide.get_duplications(c)), c
+    parity.assert_same_results(want, wide.align_batch(batch, threads=1), "biased positions, host-built index")
+    db.detect_duplications()
+    up = xm_emu.Emu(synth.DEFAULT_PARAMS)   # the Java host's path: tables uploaded with 64-bit positions
+    up.set_position_bias(bias)
+    parity.feed_reference(up, db)
+    for t in tables:
+        up.set_index_length(t, wide=True)
+    up.finish_index(mi, mb)
+    for c in range(db.num_contigs()):
+        up.set_duplications(1000, db.dup_granularity(), c, plain.get_duplications(c))
+    parity.assert_same_results(want, up.align_batch(batch, threads=1), "biased positions, uploaded index")
+    for e in (plain, wide, up):
+        e.close()
+
+
 def ambiguate(batch, seed, rate, codes=(15, 15, 15, 5, 10, 3, 12, 7)):
     """Replaces a fraction of the query bases by IUPAC-ambiguous codes that still contain the original base (N mostly, some
     two- and three-base codes), in the QV 4-bit packing the batch carries."""

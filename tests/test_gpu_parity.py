@@ -139,6 +139,50 @@ def test_duplication_table_device_scan(ambiguous):
     g.close()
 
 
+def test_positions_past_2_32(monkeypatch):
+    """Global positions wider than 32 bits (QV/SequenceDatabase.java:69-74; KAT T/PackedMap_Test.testLargeReferenceSize): with
+    XM_POSITION_BIAS the reference sits 2^33 + 12345 bases into the position space.  The device builder (64-bit sort values, uint32 +
+    uint8 planes), the host builder and uploaded 64-bit tables give the unbiased tables shifted by the bias; the device duplication scan
+    gives the same table; alignments (single and paired) are bit-identical to the oracle's; the 32-bit entry points refuse."""
+    bias = (1 << 33) + 12345
+    ref = synth.random_reference(400000, seed=221, n_contigs=3, repeat_fraction=0.1, repeat_len=(100, 1500))
+    db = xo.Oracle([(n, synth.codes_to_text(s)) for n, s in ref], sort_by_length=True, threads=8, dup=dict(min_copies=2, window=1000))
+    contigs = [db.contig(i) for i in range(db.num_contigs())]
+    plain = gpu_from_oracle(db, synth.DEFAULT_PARAMS, 150, 1000, False, False)
+    monkeypatch.setenv("XM_POSITION_BIAS", str(bias))
+    wide = gpu_from_oracle(db, synth.DEFAULT_PARAMS, 150, 1000, False, False)
+    host = gpu_from_oracle(db, synth.DEFAULT_PARAMS, 150, 1000, False, False, threads=4)
+    mi, mb = wide.index_info()
+    assert (mi, mb) == plain.index_info()
+    with pytest.raises(capi.XmError):
+        wide.get_index_length(mi)
+    tables = []
+    for n in range(1, mb + 1):
+        t0, t1, t2 = plain.get_index_length(n), wide.get_index_length(n, wide=True), host.get_index_length(n, wide=True)
+        assert t0["capacity"] == t1["capacity"] and np.array_equal(t0["offsets"], t1["offsets"]) and np.array_equal(t0["overfull"], t1["overfull"]), n
+        assert np.array_equal(t0["positions"].astype(np.uint64) + np.uint64(bias), t1["positions"]), n
+        assert np.array_equal(t1["positions"], t2["positions"]) and np.array_equal(t1["offsets"], t2["offsets"]), n
+        tables.append(t1)
+    for c in range(db.num_contigs()):
+        assert np.array_equal(plain.get_duplications(c), wide.get_duplications(c)), c
+    up = capi.XMapper(synth.DEFAULT_PARAMS, device=0)   # the Java host's path: tables uploaded with 64-bit positions
+    parity.feed_reference(up, db)
+    with pytest.raises(capi.XmError):
+        up.set_index_length(dict(tables[-1], positions=tables[-1]["positions"].astype(np.uint32)))
+    for t in tables:
+        up.set_index_length(t, wide=True)
+    up.finish_index(mi, mb)
+    for c in range(db.num_contigs()):
+        up.set_duplications(1000, db.dup_granularity(), c, plain.get_duplications(c))
+    for paired in (False, True):
+        batch = synth.simulate_reads(contigs, 5000, 150, seed=222 + paired, sub_rate=0.02, indel_rate=0.003, paired=paired)
+        want = db.align_batch(synth.DEFAULT_PARAMS, batch, threads=8)
+        for g, what in ((wide, "device-built"), (host, "host-built"), (up, "uploaded")):
+            parity.assert_same_results(want, g.align_batch(batch, strict=True), "positions past 2^32, %s index, paired=%s" % (what, paired))
+    for g in (plain, wide, host, up):
+        g.close()
+
+
 def test_long_reads_1kbp_split_shape():
     """BASELINE.json configs[4] shape: 1 kbp pieces (what --split-queries-past-size 1000 hands the aligner, M/SequenceSplitter.java:9-38)
     with 1 % substitutions + 0.5 % indels on a multi-contig reference with repeat families."""

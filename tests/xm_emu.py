@@ -70,14 +70,19 @@ class Emu:
         self._keep = [packed_contigs, lens]
         self._ok(self.L.xe_set_reference(C.c_void_p(self.h), n, arr, lens.ctypes.data_as(C.c_void_p)))
 
-    def set_index_length(self, t):
+    def set_position_bias(self, bias):
+        """Global position of the first contig (call before set_reference): moves every index position past 2^32."""
+        self._ok(self.L.xe_set_position_bias(C.c_void_p(self.h), C.c_longlong(int(bias))))
+
+    def set_index_length(self, t, wide=False):
         off = np.ascontiguousarray(t["offsets"], dtype=np.int64)
         over = np.ascontiguousarray(t["overfull"], dtype=np.uint8)
-        pos = np.ascontiguousarray(t["positions"], dtype=np.uint32)
+        pos = np.ascontiguousarray(t["positions"], dtype=np.uint64 if wide else np.uint32)
         if len(pos) == 0:
-            pos = np.zeros(1, dtype=np.uint32)
-        self._ok(self.L.xe_set_index_length(C.c_void_p(self.h), t["used"], t["capacity"], t["max_count"], off.ctypes.data_as(C.c_void_p),
-                                            over.ctypes.data_as(C.c_void_p), pos.ctypes.data_as(C.c_void_p)))
+            pos = np.zeros(1, dtype=pos.dtype)
+        f = self.L.xe_set_index_length_wide if wide else self.L.xe_set_index_length
+        self._ok(f(C.c_void_p(self.h), t["used"], t["capacity"], t["max_count"], off.ctypes.data_as(C.c_void_p),
+                   over.ctypes.data_as(C.c_void_p), pos.ctypes.data_as(C.c_void_p)))
 
     def finish_index(self, min_interesting, max_built):
         self._ok(self.L.xe_finish_index(C.c_void_p(self.h), min_interesting, max_built))
@@ -90,7 +95,7 @@ class Emu:
         self.L.xe_index_info(C.c_void_p(self.h), C.byref(a), C.byref(b))
         return a.value, b.value
 
-    def get_index_length(self, n):
+    def get_index_length(self, n, wide=False):
         cap, mx, npos = C.c_int(), C.c_int(), C.c_int64()
         self._ok(self.L.xe_get_index_length(C.c_void_p(self.h), n, C.byref(cap), C.byref(mx), C.byref(npos), None, None, None))
         off = np.zeros(cap.value + 1, dtype=np.int64)
@@ -98,7 +103,12 @@ class Emu:
         pos = np.zeros(max(npos.value, 1), dtype=np.uint32)
         self._ok(self.L.xe_get_index_length(C.c_void_p(self.h), n, C.byref(cap), C.byref(mx), C.byref(npos), off.ctypes.data_as(C.c_void_p),
                                             over.ctypes.data_as(C.c_void_p), pos.ctypes.data_as(C.c_void_p)))
-        return dict(used=n, capacity=cap.value, max_count=mx.value, offsets=off, overfull=over, positions=pos[:npos.value])
+        t = dict(used=n, capacity=cap.value, max_count=mx.value, offsets=off, overfull=over, positions=pos[:npos.value])
+        if wide:
+            pos64 = np.zeros(max(npos.value, 1), dtype=np.uint64)
+            self._ok(self.L.xe_get_index_positions_wide(C.c_void_p(self.h), n, pos64.ctypes.data_as(C.c_void_p)))
+            t["positions"] = pos64[:npos.value]
+        return t
 
     def set_duplications(self, window, granularity, contig, starts):
         s = np.ascontiguousarray(starts, dtype=np.int32)
