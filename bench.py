@@ -426,7 +426,7 @@ def main():
                     achieved_source=(prof.get("source") if warp_inst else "no ncu capture for this workload: issue rate not quoted"),
                     kernel_ms_per_launch=dom_ms,
                     useful_thread_instruction_fraction=((issue_achieved / issue_peak) * (pk["useful_lanes_per_instruction"] / 32.0) if (issue_achieved and pk.get("useful_lanes_per_instruction")) else None),
-                    lanes_note=("%.1f of 32 lanes active per instruction, but the per-query code is warp-uniform: about %.1f of them carry distinct work (lane-parallel inner loops), the rest repeat a scalar" % (lanes, pk.get("useful_lanes_per_instruction", 0)) if lanes else None),
+                    lanes_note=("%.1f of 32 lanes active per instruction; the per-query control code is warp-uniform (every lane repeats the same scalar), only the inner loops (pyramid rows, hit verification, ungapped scores, table fills) give the lanes distinct work" % lanes if lanes else None),
                     traffic=((pk["dram_bytes_read"] + pk["dram_bytes_write"]) if pk.get("dram_bytes_read") is not None else None),
                     hbm=dict(bound="hbm", achieved=hbm_achieved, peak=peak, unit="GB/s", frac=(hbm_achieved / peak) if hbm_achieved else None,
                              algorithmic_bytes_per_launch=dom_bytes, peak_source=peak_src,
