@@ -362,6 +362,15 @@ struct IndexBuildD {
   unsigned long long* keys; void* vals; int wide; unsigned long long cap_entries;   // vals: uint32 global positions, uint64 when the reference needs more than 32 bits (wide)
   __device__ __forceinline__ void store_pos(unsigned long long o, long long g) const { if (wide) ((unsigned long long*)vals)[o] = (unsigned long long)g; else ((uint32_t*)vals)[o] = (uint32_t)g; }
   unsigned long long* n_entries; int* ticket; int* fail;
+  int used_lo, used_hi;             // only blocks with used_lo <= numBasepairsUsed <= used_hi are emitted (a build chunked by block length)
+  unsigned long long* hist;         // counting pass: entries per numBasepairsUsed (hi + 1 counters), nullptr = not wanted
+  // counting pass: adds this lane's entries to hist[used]; lanes with the same length share one atomic
+  __device__ __forceinline__ void count_used(int used, int n) const {
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, used);
+    const int total = __reduce_add_sync(peers, n);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[used], (unsigned long long)total);
+  }
 };
 static const unsigned long long XM_IX_MULTI = 1ull << 63;   // key bit of a MultiHashBlock possibility: above the sorted bits, dropped by the de-duplication
 __device__ __forceinline__ int32_t ext_hash_lane(const SeqView& seq, int from, int n, int dir, bool complement) {  // one block per LANE
@@ -432,13 +441,14 @@ __global__ void __launch_bounds__(128) xm_index_emit_kernel(IndexBuildD B) {
             HB b; b.start = s + c16.start; b.len = c16.len; b.used = c16.len; b.fwd = c16.fwd; b.rev = c16.rev; b.gap_dir = c16.gap_dir; b.flags = c16.flags; b.extra = c16.extra; b.ident = 0;
             bool ok = true;
             if (B.gapmers) ok = gapmer_lane(b, seq, g); else g = b;
-            if (ok && g.used >= B.min_interesting && g.used <= B.hi) {
+            if (ok && g.used >= B.min_interesting && g.used <= B.hi && g.used >= B.used_lo && g.used <= B.used_hi) {
               const bool rml = g.rml(), rmr = g.rmr();
               prim = (rml != rmr) ? rml : (g.fwd >= g.rev);
               sec = (rml != rmr) ? rmr : (g.fwd <= g.rev);   // HashBlock.isSecondaryPolarity :339-343
             }
           }
         }
+        if (B.hist != nullptr && (prim || sec)) B.count_used(g.used, (prim ? 1 : 0) + (sec ? 1 : 0));
         const unsigned pm = __ballot_sync(0xffffffffu, prim), sm = __ballot_sync(0xffffffffu, sec);
         const int total = __popc(pm) + __popc(sm);
         if (total) {
@@ -530,13 +540,14 @@ __global__ void __launch_bounds__(32) xm_index_emit_amb_kernel(IndexBuildD B) {
               HB b; b.start = s + o16.start; b.len = o16.len; b.used = o16.len; b.fwd = o16.fwd; b.rev = o16.rev; b.gap_dir = o16.gap_dir; b.flags = o16.flags; b.extra = o16.extra; b.ident = 0;
               bool ok = true;
               if (B.gapmers) ok = gapmer_lane(b, full, g); else g = b;
-              if (ok && g.used >= B.min_interesting && g.used <= B.hi) {
+              if (ok && g.used >= B.min_interesting && g.used <= B.hi && g.used >= B.used_lo && g.used <= B.used_hi) {
                 const bool rml = g.rml(), rmr = g.rmr();
                 prim = (rml != rmr) ? rml : (g.fwd >= g.rev);
                 sec = (rml != rmr) ? rmr : (g.fwd <= g.rev);
               }
             }
           }
+          if (B.hist != nullptr && (prim || sec)) B.count_used(g.used, (prim ? 1 : 0) + (sec ? 1 : 0));
           const unsigned pm = __ballot_sync(0xffffffffu, prim), sm = __ballot_sync(0xffffffffu, sec);
           const int total = __popc(pm) + __popc(sm);
           if (total) {
@@ -852,7 +863,7 @@ struct xm_handle {
   DevBuf d_words, d_word_off, d_len, d_gstart, d_tables, d_dup_off, d_dup_starts;
   std::vector<DevBuf> d_buckets, d_positions, d_positions_hi;
   std::vector<TableD> tables_host;   // host copy of the device table descriptors
-  DevBuf d_ix_buckets, d_ix_pos, d_ix_pos_hi;   // tables the device index builder left in place (every length in one allocation)
+  std::vector<DevBuf> d_ix_chunks;   // tables the device index builder left in place: per chunk of block lengths, {bucket words, positions, positions bits 32-39}
   RefD ref{}; IndexD ix{}; DupD dup{};
   // Batches in flight.  A call of xm_align_batch owns one slot from its first host->device copy to its last device->host copy: the
   // slot's staging buffers, its copy stream and its device copy of the result arrays.  The kernels of different calls run one after
@@ -927,7 +938,8 @@ static int mirror_model(xm_handle* h) {
          up(h->d_len, M.len.data(), M.len.size() * 4) && up(h->d_gstart, M.gstart.data(), M.gstart.size() * 8);
     size_t nt = (size_t)M.max_built + 1;
     if (M.tables.size() < nt) M.tables.resize(nt);
-    h->d_ix_buckets.release(); h->d_ix_pos.release(); h->d_ix_pos_hi.release();
+    for (auto& b : h->d_ix_chunks) b.release();
+    h->d_ix_chunks.clear();
     h->d_buckets.resize(nt); h->d_positions.resize(nt); h->d_positions_hi.resize(nt);
     std::vector<TableD> tabs(nt);
     for (size_t i = 0; ok && i < nt; i++) {
@@ -1146,13 +1158,14 @@ void xm_destroy(xm_handle* h) {
     if (sl.copy) cudaStreamDestroy(sl.copy);
     for (cudaEvent_t e : {sl.h2d_done, sl.kernels_done, sl.ev0, sl.ev1}) if (e) cudaEventDestroy(e);
   }
-  DevBuf* bufs[] = {&h->d_ix_buckets, &h->d_ix_pos, &h->d_ix_pos_hi, &h->d_words, &h->d_word_off, &h->d_len, &h->d_gstart, &h->d_tables, &h->d_dup_off, &h->d_dup_starts, &h->d_chunk, &h->d_q, &h->d_choices, &h->d_sas, &h->d_blocks,
+  DevBuf* bufs[] = {&h->d_words, &h->d_word_off, &h->d_len, &h->d_gstart, &h->d_tables, &h->d_dup_off, &h->d_dup_starts, &h->d_chunk, &h->d_q, &h->d_choices, &h->d_sas, &h->d_blocks,
                     &h->d_misc, &h->d_ids_a, &h->d_ids_b, &h->d_ids_full, &h->d_ws, &h->d_qcycles, &h->d_csr_cnt, &h->d_csr_base, &h->d_csr_tmp, &h->d_keys_a, &h->d_keys_b, &h->d_sort_tmp, &h->d_big, &h->d_big_busy, &h->d_sam_len, &h->d_sam_text, &h->d_sam_names, &h->d_sam_name_off, &h->d_sam_cnames, &h->d_sam_cname_off, &h->d_svc, &h->d_planes, &h->d_contig_off, &h->d_var, &h->d_var_n, &h->d_order, &h->d_var_sizes,
                     &h->var_scratch.keys_a, &h->var_scratch.keys_b, &h->var_scratch.idx_a, &h->var_scratch.idx_b, &h->var_scratch.gathered, &h->var_scratch.out_keys, &h->var_scratch.n_out, &h->var_scratch.tmp};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : h->d_buckets) b.release();
   for (auto& b : h->d_positions) b.release();
   for (auto& b : h->d_positions_hi) b.release();
+  for (auto& b : h->d_ix_chunks) b.release();
   if (h->stream) cudaStreamDestroy(h->stream);
   for (cudaEvent_t e : {h->ev2, h->ev3, h->ev4, h->ev5}) if (e) cudaEventDestroy(e);
   delete h;
@@ -1261,8 +1274,14 @@ static int build_index_device(xm_handle* h, int max_used) {
     A.arenas = (char*)d_amb_arena.p;
     A.slice_contig = (const int*)d_amb_sc.p; A.slice_start = (const int*)d_amb_ss.p; A.n_slices = n_amb;
   }
+  DevBuf d_hist; fr.v.push_back(&d_hist);
+  if (!d_hist.ensure(((size_t)hi + 2) * 8)) { h->err = "out of device memory (index build)"; return XM_ERR_CUDA; }
+  int used_lo = 0, used_hi = 0x7fffffff;   // the block lengths of the current chunk
   auto emit = [&](unsigned long long* keys, void* vals, unsigned long long cap_entries) -> int {
     B.keys = A.keys = keys; B.vals = A.vals = vals; B.wide = A.wide = M.wide_positions() ? 1 : 0; B.cap_entries = A.cap_entries = cap_entries;
+    B.used_lo = A.used_lo = used_lo; B.used_hi = A.used_hi = used_hi;
+    B.hist = A.hist = (keys == nullptr) ? (unsigned long long*)d_hist.p : nullptr;
+    if (keys == nullptr) CK(cudaMemsetAsync(d_hist.p, 0, ((size_t)hi + 2) * 8, st));
     CK(cudaMemsetAsync(d_cnt.p, 0, 64, st));
     if (B.n_slices) xm_index_emit_kernel<<<blocks, 128, 0, st>>>(B);
     if (n_amb) { CK(cudaMemsetAsync(B.ticket, 0, 4, st)); xm_index_emit_amb_kernel<<<amb_blocks, 32, 0, st>>>(A); }
@@ -1279,9 +1298,41 @@ static int build_index_device(xm_handle* h, int max_used) {
   if (const int fs = (int)(cnt_host[4] & 0xffffffffu)) { h->err = "xm_build_index: MultiHashBlock expansion of the reference ran out of workspace (status " + std::to_string(fs) + "); raise XM_INDEX_AMB_ARENA_MB or use the host builder (n_threads > 0)"; return XM_ERR_ARG; }
   M.tables.assign((size_t)hi + 1, HostTable());
   std::vector<long long> tab_bbase((size_t)hi + 2, 0), tab_koff((size_t)hi + 2, 0);
-  if (E >= (1ull << 31)) { h->err = "xm_build_index: more than 2^31 index entries"; return XM_ERR_ARG; }
   const bool wide = M.wide_positions();
   const int pos_bits = wide ? 40 : 32;
+  // One sort handles < 2^31 entries and has to fit the device next to the finished tables: the build is chunked by block length.
+  // Every chunk runs the emit kernels again with a length filter (the pyramids are cheap next to the sorts).
+  std::vector<unsigned long long> hist((size_t)hi + 2, 0);
+  CK(cudaMemcpy(hist.data(), d_hist.p, ((size_t)hi + 2) * 8, cudaMemcpyDeviceToHost));
+  unsigned long long max_entries = (1ull << 31) - 1;
+  {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+      // per entry: key / value double buffers, run keys + counts, sort scratch, keep flag, the four 64-bit scan arrays over the runs (a
+      // random reference has almost one run per entry), and the finished tables (bucket word + position)
+      const unsigned long long per_entry = 2 * (8 + (wide ? 8 : 4)) + 12 + 8 + 1 + 32 + 13;
+      max_entries = std::min<unsigned long long>(max_entries, (unsigned long long)((double)free_b * 0.75) / per_entry);
+    }
+    if (const char* e = getenv("XM_INDEX_MAX_ENTRIES")) max_entries = std::min<unsigned long long>(max_entries, std::max(1LL, atoll(e)));
+  }
+  std::vector<std::pair<int, int>> chunks;
+  {
+    int lo = 0; unsigned long long acc = 0;
+    for (int k = 0; k <= hi; k++) {
+      if (hist[(size_t)k] > max_entries) { h->err = "xm_build_index: the blocks of length " + std::to_string(k) + " alone (" + std::to_string(hist[(size_t)k]) + " entries) exceed what one sort can hold on this device; use the host builder (n_threads > 0) or upload the tables"; return XM_ERR_ARG; }
+      if (acc + hist[(size_t)k] > max_entries) { chunks.push_back({lo, k - 1}); lo = k; acc = 0; }
+      acc += hist[(size_t)k];
+    }
+    chunks.push_back({lo, hi});
+  }
+  if (getenv("XM_TRACE_SETUP")) fprintf(stderr, "[xm] index build: %llu entries for block lengths <= %d, at most %llu per sort: %zu chunk(s) of lengths\n", E, hi, max_entries, chunks.size());
+  for (auto& b : h->d_buckets) b.release();
+  for (auto& b : h->d_positions) b.release();
+  for (auto& b : h->d_positions_hi) b.release();
+  for (auto& b : h->d_ix_chunks) b.release();
+  h->d_ix_chunks.clear();
+  std::vector<TableD> tabs((size_t)hi + 1);
+  for (int k = 0; k <= hi; k++) { tabs[(size_t)k].capacity = 1; tabs[(size_t)k].max_count = 1; tabs[(size_t)k].buckets = nullptr; tabs[(size_t)k].positions = nullptr; tabs[(size_t)k].positions_hi = nullptr; }
   auto sort_fill = [&](auto pos_tag) -> int {
     using PosT = decltype(pos_tag);
     if (!d_keys_a.ensure(E * 8) || !d_keys_b.ensure(E * 8) || !d_vals_a.ensure(E * sizeof(PosT)) || !d_vals_b.ensure(E * sizeof(PosT))) { h->err = "out of device memory (index entries)"; return XM_ERR_CUDA; }
@@ -1362,23 +1413,25 @@ static int build_index_device(xm_handle* h, int max_used) {
     }
     return XM_OK;
   };
-  if (E > 0) { if (int rc = wide ? sort_fill((unsigned long long)0) : sort_fill((uint32_t)0)) return rc; }
-  M.max_built = hi; M.index_finished = true; M.generation++;
-  // the tables stay where the fill kernel wrote them: the device view is current, nothing is uploaded again
-  for (auto& b : h->d_buckets) b.release();
-  for (auto& b : h->d_positions) b.release();
-  for (auto& b : h->d_positions_hi) b.release();
-  h->d_ix_buckets.release(); h->d_ix_pos.release(); h->d_ix_pos_hi.release();
-  std::swap(h->d_ix_buckets, d_buckets); std::swap(h->d_ix_pos, d_pos); std::swap(h->d_ix_pos_hi, d_pos_hi);
-  std::vector<TableD> tabs((size_t)hi + 1);
-  for (int k = 0; k <= hi; k++) {
-    const HostTable& T = M.tables[(size_t)k];
-    tabs[(size_t)k].capacity = T.capacity; tabs[(size_t)k].max_count = T.max_count; tabs[(size_t)k].buckets = nullptr; tabs[(size_t)k].positions = nullptr; tabs[(size_t)k].positions_hi = nullptr;
-    if (!T.buckets.empty()) {
-      tabs[(size_t)k].buckets = (const uint64_t*)h->d_ix_buckets.p + tab_bbase[(size_t)k]; tabs[(size_t)k].positions = (const uint32_t*)h->d_ix_pos.p + tab_koff[(size_t)k];
-      if (wide) tabs[(size_t)k].positions_hi = (const uint8_t*)h->d_ix_pos_hi.p + tab_koff[(size_t)k];
+  for (const auto& ch : chunks) {
+    used_lo = ch.first; used_hi = ch.second;
+    E = 0; for (int k = used_lo; k <= used_hi; k++) E += hist[(size_t)k];
+    if (E == 0) continue;
+    if (int rc = wide ? sort_fill((unsigned long long)0) : sort_fill((uint32_t)0)) return rc;
+    // the chunk's tables stay where the fill kernel wrote them
+    const size_t at = h->d_ix_chunks.size();
+    h->d_ix_chunks.resize(at + 3);
+    std::swap(h->d_ix_chunks[at], d_buckets); std::swap(h->d_ix_chunks[at + 1], d_pos); std::swap(h->d_ix_chunks[at + 2], d_pos_hi);
+    for (int k = std::max(1, used_lo); k <= used_hi; k++) {
+      const HostTable& T = M.tables[(size_t)k];
+      tabs[(size_t)k].capacity = T.capacity; tabs[(size_t)k].max_count = T.max_count;
+      if (T.buckets.empty()) continue;
+      tabs[(size_t)k].buckets = (const uint64_t*)h->d_ix_chunks[at].p + tab_bbase[(size_t)k]; tabs[(size_t)k].positions = (const uint32_t*)h->d_ix_chunks[at + 1].p + tab_koff[(size_t)k];
+      if (wide) tabs[(size_t)k].positions_hi = (const uint8_t*)h->d_ix_chunks[at + 2].p + tab_koff[(size_t)k];
     }
   }
+  M.max_built = hi; M.index_finished = true; M.generation++;
+  // the tables stay where the fill kernels wrote them: the device view is current, nothing is uploaded again
   if (!up(h->d_tables, tabs.data(), tabs.size() * sizeof(TableD))) { h->err = "device upload failed (index tables)"; return XM_ERR_CUDA; }
   h->tables_host = tabs;
   h->mirrored_generation = M.generation; h->mirrored_dup_generation = ~0ull;   // mirror_model still uploads the duplication table and sets the views

@@ -82,11 +82,15 @@ def test_edge_cases():
     g.close()
 
 
-@pytest.mark.parametrize("threads", [0, 4], ids=["device", "host"])
-def test_library_index_builder_on_gpu_box(threads):
+@pytest.mark.parametrize("threads,max_entries", [(0, 0), (0, 300000), (4, 0)], ids=["device", "device-chunked", "host"])
+def test_library_index_builder_on_gpu_box(threads, max_entries, monkeypatch):
     """xm_build_index: the device builder (threads=0) and the host builder it is checked against both reproduce the oracle's
     HashBlock_Database tables (M/HashBlock_Database.java:490-665, M/PackedMap.java:99-153): capacity, max count, overfull buckets,
-    bucket offsets and positions."""
+    bucket offsets and positions.  device-chunked: XM_INDEX_MAX_ENTRIES makes the device builder work through the block lengths in
+    several sorts (what it does by itself when a reference has more than 2^31 index entries or they do not fit the device); the
+    alignments that read those tables in place must equal the oracle's too."""
+    if max_entries:
+        monkeypatch.setenv("XM_INDEX_MAX_ENTRIES", str(max_entries))
     ref = synth.random_reference(300000, seed=61, n_contigs=3, repeat_fraction=0.1, repeat_len=(100, 800))
     db = xo.Oracle([(n, synth.codes_to_text(s)) for n, s in ref], sort_by_length=True, dup=dict(min_copies=2, window=1000))
     built = db.build_through(100)
@@ -100,6 +104,11 @@ def test_library_index_builder_on_gpu_box(threads):
         assert t0["capacity"] == t1["capacity"] and t0["max_count"] == t1["max_count"], n
         assert np.array_equal(t0["overfull"], t1["overfull"]) and np.array_equal(t0["positions"], t1["positions"]), n
         assert np.array_equal(t0["offsets"], t1["offsets"]), n
+    if max_entries:
+        g.build_duplications(-1, -1, 2, 1000)
+        contigs = [db.contig(i) for i in range(db.num_contigs())]
+        batch = synth.simulate_reads(contigs, 3000, 100, seed=62, sub_rate=0.02, indel_rate=0.003)
+        parity.assert_same_results(db.align_batch(synth.DEFAULT_PARAMS, batch, threads=8), g.align_batch(batch, strict=True), "chunked index build")
     g.close()
 
 
