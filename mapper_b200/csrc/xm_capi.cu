@@ -188,6 +188,11 @@ __global__ void __launch_bounds__(EASY ? XM_BLOCK : XM_FULL_BLOCK, EASY ? XM_MIN
       t = __shfl_sync(0xffffffffu, t, 0);
       if (t >= L.n_ids) break;
     }
+    __syncwarp();   // every query starts with the warp converged: the per-query code runs on warp-shared state with all 32 lanes
+#if defined(XM_DBG_UNIFORM)
+    const bool split_at_start = __activemask() != 0xffffffffu;
+    int dbg_split = 0;
+#endif
     int qi = L.ids ? L.ids[t] : t;
     QueryIn q;
     long long c0 = L.q_cycles ? clock64() : 0;
@@ -203,15 +208,29 @@ __global__ void __launch_bounds__(EASY ? XM_BLOCK : XM_FULL_BLOCK, EASY ? XM_MIN
     if (!ws_init(w, arena, L.arena_bytes, &L.ref, &L.ix, &L.dup, L.prm, q, !EASY)) w.status = Q_NEED_MORE;
     else align_query<EASY>(w, L.out, rec);
     __syncwarp();
+#if defined(XM_DBG_UNIFORM)
+    if (__activemask() != 0xffffffffu) dbg_split = 8000;
+#endif
     int status = w.status;
     if (status == Q_HARD) status = Q_NEED_MORE;
     if (!EASY && status == Q_NEED_MORE && L.n_big > 0) {
       // escalate in place: grab a free big arena (no waiting - if none is free the query goes to the next tier as before)
       int slot = -1;
-      if (lane == 0) {
-        for (int i = 0; i < L.n_big; i++) { const int j = (int)((warp + i) % L.n_big); if (atomicCAS(&L.big_busy[j], 0, 1) == 0) { slot = j; break; } }
+#if defined(XM_DBG_UNIFORM)
+      if (__activemask() != 0xffffffffu) dbg_split = 8001;
+#endif
+      // every lane walks the slots (uniform control flow); only the claim itself is lane 0's
+      for (int i = 0; i < L.n_big && slot < 0; i++) {
+        const int j = (int)((warp + i) % L.n_big);
+        int got = 0;
+        if (lane == 0) got = (atomicCAS(&L.big_busy[j], 0, 1) == 0) ? 1 : 0;
+        got = __shfl_sync(0xffffffffu, got, 0);
+        if (got) slot = j;
       }
-      slot = __shfl_sync(0xffffffffu, slot, 0);
+      __syncwarp();
+#if defined(XM_DBG_UNIFORM)
+      if (__activemask() != 0xffffffffu && dbg_split == 0) dbg_split = 8002;
+#endif
       if (slot >= 0) {
         rec.status = 0; rec.n_comp = 1; rec.n_choice[0] = 0; rec.n_choice[1] = 0; rec.choice_first[0] = 0; rec.choice_first[1] = 0;
         if (!ws_init(w, L.big_arenas + (long long)slot * L.big_arena_bytes, L.big_arena_bytes, &L.ref, &L.ix, &L.dup, L.prm, q, true)) w.status = Q_NEED_MORE;
@@ -220,6 +239,7 @@ __global__ void __launch_bounds__(EASY ? XM_BLOCK : XM_FULL_BLOCK, EASY ? XM_MIN
         status = w.status;
         __threadfence();
         if (lane == 0) atomicExch(&L.big_busy[slot], 0);
+        __syncwarp();
       }
     }
     if (status == Q_NEED_MORE) {
@@ -227,10 +247,14 @@ __global__ void __launch_bounds__(EASY ? XM_BLOCK : XM_FULL_BLOCK, EASY ? XM_MIN
       else if (lane == 0) { int k = atomicAdd(L.n_need_more, 1); L.need_more[k] = qi; if (L.need_more_key) L.need_more_key[k] = w.hard_hint; }
     } else if (status == Q_OUT_FULL) { if (lane == 0) { int k = atomicAdd(L.n_out_full, 1); L.out_full[k] = qi; } }
     rec.status = status;
+#if defined(XM_DBG_UNIFORM)
+    if (split_at_start) rec.status = -7777; else if (dbg_split) rec.status = -dbg_split; else if (w.st_cyc[5] != 0) rec.status = -(int)(100000 + w.st_cyc[5]);
+#endif
     if (lane == 0) {
       L.out.q[qi] = rec;
       if (L.q_cycles) L.q_cycles[qi] = clock64() - c0;
     }
+    __syncwarp();
     if (status != Q_NEED_MORE && status != Q_OUT_FULL) {
       st[0] += w.st_probes; st[1] += w.st_seeds; st[2] += w.st_hits; st[3] += w.st_straight; st[4] += w.st_path_calls; st[5] += w.st_path_steps; st[6] += w.st_path_cells;
       for (int i = 0; i < 6; i++) st[7 + i] += w.st_cyc[i];

@@ -105,6 +105,7 @@ XM_HD inline int32_t ext_hash(const SeqView& seq, int from, int n, int dir, bool
       if (e & 16) pw *= M16;
       term = (uint32_t)ext_char_to_int(c) * pw;
     }
+    __syncwarp();
     term += __shfl_xor_sync(0xffffffffu, term, 16);
     term += __shfl_xor_sync(0xffffffffu, term, 8);
     term += __shfl_xor_sync(0xffffffffu, term, 4);
@@ -350,6 +351,14 @@ XM_INLINE POpt pyr_opt(const Pyr& P, const HB16& e, int k) {
   if (e.flags & HB_MULTI) return P.opt[e.fwd + k];
   POpt o; o.hb = e; o.n_kv = 0; o.has = 1; o.pad = 0; return o;
 }
+#if defined(XM_DBG_UNIFORM) && defined(__CUDA_ARCH__)
+#define XM_CHECK_MASK(wref) do { if (__activemask() != 0xffffffffu && (wref).st_cyc[5] == 0) (wref).st_cyc[5] = (unsigned long long)__LINE__ + ((unsigned long long)(__FILE__[3] == 's' ? 1 : __FILE__[3] == 'a' ? 2 : 3) * 10000ull); } while (0)
+#define XM_CHECK_UNIFORM(tag, val_) do { const unsigned _am = __activemask(); const int _v = (int)(val_); const int _v0 = __shfl_sync(_am, _v, __ffs(_am) - 1); \
+  if (_am != 0xffffffffu) { w.status = -(3000 + __LINE__); return false; } if (__any_sync(_am, _v != _v0)) { w.status = -(2000 + __LINE__); return false; } } while (0)
+#else
+#define XM_CHECK_UNIFORM(tag, val_) do { } while (0)
+#define XM_CHECK_MASK(wref) do { } while (0)
+#endif
 struct PExpandFrame { int j, k, found, pad; POpt cond; };
 // HashBlock_ParentRow.expand :137-191 with its recursion unrolled onto `stack`: appends to res[0..n_res)
 XM_FN bool pyr_expand(WS& w, const Pyr& P, const HB16* prev, int n_prev, const HB16& left, const POpt& start_cond, int j_from,
@@ -361,6 +370,7 @@ XM_FN bool pyr_expand(WS& w, const Pyr& P, const HB16* prev, int n_prev, const H
   while (sp > 0) {
     PExpandFrame& f = stack[sp - 1];
     if (f.j >= n_prev) { sp--; continue; }           // getAfter(...) == null
+    XM_CHECK_UNIFORM("sp", sp); XM_CHECK_UNIFORM("f.j", f.j); XM_CHECK_UNIFORM("f.k", f.k);
     const HB16 nxt = prev[f.j];
     if (f.k >= pyr_num_opts(nxt)) { sp--; continue; }
     const POpt ro = pyr_opt(P, nxt, f.k);
@@ -369,6 +379,7 @@ XM_FN bool pyr_expand(WS& w, const Pyr& P, const HB16* prev, int n_prev, const H
     bool overflow = false;
     if (!popt_intersect(f.cond, ro, inter, overflow)) { if (f.found) sp--; continue; }  // :163-167 (break once an intersection was seen)
     if (overflow) { w.fail(Q_AMBIGUOUS_QUERY); return false; }
+    XM_CHECK_UNIFORM("inter.n_kv", inter.n_kv); XM_CHECK_UNIFORM("ro.has", ro.has);
     f.found = 1;
     if (n_res > max_combos) { sp--; continue; }      // :170 return
     if (!ro.has) {                                   // :171-174 look further right under the narrowed condition
@@ -398,9 +409,14 @@ XM_FN bool pyr_build_ambiguous(WS& w, MatePath& m) {
   PExpandFrame* stack = (PExpandFrame*)w.salloc((long long)cap_stack * (long long)sizeof(PExpandFrame));
   if (w.status != 0) return false;
   int n_amb = 0;
+  XM_CHECK_UNIFORM("entry", len);
+  XM_CHECK_UNIFORM("bytes", (int)(unsigned long long)m.q.bytes);
   XM_NOUNROLL
   for (int k = 0; k < len; k++) {  // HashBlock_BaseRow.get :27-59
     const uint8_t code = m.q.at(k);
+    XM_CHECK_UNIFORM("code", code);
+    XM_CHECK_UNIFORM("k", k);
+    XM_CHECK_UNIFORM("nopt_in", P.n_opt);
     P.child[k] = -1; P.up[k] = -1;
     if (!bp_is_ambiguous(code)) { P.blk[k] = base_block16(code, k); continue; }
     HB16 e; e.start = (int16_t)k; e.len = 1; e.fwd = P.n_opt; e.rev = 0; e.flags = HB_MULTI; e.gap_dir = 0; e.extra = 0;
@@ -412,9 +428,13 @@ XM_FN bool pyr_build_ambiguous(WS& w, MatePath& m) {
       POpt c; c.hb = base_block16(base, k); c.has = 1; c.pad = 0; c.n_kv = 1; c.kv[0] = ((uint32_t)k << 2) | (uint32_t)o;
       P.opt[P.n_opt++] = c; e.rev++;
     }
+    XM_CHECK_UNIFORM("e.rev", e.rev);
+    XM_CHECK_UNIFORM("nopt_out", P.n_opt);
     P.blk[k] = e;
     n_amb++;
   }
+  XM_CHECK_UNIFORM("n_amb", n_amb);
+  XM_CHECK_UNIFORM("n_opt0", P.n_opt);
   P.level_off[0] = 0; P.level_off[1] = len; P.n_levels = 1;
   int prev_off = 0, n_prev = len, level = 1;
   XM_NOUNROLL
@@ -437,6 +457,7 @@ XM_FN bool pyr_build_ambiguous(WS& w, MatePath& m) {
           if (lo.has) { if (!pyr_expand(w, P, prev, n_prev, lo.hb, lo, i, res, n_res, cap_res, stack, cap_stack)) return false; }
           else { if (n_res >= cap_res) { w.fail(Q_NEED_MORE); return false; } res[n_res] = lo; res[n_res].has = 0; n_res++; }
         }
+        XM_CHECK_UNIFORM("n_res", n_res); XM_CHECK_UNIFORM("n_left", n_left);
         bool any = false;
         for (int a = 0; a < n_res; a++) any |= res[a].has != 0;
         if (n_res > 0 && n_res <= 64 && any) {
@@ -446,6 +467,7 @@ XM_FN bool pyr_build_ambiguous(WS& w, MatePath& m) {
           keep = true;
         }
       }
+      XM_CHECK_UNIFORM("keep", keep); XM_CHECK_UNIFORM("n_new", n_new); XM_CHECK_UNIFORM("i", i); XM_CHECK_UNIFORM("n_prev", n_prev);
       if (keep) {
         if (cur_off + n_new + 1 > P.cap_blocks) { w.fail(Q_NEED_MORE); return false; }
         P.blk[cur_off + n_new] = made; P.child[cur_off + n_new] = (int16_t)i; P.up[cur_off + n_new] = -1;
@@ -462,6 +484,7 @@ XM_FN bool pyr_build_ambiguous(WS& w, MatePath& m) {
 XM_FN bool pyr_build(WS& w, MatePath& m) {
   Pyr& P = m.pyr;
   const int len = m.q.len;
+  XM_CHECK_MASK(w);
   if (len > P.cap_blocks || P.cap_levels < 2 || len > 32000) { w.fail(Q_NEED_MORE); return false; }
 #if defined(__CUDA_ARCH__)
   const int lane = (int)(threadIdx.x & 31);
@@ -473,7 +496,12 @@ XM_FN bool pyr_build(WS& w, MatePath& m) {
     amb |= bp_is_ambiguous(code);
     P.blk[k] = base_block16(code, k); P.child[k] = -1; P.up[k] = -1;
   }
+  // The lanes leave the loop after different trip counts.  A vote synchronises them for the vote only; what follows (the scalar
+  // MultiHashBlock build in particular) is executed by every lane on the same warp-shared state and needs the warp CONVERGED.
+  __syncwarp();
+  XM_CHECK_MASK(w);
   amb = __any_sync(0xffffffffu, amb);
+  XM_CHECK_MASK(w);
 #else
   bool amb = false;
   for (int k = 0; k < len; k++) {
@@ -834,6 +862,7 @@ XM_FN bool counting_step(WS& w, MatePath& m) {  // step :40-179
     const int n = imin(32, count - base);
     SM mine; mine.mate = -1; mine.rev = 0; mine.contig = 0; mine.offset = 0; mine.from_hash = 1;
     if (lane < n) mine = verify_hit(w, m, qb, t->position(pos0 + base + lane), invert);
+    __syncwarp();   // back from the divergent call: the replay below updates warp-shared state with every lane
     XM_NOUNROLL
     for (int j = 0; j < n; j++) {
       SM full;
