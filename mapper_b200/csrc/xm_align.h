@@ -880,173 +880,6 @@ XM_HD inline DAln straight_alignment(WS& w, const ACtx& c, const Sec& q, const S
   b->a_start = qs; b->b_start = rs; b->a_len = qe - qs; b->b_len = re - rs;
   return new_aln(p, c, b, 1, c.a_reversed_obj);
 }
-// ---- a certificate that the straight alignment cannot be beaten ----
-// StraightAligner.align :13-71 hands a section with mismatches to the rest of the cascade only to learn, most of the time, that nothing
-// in the window scores better; it then returns its own alignment (`!a.valid || a.aligned >= sp`).  Every deeper stage (SkipHighAmbiguity,
-// HashBlock_Aligner, BlockAligner, PathAligner, the inner StraightAligners) returns alignments that consume the whole section q inside
-// the window r and are scored block by block by AlignmentParameters.getPenalty(AlignedBlock) :106-126 (+ the starting-insertion rebate
-// of newSequenceAlignment :73-95) - as long as the window touches neither end of the contig (no "extension" past the reference, no
-// clipping).  The minimum of that score over ALL such alignments - global in q, free ends in r, affine gaps, any mix of gaps - is an
-// ordinary dynamic program.  It is evaluated here in exact integer arithmetic (penalties x 1024; only when all five penalties are such
-// dyadic numbers and no base of q or of the window is ambiguous), over the band of diagonals an alignment cheaper than sp can reach.
-// min >= sp  =>  no stage can return anything with aligned < sp  =>  the cascade would return `simple`; it is skipped.
-// min <  sp  =>  nothing is concluded and the cascade runs as in the reference (its search order decides ties and which optimum).
-// Rows are sequential; the lanes hold four diagonals each: the diagonal move is lane-local, the insertion move reads the next
-// diagonal of the previous row (one shuffle), the deletion move is a min-plus prefix scan along the row.
-static const int XM_CERT_E = 4, XM_CERT_DIAGS = 32 * XM_CERT_E, XM_CERT_INF = 1 << 28;
-XM_HD inline bool cert_scaled(double v, int& out) { const double sv = v * 1024.0; if (!(sv >= 0) || sv > 1048576.0 || sv != (double)(int)sv) return false; out = (int)sv; return true; }
-#if defined(XM_CERT_VC)
-XM_HD inline bool straight_is_optimal(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Params& p, double sp) {
-#else
-XM_FN bool straight_is_optimal(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Params& p, double sp) {
-#endif
-#if defined(XM_CERT_VB) && defined(__CUDA_ARCH__)
-  __syncwarp();
-#endif
-#if defined(XM_CERT_V1)
-  return false;
-#endif
-  const int A = q.length(), B = r.length();
-  if (A < 1 || A > 4096 || B < A || r.start <= 0 || r.end >= c.b.len || q.start < 0 || q.end > c.a.len) return false;
-  int mut, ins_s, ins_e, del_s, del_e, bound;
-  if (!cert_scaled(p.mutation, mut) || !cert_scaled(p.ins_start, ins_s) || !cert_scaled(p.ins_ext, ins_e) || !cert_scaled(p.del_start, del_s) ||
-      !cert_scaled(p.del_ext, del_e) || !cert_scaled(sp, bound)) return false;
-  if (ins_e < 1 || del_e < 1 || bound < 1) return false;
-#if defined(XM_CERT_DBG) && defined(__CUDA_ARCH__)
-  if ((threadIdx.x & 31) == 0) printf("cert pass mut=%d ins=%d/%d del=%d/%d bound=%d A=%d B=%d\n", mut, ins_s, ins_e, del_s, del_e, bound, A, B);
-#endif
-  const int first_ins = p.start_free ? 0 : ins_s;
-  // the furthest an alignment cheaper than `bound` can drift from the diagonal it starts on
-  const int k_ins = (bound - 1 - first_ins) >= 0 ? (bound - 1 - first_ins) / ins_e : 0;
-  const int k_del = (bound - 1 - del_s) >= 0 ? (bound - 1 - del_s) / del_e : 0;
-  const int K = imax(k_ins, k_del);
-  const int dlo = -K, nd = (B - A) + 1 + 2 * K;   // diagonal d = j - i of cell (i query bases consumed, j window bases consumed)
-  if (nd > XM_CERT_DIAGS) return false;
-#if defined(__CUDA_ARCH__) && !defined(XM_CERT_SCALAR)
-  const int lane = (int)(threadIdx.x & 31);
-  {  // no ambiguous base on either side
-    bool amb = false;
-    XM_NOUNROLL
-    for (int k = lane; k < A; k += 32) amb |= bp_is_ambiguous(c.a.at(q.start + k));
-    XM_NOUNROLL
-    for (int k = lane; k < B; k += 32) amb |= bp_is_ambiguous(c.b.at(r.start + k));
-    __syncwarp();
-    if (__any_sync(0xffffffffu, amb)) return false;
-  }
-  int M[XM_CERT_E], I[XM_CERT_E], D[XM_CERT_E];
-#pragma unroll
-  for (int e = 0; e < XM_CERT_E; e++) {
-    const int di = lane * XM_CERT_E + e, j = dlo + di;   // row 0: nothing consumed, any start column is free
-    M[e] = (di < nd && j >= 0 && j <= B) ? 0 : XM_CERT_INF; I[e] = XM_CERT_INF; D[e] = XM_CERT_INF;
-  }
-  XM_NOUNROLL
-  for (int i = 1; i <= A; i++) {
-    const uint8_t qb = c.a.at(q.start + i - 1);
-    // insertion move: from the next diagonal of the previous row
-    int up_md[XM_CERT_E], up_i[XM_CERT_E];
-    {
-      const int md0 = imin(M[0], D[0]);
-#if defined(XM_CERT_VA)
-      const int nmd = __shfl_sync(0xffffffffu, md0, (lane + 1) & 31), ni = __shfl_sync(0xffffffffu, I[0], (lane + 1) & 31);
-#else
-      const int nmd = __shfl_down_sync(0xffffffffu, md0, 1), ni = __shfl_down_sync(0xffffffffu, I[0], 1);
-#endif
-#pragma unroll
-      for (int e = 0; e + 1 < XM_CERT_E; e++) { up_md[e] = imin(M[e + 1], D[e + 1]); up_i[e] = I[e + 1]; }
-      up_md[XM_CERT_E - 1] = lane < 31 ? nmd : XM_CERT_INF; up_i[XM_CERT_E - 1] = lane < 31 ? ni : XM_CERT_INF;
-    }
-    const int open_i = (i == 1) ? first_ins : ins_s;
-    int X[XM_CERT_E];
-    bool alive = false;
-#pragma unroll
-    for (int e = 0; e < XM_CERT_E; e++) {
-      const int di = lane * XM_CERT_E + e, j = i + dlo + di;
-      const bool cell = di < nd && j >= 0 && j <= B;
-      int m = XM_CERT_INF, ins = XM_CERT_INF;
-      if (cell) {
-        if (j >= 1) {
-          const int prev = imin(imin(M[e], I[e]), D[e]);
-          if (prev < XM_CERT_INF) m = prev + ((qb & c.b.at(r.start + j - 1)) ? 0 : mut);
-        }
-        const int a1 = up_md[e] < XM_CERT_INF ? up_md[e] + open_i + ins_e : XM_CERT_INF;
-        const int a2 = up_i[e] < XM_CERT_INF ? up_i[e] + ins_e : XM_CERT_INF;
-        ins = imin(a1, a2);
-      }
-      M[e] = m; I[e] = ins;
-      X[e] = imin(m, ins);
-    }
-    // deletion move: D[di] = del_s + del_e * di + min over k < di of (X[k] - del_e * k), cells between k and di are all valid (a row's
-    // valid diagonals are contiguous)
-    int y[XM_CERT_E];
-#pragma unroll
-    for (int e = 0; e < XM_CERT_E; e++) y[e] = X[e] < XM_CERT_INF ? X[e] - del_e * (lane * XM_CERT_E + e) : XM_CERT_INF;
-    int tot = y[0];
-#pragma unroll
-    for (int e = 1; e < XM_CERT_E; e++) tot = imin(tot, y[e]);
-    int inc = tot;   // inclusive scan of the lane minima
-#pragma unroll
-#if defined(XM_CERT_VA)
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_sync(0xffffffffu, inc, (lane - o) & 31); if (lane >= o) inc = imin(inc, t); }
-    int carry = __shfl_sync(0xffffffffu, inc, (lane - 1) & 31);
-#else
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = imin(inc, t); }
-    int carry = __shfl_up_sync(0xffffffffu, inc, 1);
-#endif
-    if (lane == 0) carry = XM_CERT_INF;
-#pragma unroll
-    for (int e = 0; e < XM_CERT_E; e++) {
-      const int di = lane * XM_CERT_E + e, j = i + dlo + di;
-      const bool cell = di < nd && j >= 0 && j <= B;
-      D[e] = (cell && carry < XM_CERT_INF / 2) ? carry + del_s + del_e * di : XM_CERT_INF;
-      carry = imin(carry, y[e]);
-      alive |= imin(X[e], D[e]) < bound;
-    }
-    if (!__any_sync(0xffffffffu, alive)) return true;   // every cell of the row already costs >= sp
-  }
-  int best = XM_CERT_INF;
-#pragma unroll
-  for (int e = 0; e < XM_CERT_E; e++) best = imin(best, imin(imin(M[e], I[e]), D[e]));
-  best = __reduce_min_sync(0xffffffffu, best);
-  return best >= bound;
-#else
-  for (int k = 0; k < A; k++) if (bp_is_ambiguous(c.a.at(q.start + k))) return false;
-  for (int k = 0; k < B; k++) if (bp_is_ambiguous(c.b.at(r.start + k))) return false;
-  int M[2][XM_CERT_DIAGS], I[2][XM_CERT_DIAGS], D[2][XM_CERT_DIAGS];
-  for (int di = 0; di < nd; di++) { const int j = dlo + di; M[0][di] = (j >= 0 && j <= B) ? 0 : XM_CERT_INF; I[0][di] = XM_CERT_INF; D[0][di] = XM_CERT_INF; }
-  int cur = 0;
-  for (int i = 1; i <= A; i++) {
-    const int prv = cur; cur ^= 1;
-    const uint8_t qb = c.a.at(q.start + i - 1);
-    const int open_i = (i == 1) ? first_ins : ins_s;
-    bool alive = false;
-    for (int di = 0; di < nd; di++) {
-      const int j = i + dlo + di;
-      const bool cell = j >= 0 && j <= B;
-      int m = XM_CERT_INF, ins = XM_CERT_INF, del = XM_CERT_INF;
-      if (cell) {
-        if (j >= 1) { const int prev = imin(imin(M[prv][di], I[prv][di]), D[prv][di]); if (prev < XM_CERT_INF) m = prev + ((qb & c.b.at(r.start + j - 1)) ? 0 : mut); }
-        if (di + 1 < nd) {
-          const int umd = imin(M[prv][di + 1], D[prv][di + 1]), ui = I[prv][di + 1];
-          const int a1 = umd < XM_CERT_INF ? umd + open_i + ins_e : XM_CERT_INF, a2 = ui < XM_CERT_INF ? ui + ins_e : XM_CERT_INF;
-          ins = imin(a1, a2);
-        }
-        if (di >= 1) {
-          const int lx = imin(M[cur][di - 1], I[cur][di - 1]), ld = D[cur][di - 1];
-          const int b1 = lx < XM_CERT_INF ? lx + del_s + del_e : XM_CERT_INF, b2 = ld < XM_CERT_INF ? ld + del_e : XM_CERT_INF;
-          del = imin(b1, b2);
-        }
-      }
-      M[cur][di] = m; I[cur][di] = ins; D[cur][di] = del;
-      alive |= imin(imin(m, ins), del) < bound;
-    }
-    if (!alive) return true;
-  }
-  int best = XM_CERT_INF;
-  for (int di = 0; di < nd; di++) best = imin(best, imin(imin(M[cur][di], I[cur][di]), D[cur][di]));
-  return best >= bound;
-#endif
-}
-
 // EASY = the first-pass kernel: it completes a query only when every alignMatch is settled by the outermost
 // StraightAligner; the first time the cascade would go deeper the query is handed to the full kernel (Q_HARD).
 template <bool EASY, int STAGE>
@@ -1067,10 +900,6 @@ XM_FN DAln straight_align_t(WS& w, const ACtx& c, const Sec& q, const Sec& r, co
   double rate = simple.aligned / q.length();
   Params sub = p;
   sub.max_error_rate = dmin(rate, p.max_error_rate);
-  // the cascade below can only confirm `simple` when nothing in the window is cheaper: prove that instead, when the proof is cheap
-#if !defined(XM_CERT_V2)
-  if (STAGE == ST_STRAIGHT1 && sp <= max_interesting && simple.n == 1 && simple.b[0].a_len == q.length() && straight_is_optimal(w, c, q, r, p, sp)) return simple;
-#endif
   if constexpr (EASY) { w.hard_hint = (int)(sp * 16.0); w.fail(Q_HARD); return aln_null(); }
   else {
     DAln a = cascade_t<STAGE + 1>(w, c, q, r, sub, an);
