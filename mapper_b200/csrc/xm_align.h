@@ -650,9 +650,16 @@ __device__ __noinline__ int pa_search_remote(WS& w, PathState& S, PaOverflow* ov
     __threadfence();   // PathState, sections and the request are in L2 before the ring entry is
     const unsigned int pos = atomicAdd(w.svc.tail, 1u);
     *(volatile int*)&w.svc.ring[pos & w.svc.ring_mask] = w.svc_slot + 1;
-    while (ld_volatile_i(&rq->state) != 2) __nanosleep(400);
-    __threadfence();
   }
+  __syncwarp();
+  while (true) {   // every lane takes part in the wait (uniform control flow), lane 0 looks
+    int done = 0;
+    if (lane == 0) done = ld_volatile_i(&rq->state) == 2 ? 1 : 0;
+    done = __shfl_sync(0xffffffffu, done, 0);
+    if (done) break;
+    __nanosleep(400);
+  }
+  __threadfence();
   __syncwarp();
   const int rc = __ldcg(&rq->rc);
   last_x = __ldcg(&rq->last_x); last_y = __ldcg(&rq->last_y);

@@ -124,17 +124,21 @@ __global__ void __launch_bounds__(EASY ? XM_BLOCK : XM_FULL_BLOCK, EASY ? XM_MIN
       uint8_t* seq = xm_dyn_smem + (size_t)warp_in_block * L.dyn_stride + ((sizeof(PathState) + 15) & ~(size_t)15);
       while (true) {
         unsigned int pos = 0; int slot1 = 0;
-        if (lane == 0) {
-          pos = atomicAdd(L.svc.head, 1u);
-          int* cell = &L.svc.ring[pos & L.svc.ring_mask];
-          while (true) {
-            if (ld_volatile_i(cell) != 0) { slot1 = atomicExch(cell, 0); if (slot1 != 0) break; }
-            if (ld_volatile_i(L.svc.started_blocks) >= (int)gridDim.x && ld_volatile_i(L.svc.active_clients) <= 0) { slot1 = -1; break; }
-            __nanosleep(200);
+        if (lane == 0) pos = atomicAdd(L.svc.head, 1u);
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        int* cell = &L.svc.ring[pos & L.svc.ring_mask];
+        while (true) {   // uniform control flow: every lane takes part in the polling loop, lane 0 looks (a lane-0-only loop would leave the warp split)
+          int s = 0;
+          if (lane == 0) {
+            if (ld_volatile_i(cell) != 0) s = atomicExch(cell, 0);
+            if (s == 0 && ld_volatile_i(L.svc.started_blocks) >= (int)gridDim.x && ld_volatile_i(L.svc.active_clients) <= 0) s = -1;
           }
-          __threadfence();
+          s = __shfl_sync(0xffffffffu, s, 0);
+          if (s != 0) { slot1 = s; break; }
+          __nanosleep(200);
         }
-        slot1 = __shfl_sync(0xffffffffu, slot1, 0);
+        __threadfence();
+        __syncwarp();
         if (slot1 < 0) break;
         PaReq* rq = L.svc.reqs + (slot1 - 1);
         PathState* gS = (PathState*)__ldcg((const unsigned long long*)&rq->S);
