@@ -185,6 +185,7 @@ XM_INLINE void matcher_scan_encodings(const MatcherD& m, const SeqView& ref, int
 }
 // value of section[encoded] after indexSection(sectionIndex)
 XM_FN int matcher_section_value(WS& w, MatcherD& m, const SeqView& ref, int section_index, int target) {
+  XM_CHECK_MASK(w);
   int start = m.ref_start + section_index * m.section_len;
   if (m.tables != nullptr) {
     int slot = -1;
@@ -243,6 +244,7 @@ XM_FN int matcher_scan_section(const MatcherD& m, const ACtx& c, int query_index
   return result;
 }
 XM_FN int matcher_lookup(WS& w, MatcherD& m, const ACtx& c, int query_index, int min_ref, int max_ref) {  // :98-141
+  XM_CHECK_MASK(w);
   if (min_ref < 0) return M_UNKNOWN;
   if (max_ref > c.b.len) return M_UNKNOWN;
   int enc = matcher_encode(c.a, query_index, m.block_len);
@@ -501,6 +503,7 @@ XM_HD inline double pa_estimate(const PathState& s, int x, int y, const PNode& n
 // update code, and base pairs are classified through the 256-entry tables.  This loop is where gapped reads spend
 // their time.  Returns 0 goal reached (last_x/last_y), 1 over budget (null), 2 failed (w.status set).
 XM_FN int pa_search(WS& w, PathState& S, PaOverflow* ovf, int cap_ovf, int& last_x, int& last_y) {
+  XM_CHECK_MASK(w);
   const int A = S.A, B = S.B, H = S.H, step = S.step, goal_x = S.goal_x, goal_y = S.goal_y, diag = S.diagonal;
   const bool may_extend = S.may_extend != 0, confident = S.an_confident != 0;
   const double ins_start = S.prm.ins_start, ins_ext = S.prm.ins_ext, del_start = S.prm.del_start, del_ext = S.prm.del_ext, unaligned = S.prm.unaligned;
@@ -670,6 +673,7 @@ __device__ __noinline__ int pa_search_remote(WS& w, PathState& S, PaOverflow* ov
 }
 #endif
 XM_FN DAln path_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Params& p, Analysis& an) {  // PathAligner.align :55-293
+  XM_CHECK_MASK(w);
   PhaseClock pc_(&w.st_cyc[3]);
   long long mark = w.scratch_top;
   PathState* sp = (PathState*)w.salloc(sizeof(PathState));
@@ -891,6 +895,7 @@ XM_HD inline DAln straight_alignment(WS& w, const ACtx& c, const Sec& q, const S
 // StraightAligner; the first time the cascade would go deeper the query is handed to the full kernel (Q_HARD).
 template <bool EASY, int STAGE>
 XM_FN DAln straight_align_t(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Params& p, Analysis& an) {  // StraightAligner.align :13-71
+  XM_CHECK_MASK(w);
   an.last_checked = an.predicted;
   w.st_straight++;
   DAln simple;
@@ -996,6 +1001,7 @@ XM_HD inline double max_ext_many_deletions(int n, double total, const Params& p)
 struct PenaltyAnalysisD { double min_possible, max_ins, max_del; int offset_most, num_best; };
 
 XM_FN PenaltyAnalysisD hba_analyze(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Params& p, Analysis& an) {  // analyzePenalty :94-283
+  XM_CHECK_MASK(w);
   PenaltyAnalysisD res; res.min_possible = 0; res.max_ins = 0; res.max_del = 0; res.offset_most = 0; res.num_best = 0;
   PhaseClock pc_(&w.st_cyc[2]);
   MatcherD* matcher = an.matcher;
@@ -1103,6 +1109,7 @@ XM_FN PenaltyAnalysisD hba_analyze(WS& w, const ACtx& c, const Sec& q, const Sec
 
 template <int STAGE>
 XM_FN DAln hba_align(WS& w, const ACtx& c, const Sec& q, const Sec& r_in, const Params& p, Analysis& an_in) {  // HashBlock_Aligner.align :21-81 (tail recursion as a loop)
+  XM_CHECK_MASK(w);
   Sec r = r_in;
   Analysis cur = an_in;       // the analysis object of the current recursion level
   Analysis* anp = &an_in;     // first level mutates the caller's object (hashBlock_matcher assignment)
@@ -1170,6 +1177,7 @@ XM_FN DAln block_try_merge(WS& w, const ACtx& c, const DAln& left, const DAln& r
   return new_aln(p, c, b, n, left.ref_reversed);
 }
 XM_FN DAln block_align(WS& w, const ACtx& c, const Sec& q, const Sec& r, const Params& p, Analysis& an) {  // BlockAligner.align :17-36
+  XM_CHECK_MASK(w);
   double max_interesting = p.max_error_rate * q.length();
   // initialAlignments :39-96
   double max_initial = p.max_error_rate * c.a.len;
@@ -1340,6 +1348,7 @@ XM_INLINE int sa_end_a(const SAStore& s) { return s.blk[s.n_blk - 1].a_start + s
 // QueryMatch_Aligner.alignMatch(SequenceMatch, parameters) :412-462. c describes a and b.
 template <bool EASY>
 XM_FN DAln qma_align_match(WS& w, const ACtx& c, const SM& sm, const Params& p, double per_penalty) {
+  XM_CHECK_MASK(w);
   int a_len = c.a.len, b_len = c.b.len;
   int sb = imax(0, sm.offset), eb = imin(sm.offset + a_len, b_len);
   Sec q; q.start = sb - sm.offset; q.end = eb - sm.offset;
@@ -1463,6 +1472,7 @@ XM_HD inline int qmx_distance(const WS& w, const QMX& m, const SM& a, const SM& 
 // doAlign :94-272; returns stored alignment or nullptr
 template <bool EASY>
 XM_FN QAStore* qma_do_align(WS& w, QMA& A, const QMX& match, double extra_spacing, int q_total_len_for_spacing) {
+  XM_CHECK_MASK(w);
   const Params& P = A.prm;
   int spacing_i = 0;
   if (match.n >= 2) spacing_i = qmx_distance(w, match, match.comp[0], match.comp[1]);
@@ -1653,6 +1663,7 @@ XM_HD inline bool qa_equals(const QAStore& a, const QAStore& b) {  // QueryAlign
 }
 // getBestAlignments :71-83 + withoutDuplicates :86-92 (java.util.HashSet iteration order). Writes indices into out (scratch), returns count.
 XM_FN int qma_best(WS& w, QMA& A, QAStore**& out) {
+  XM_CHECK_MASK(w);
   double max_anywhere = A.q_len * A.prm.max_error_rate;
   double cutoff = A.best_penalty + A.prm.span;
   if (cutoff > max_anywhere) cutoff = max_anywhere;
@@ -1735,6 +1746,7 @@ XM_HD inline bool qa_has_ambiguous(const WS& w, const QAStore& q) {
   return false;
 }
 XM_FN bool quickly_confident(WS& w, const QAStore* best, const QMX& bm) {  // quicklyConfidentInBestAlignment :494-587
+  XM_CHECK_MASK(w);
   if (best == nullptr) return false;
   if (qa_has_indel(*best)) return false;
   int contig = bm.comp[0].contig;
@@ -1772,6 +1784,7 @@ XM_HD inline QMX qmx_from_qm(const WS& w, const QM& q) {
 
 // emits one component's choices into the result arena
 XM_FN void emit_component(WS& w, OutArena& out, OutQuery& oq, int comp_index, QAStore** list, int n) {
+  XM_CHECK_MASK(w);
   oq.n_choice[comp_index] = n;
   if (n == 0) { oq.choice_first[comp_index] = 0; return; }
   long long n_sa = 0, n_blk = 0;

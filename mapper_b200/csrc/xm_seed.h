@@ -710,6 +710,7 @@ XM_HD inline void counting_add_match(WS& w, MatePath& m, const SM& full, const H
   }
 }
 XM_FN void counting_update_matches(WS& w, MatePath& m, const SM& sm, const HB& qb, int qb_num_matches) {  // updateMatches :193-252
+  XM_CHECK_MASK(w);
   int set = sm.rev ? 0 : 1;  // reversed matches live in "forwardMatchCounters" (:197-200)
   int cur = -1, lower = -1, higher = -1;
   XM_NOUNROLL
@@ -753,6 +754,7 @@ XM_HD inline int counters_next_sorted(const MatePath& m, int n, int after) {  //
   return best;
 }
 XM_FN void counting_try_ensure_good(WS& w, MatePath& m) {  // :292-308
+  XM_CHECK_MASK(w);
   if (!m.found_good && m.n_counters <= m.q.len) {
     int after = -1;
     XM_NOUNROLL
@@ -823,6 +825,7 @@ XM_FN SM verify_hit(const WS& w, const MatePath& m, const HB& qb, int64_t pos, b
   return full;
 }
 XM_FN bool counting_step(WS& w, MatePath& m) {  // step :40-179
+  XM_CHECK_MASK(w);
   if (m.done || w.status != 0) return false;
   PhaseClock pc_(&w.st_cyc[0]);
   HB qb;
@@ -951,6 +954,7 @@ XM_HD inline int pc_count_priority(WS& w, const QM& q) {  // countPriority :314-
 }
 // matchWithoutCache :136-246 + assembleQueryMatches :248-265
 XM_FN void pc_match_without_cache(WS& w, const CL* lists, int n_lists) {
+  XM_CHECK_MASK(w);
   w.n_assembled = 0;
   if (n_lists == 1) {
     int cur = -1, ci;
@@ -1021,6 +1025,7 @@ XM_HD inline void pc_match(WS& w, const CL* lists, int n_lists) {  // match :116
   }
 }
 XM_FN void pc_find_good_up_to(WS& w, int k) {  // findGoodPositionsWithPriorityUpTo :52-82
+  XM_CHECK_MASK(w);
   CL lists[2];
   int n = w.query.n_seqs;
   XM_NOUNROLL
@@ -1051,6 +1056,7 @@ XM_FN int pc_optimistic_best(WS& w) {
   return mn;
 }
 XM_FN bool pc_find_partially_good(WS& w) {  // findPartiallyGoodPositions :26-50; false = empty list
+  XM_CHECK_MASK(w);
   if (w.query.n_seqs != 2) return false;
   if (!w.pc_found_nonempty) return false;
   CL lists[2];

@@ -1,0 +1,20 @@
+"""The warp-uniform design is only correct while every warp stays converged: the probe build of the library reports a
+split warp, or a "uniform" value that differs between lanes, as a per-query status.  Round 2 found one such split (lane 0's slot
+search of the in-place escalation) only because a compiler decision stopped masking it; this test keeps the rule checked."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DBG = os.path.join(ROOT, "mapper_b200", "libxmapper_b200_dbg.so")
+pytestmark = pytest.mark.gpu
+
+
+def test_warps_stay_converged():
+    assert os.path.exists(DBG), "probe build missing: run __graft_entry__.build() (make -C mapper_b200/csrc ../libxmapper_b200_dbg.so)"
+    env = dict(os.environ, XM_LIB_PATH=DBG)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_convergence.py")], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok:") == 3, r.stdout
