@@ -17,4 +17,4 @@ def test_warps_stay_converged():
     env = dict(os.environ, XM_LIB_PATH=DBG)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_convergence.py")], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("ok:") == 3, r.stdout
+    assert r.stdout.count("ok:") == 7, r.stdout

@@ -30,15 +30,40 @@ batches = [
     ("1 kbp reads", synth.simulate_reads(contigs, 600, 1000, seed=135, sub_rate=0.01, indel_rate=0.005)),
 ]
 bad = 0
-for name, batch in batches:
+
+
+def run(g, db, params, name, batch):
+    global bad
     for rep in range(2):
         got = g.align_batch(batch)
         vals, cnt = np.unique(got["q_status"], return_counts=True)
         if len(vals) != 1 or vals[0] != 0:
             bad += 1
             print("SPLIT", name, dict(zip(vals.tolist(), cnt.tolist())))
-    want = db.align_batch(synth.DEFAULT_PARAMS, batch, threads=8)
+    want = db.align_batch(params, batch, threads=8)
     parity.assert_same_results(want, got, name)
     print("ok:", name)
+
+
+for name, batch in batches:
+    run(g, db, synth.DEFAULT_PARAMS, name, batch)
 g.close()
+# reads with long ambiguous tails, short reads, and two non-default penalty models (other paths through the cascade)
+many_n = synth.simulate_reads(contigs, 1500, 150, seed=136, sub_rate=0.01, indel_rate=0.002)
+codes = [q[0].copy() for q in synth.unpack_reads(many_n)]
+for i, r in enumerate(codes):
+    if i % 3 == 0:
+        r[-(20 + i % 60):] = 15
+many_n = synth.batch_from_reads(codes)
+short = synth.simulate_reads(contigs, 3000, 40, seed=137, sub_rate=0.02, indel_rate=0.005)
+from test_emu_parity import variant_params  # noqa: E402
+for vname in ("cheap-indels", "loose-error-rate"):
+    p = variant_params(vname)
+    g = capi.XMapper(p, device=0)
+    parity.feed_reference(g, db)
+    g.build_index(150)
+    g.build_duplications(-1, -1, 2, 1000)
+    run(g, db, p, vname + ": reads with N tails", many_n)
+    run(g, db, p, vname + ": 40 bp reads", short)
+    g.close()
 sys.exit(1 if bad else 0)
