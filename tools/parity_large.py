@@ -35,7 +35,7 @@ t1 = time.time()
 g.build_index(150)
 t2 = time.time()
 g.build_duplications(-1, -1, 2, 1000)
-print("index build on the device: %.2f s; duplication table (host): %.2f s" % (t2 - t1, time.time() - t2), flush=True)
+print("index build on the device: %.2f s; duplication table: %.2f s" % (t2 - t1, time.time() - t2), flush=True)
 if a.host_index:
     t1 = time.time()
     g.build_index(150, threads=os.cpu_count())
